@@ -1,0 +1,132 @@
+/*
+ * pixpro_b200.h — C ABI of the B200-native pixel-pretext hot path of PixPro-with-OpticalFlow.
+ *
+ * One shared library (libpixpro_b200.so, built from pixpro-with-opticalflow_b200/csrc/ for
+ * sm_100a).  Plain pointers and sizes only: no torch types cross this boundary.  All
+ * pointers are DEVICE pointers unless the function name ends in `_host`.  Every launch is
+ * asynchronous on `stream` (a cudaStream_t passed as void*; 0 = legacy default stream) and
+ * never synchronises.  Tensors are dense row-major fp32 unless stated; masks are one byte
+ * per element (0/1), bit-compatible with torch.bool.
+ *
+ * Each entry point replaces one function of the reference (paths relative to the
+ * reference repository root); the citation is on the declaration.  Return value: 0 on
+ * success, non-zero PP_ERR_* otherwise (pp_last_error() gives the message for the calling
+ * thread).  There is no CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * div_mode selects how `tensor / python_scalar` sites of the reference round:
+ *   PP_DIV_IEEE (0)  true IEEE division  — what the reference computes on CPU (pinned oracle)
+ *   PP_DIV_RCP  (1)  x * fl32(1/s)       — what torch's CUDA true-divide kernel computes
+ */
+#ifndef PIXPRO_B200_H
+#define PIXPRO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* exported symbol (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define PP_API __attribute__((visibility("default")))
+#else
+#define PP_API
+#endif
+
+#define PP_OK 0
+#define PP_ERR_INVALID 1   /* bad argument (shape / null pointer / unsupported size) */
+#define PP_ERR_CUDA 2      /* CUDA runtime error at launch */
+
+#define PP_DIV_IEEE 0
+#define PP_DIV_RCP 1
+
+#define PP_NORM_COORD 0
+#define PP_NORM_FLOW 1
+#define PP_DENORM_FLOW 2
+
+/* library identification / diagnostics */
+PP_API int pp_abi_version(void);
+PP_API const char* pp_last_error(void);
+/* number of kernels launched by this library in the calling process since load */
+PP_API int64_t pp_launch_count(void);
+/* Per-kernel device timing (tracing aid).  pp_profile_enable(1) clears the records and makes
+ * every launch bracket its kernel with a cudaEvent pair on the launch stream;
+ * pp_profile_num_kernels() synchronises those events and aggregates by kernel name;
+ * pp_profile_get(i, ...) returns name, launch count and total device milliseconds. */
+PP_API int pp_profile_enable(int on);
+PP_API int pp_profile_num_kernels(void);
+PP_API int pp_profile_get(int idx, char* name, int name_cap, int64_t* launches, double* total_ms);
+
+/* ---- a1: upflow8 — contrast/flow/utils/utils.py:87-89 -----------------------------------
+ * in [planes,h,w] -> out [planes,8h,8w] = 8 * bilinear(align_corners=True).               */
+PP_API int pp_upflow8(const float* in, int64_t planes, int h, int w, float* out, void* stream);
+
+/* ---- a2: normalize_coord / normalize_flow / denormalize_flow — contrast/util.py:334-357 -
+ * x,out [B,2,H,W]; kind = PP_NORM_COORD | PP_NORM_FLOW | PP_DENORM_FLOW.                   */
+PP_API int pp_normalize(const float* x, int64_t B, int H, int W, int kind, int div_mode, float* out, void* stream);
+
+/* ---- a3: concat_flow — contrast/util.py:301-330 -----------------------------------------
+ * Chains n dense flow links.  Link i of sample b is the [2,H,W] block at
+ * flows + i*stride_n + b*stride_b (elements), so [n,B,2,H,W] and [B,n,2,H,W] both work.
+ * out [B,2,H,W].  n==1 copies (normalises if is_norm), as the reference does.             */
+PP_API int pp_concat_flow(const float* flows, int n, int64_t B, int H, int W, int64_t stride_n, int64_t stride_b,
+                   int is_norm, int div_mode, float* out, void* stream);
+
+/* ---- a5: forward_backward_consistency — contrast/util.py:253-297 ------------------------
+ * fwd,bwd [B,2,H,W] -> mask u8 [B,H,W]; optional cycle [B,2,H,W] and coords1_norm
+ * [B,2,H,W] (NULL to skip).  is_norm: inputs are already normalised (util.py:258-262).    */
+PP_API int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int W, double alpha_1, double alpha_2,
+                      int is_norm, int div_mode, uint8_t* mask, float* cycle, float* coords1_norm, void* stream);
+
+/* ---- a6 (a1+a3+a5 fused): flow stage of apply_optical_flow — contrast/util.py:175-248 ---
+ * (use_flow_file, not use_flow_frames).  lo_fwd/lo_bwd in the loader layout [B,n,2,h,w]
+ * (contrast/data/dataset.py:485-495).  flow_up: links are x8-upsampled on the fly and never
+ * materialised.  Outputs flow_fwd/flow_bwd [B,2,H,W] (H,W = 8h,8w if flow_up), and, when
+ * use_mask, mask_fwd/mask_bwd u8 [B,H,W].  is_norm restates --flow_cat_norm.              */
+PP_API int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, int h, int w, int flow_up, int use_mask,
+                  double alpha_1, double alpha_2, int is_norm, int div_mode, float* flow_fwd, float* flow_bwd,
+                  uint8_t* mask_fwd, uint8_t* mask_bwd, void* stream);
+
+/* ---- a11: calc_mask_ratio — contrast/util.py:361-366 ------------------------------------
+ * mask u8 [B,H,W] -> ratio [B] = fraction of zero entries.                                */
+PP_API int pp_calc_mask_ratio(const uint8_t* mask, int64_t B, int H, int W, float* ratio, void* stream);
+
+/* ---- a7: add_optical_flow — contrast/models/PixPro.py:46-89 -----------------------------
+ * flow [B,2,Hin,Win]; x_grid,y_grid [B,P] (pixels of the H_orig x W_orig frame); mask u8
+ * [B,Hin,Win] or NULL -> out_x,out_y [B,P]; mask_grid u8 [B,P] (NULL to skip).            */
+PP_API int pp_add_optical_flow(const float* flow, int64_t B, int Hin, int Win, const float* x_grid, const float* y_grid, int P,
+                        int H_orig, int W_orig, const uint8_t* mask, int div_mode, float* out_x, float* out_y,
+                        uint8_t* mask_grid, void* stream);
+
+/* ---- a8: regression_loss forward (+ gradient) — contrast/models/PixPro.py:92-247 --------
+ * q,k [B,C,P] with P=G*G; coord_q,coord_k [B,10]; flow [B,2,Hin,Win] or NULL (no-flow path,
+ * PixPro.py:167-175); mask u8 [B,Hin,Win] or NULL.
+ * Outputs: loss[1]; pos_num[B]; pos_mean[B]; dq [B,C,P] = d loss/d q (the backward of the
+ * reference's autograd graph for upstream gradient 1; NULL to skip); optional debug/parity
+ * outputs pos_mask u8 [B,P,P] and centres [4,B,P] = (warped q x, warped q y, k x, k y).
+ * workspace: pp_regression_loss_workspace(B,G) bytes of device scratch.                   */
+PP_API int64_t pp_regression_loss_workspace(int64_t B, int G);
+PP_API int pp_regression_loss(const float* q, const float* k, int64_t B, int C, int G, const float* coord_q, const float* coord_k,
+                       const float* flow, int Hin, int Win, const uint8_t* mask, int H_orig, int W_orig, double pos_ratio,
+                       int div_mode, float* loss, float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask,
+                       float* centres, void* workspace, void* stream);
+
+/* ---- a9: PixPro.featprop (+ the caller's F.normalize) — contrast/models/PixPro.py:339-363,380
+ * feat,val [B,C,P] (val = value_transform(feat), computed by the caller) -> out [B,C,P].
+ * final_norm: also apply the L2 normalisation of PixPro.py:380.  saved: device scratch of
+ * pp_ppm_saved_bytes(B,C,P) bytes that pp_ppm_bwd reads (kept by the autograd node).       */
+PP_API int64_t pp_ppm_saved_bytes(int64_t B, int C, int P);
+PP_API int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, double gamma, double clamp_value,
+               int final_norm, float* out, void* saved, void* stream);
+/* out = what pp_ppm_fwd returned; g [B,C,P] = dL/d out -> d_feat_sim (gradient reaching feat
+ * through the similarity), d_val [B,C,P] (gradient w.r.t. val; the caller back-propagates it
+ * through value_transform).  workspace: pp_ppm_bwd_workspace(B,C,P) bytes of device scratch. */
+PP_API int64_t pp_ppm_bwd_workspace(int64_t B, int C, int P);
+PP_API int pp_ppm_bwd(const float* feat, const float* val, const float* out, const float* g, const void* saved, int64_t B, int C,
+               int P, double gamma, double clamp_value, int final_norm, float* d_feat_sim, float* d_val, void* workspace,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXPRO_B200_H */

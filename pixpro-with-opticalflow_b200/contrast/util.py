@@ -1,0 +1,151 @@
+"""contrast.util — flow chaining / forward-backward consistency utilities of the reference
+(contrast/util.py:75-366), backed by the sm_100a kernels.  Signatures and return structures
+are the reference's; tensors must live on a CUDA device (the reference hard-codes `.cuda()`
+at util.py:196-197 too)."""
+import torch
+
+from pixpro_b200 import ops as _ops
+
+from .flow import upflow8
+
+
+class AverageMeter(object):
+    """Computes and stores the average and current value (contrast/util.py:10-29)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = self.avg = self.sum = self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+@torch.no_grad()
+def normalize_coord(coords):
+    """contrast/util.py:334-339"""
+    return _ops.normalize_coord(coords)
+
+
+@torch.no_grad()
+def normalize_flow(flow):
+    """contrast/util.py:343-348"""
+    return _ops.normalize_flow(flow)
+
+
+@torch.no_grad()
+def denormalize_flow(flow_norm):
+    """contrast/util.py:352-357"""
+    return _ops.denormalize_flow(flow_norm)
+
+
+@torch.no_grad()
+def calc_mask_ratio(mask):
+    """contrast/util.py:361-366"""
+    if mask is None:
+        return None
+    return _ops.calc_mask_ratio(mask)
+
+
+@torch.no_grad()
+def concat_flow(flows, is_norm=False):
+    """contrast/util.py:301-330: chain `num` flow links [num,nb,2,ht,wd] -> [nb,2,ht,wd]."""
+    return _ops.concat_flow(flows, is_norm=is_norm)
+
+
+def all_concat_flow(flow_fwds, flow_bwds, is_norm=False, use_flow_frames=True):
+    """contrast/util.py:105-126."""
+    if not use_flow_frames:
+        return concat_flow(flow_fwds, is_norm), concat_flow(flow_bwds, is_norm)
+    num_flow = flow_bwds.shape[0]
+    fwd_list, bwd_list = [], []
+    for span in range(1, num_flow + 1):  # every contiguous sub-chain, shortest first
+        for fwd_s in range(num_flow - span + 1):
+            bwd_e = num_flow - fwd_s
+            fwd_list.append(concat_flow(flow_fwds[fwd_s:fwd_s + span], is_norm))
+            bwd_list.append(concat_flow(flow_bwds[bwd_e - span:bwd_e], is_norm))
+    return torch.stack(fwd_list), torch.stack(bwd_list)
+
+
+@torch.no_grad()
+def forward_backward_consistency(flow_fwd, flow_bwd, coords0=None, alpha_1=0.01, alpha_2=0.5, is_norm=False):
+    """contrast/util.py:253-297 -> (coords0_norm, coords1_norm, [mask, flow_cycle])."""
+    if alpha_1 is None or alpha_2 is None:
+        return flow_fwd.clone(), flow_bwd.clone(), [None, None]
+    coords1_norm, mask, cycle = _ops.forward_backward_consistency(flow_fwd, flow_bwd, alpha_1, alpha_2, is_norm=is_norm)
+    if coords0 is None:
+        nb, _, ht, wd = flow_fwd.shape
+        ys, xs = torch.meshgrid(torch.arange(ht, device=flow_fwd.device), torch.arange(wd, device=flow_fwd.device),
+                                indexing='ij')
+        coords0 = torch.stack([xs, ys], dim=0).float().repeat(nb, 1, 1, 1)
+        coords0_norm = normalize_coord(coords0)
+    else:
+        # the reference leaves coords0_norm undefined on this branch (util.py:267-271, a NameError);
+        # the only caller never passes coords0
+        raise NotImplementedError("forward_backward_consistency: explicit coords0 is not supported by the reference either")
+    return coords0_norm, coords1_norm, [mask, cycle]
+
+
+@torch.no_grad()
+def apply_optical_flow(data, flow_model, args):
+    """contrast/util.py:175-248.  data follows the loader layout (contrast/data/dataset.py:503):
+    data[5] = [target, flow_fwd [B,n,2,h,w], flow_bwd [B,n,2,h,w]], data[6] = [size [B,2], num_img [B,1], ...].
+    Returns ([flow_fwd, size, mask_fwd], [flow_bwd, size, mask_bwd])."""
+    orig_imgs_tmp = data[6]
+    size, num_img = orig_imgs_tmp[0][0], int(orig_imgs_tmp[1][0].item())
+    is_mask_flow = args.alpha1 is not None and args.alpha2 is not None
+    is_use_flow_frames = args.use_flow_frames and num_img > 2
+    if not args.use_flow_file:
+        raise NotImplementedError("on-the-fly RAFT estimation is out of scope (SURVEY.md §2.1 row 6): "
+                                  "precompute flows and pass --use_flow_file")
+    _, flow_fwds, flow_bwds = data[5]
+    debug = bool(getattr(args, 'debug', False))
+    if not is_use_flow_frames and not debug:
+        # fused path: x8 up-sampling, chaining and both FB masks in two launches, nothing else
+        # materialised (util.py:185-244 in one pass)
+        flow_fwd, flow_bwd, mask_fwd, mask_bwd = _ops.flow_stage(
+            flow_fwds.cuda(), flow_bwds.cuda(), flow_up=args.flow_up,
+            alpha_1=args.alpha1 if is_mask_flow else None, alpha_2=args.alpha2 if is_mask_flow else None,
+            is_norm=args.flow_cat_norm)
+        return [flow_fwd, size, mask_fwd], [flow_bwd, size, mask_bwd]
+
+    # general path (use_flow_frames / debug), composed from the same kernels step by step
+    flow_fwds = flow_fwds.cuda().permute(1, 0, 2, 3, 4)
+    flow_bwds = flow_bwds.cuda().permute(1, 0, 2, 3, 4)
+    if args.flow_up:
+        num, nb, c, h, w = flow_fwds.shape
+        flow_fwds = upflow8(flow_fwds.reshape(-1, c, h, w)).reshape(num, nb, c, 8 * h, 8 * w)
+        flow_bwds = upflow8(flow_bwds.reshape(-1, c, h, w)).reshape(num, nb, c, 8 * h, 8 * w)
+    flow_fwd, flow_bwd = all_concat_flow(flow_fwds, flow_bwds, is_norm=args.flow_cat_norm,
+                                         use_flow_frames=is_use_flow_frames)
+    if flow_fwd.ndim == 4:
+        flow_fwd, flow_bwd = flow_fwd.unsqueeze(0), flow_bwd.unsqueeze(0)
+    mask_fwd = mask_bwd = None
+    if is_mask_flow:
+        mf, mb, cf, cb = [], [], [], []
+        for l_fwd, l_bwd in zip(flow_fwd, flow_bwd):
+            _, _, (m1, c1) = forward_backward_consistency(l_fwd, l_bwd, alpha_1=args.alpha1, alpha_2=args.alpha2,
+                                                          is_norm=args.flow_cat_norm)
+            _, _, (m2, c2) = forward_backward_consistency(l_bwd, l_fwd, alpha_1=args.alpha1, alpha_2=args.alpha2,
+                                                          is_norm=args.flow_cat_norm)
+            mf.append(m1), mb.append(m2), cf.append(c1), cb.append(c2)
+        mask_fwd, mask_bwd = torch.stack(mf), torch.stack(mb)
+        if debug:
+            mask_fwd, mask_bwd = [mask_fwd, torch.stack(cf)], [mask_bwd, torch.stack(cb)]
+    if args.flow_cat_norm:
+        flow_fwd = torch.stack([denormalize_flow(f) for f in flow_fwd])
+        flow_bwd = torch.stack([denormalize_flow(f) for f in flow_bwd])
+    if not is_use_flow_frames:
+        flow_fwd, flow_bwd = flow_fwd[-1], flow_bwd[-1]
+        if mask_fwd is None or mask_bwd is None:
+            if debug:
+                mask_fwd, mask_bwd = [None, None], [None, None]
+        elif isinstance(mask_fwd, list):
+            mask_fwd, mask_bwd = [m[-1] for m in mask_fwd], [m[-1] for m in mask_bwd]
+        else:
+            mask_fwd, mask_bwd = mask_fwd[-1], mask_bwd[-1]
+    return [flow_fwd, size, mask_fwd], [flow_bwd, size, mask_bwd]

@@ -1,0 +1,139 @@
+// pp_common.cuh — shared device helpers for the sm_100a pixel-pretext kernels.
+//
+// Arithmetic that decides a boolean downstream (coordinates, masks) is written with the
+// round-to-nearest intrinsics (__fmul_rn, __fadd_rn, ...) so that ptxas can never contract
+// two separately rounded reference ops into one FMA; FMAs appear only where the reference's
+// own ATen kernels fuse (grid_sample tap accumulation, bilinear up-sampling).  See
+// oracle/pixpro_oracle.c for the op-by-op restatement these helpers mirror.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pixpro_b200.h"
+
+namespace pp {
+
+// ---- error plumbing --------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch(int n = 1);
+
+// Brackets one kernel launch with a cudaEvent pair when pp_profile_enable(1) is active
+// (no-op otherwise).  Usage:  { ProfScope ps("name", st); kernel<<<...,st>>>(...); }
+class ProfScope {
+  public:
+    ProfScope(const char* name, cudaStream_t st);
+    ~ProfScope();
+
+  private:
+    const char* name_;
+    cudaStream_t st_;
+    cudaEvent_t e1_;
+};
+
+// One kernel launch: optional event bracket + launch accounting.
+#define PP_LAUNCH(name, st, ...)               \
+    do {                                       \
+        ::pp::ProfScope _pp_ps(name, st);      \
+        __VA_ARGS__;                           \
+        ::pp::count_launch();                  \
+    } while (0)
+
+#define PP_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::pp::set_error(__VA_ARGS__);     \
+            return PP_ERR_INVALID;            \
+        }                                     \
+    } while (0)
+
+// ---- exactly-rounded scalar ops ----------------------------------------------------------
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// tensor / python_scalar of the reference.  IEEE mode = correctly rounded quotient (torch
+// CPU); RCP mode = x * fl32(1/s) (torch CUDA's true-divide with a CPU scalar).
+struct ScalarDiv {
+    float s;    // divisor
+    float inv;  // fl32(1/s)
+    int rcp;    // div_mode
+    __device__ __forceinline__ float operator()(float x) const {
+        return rcp ? __fmul_rn(x, inv) : __fdiv_rn(x, s);
+    }
+};
+static inline ScalarDiv make_div(float s, int div_mode) {
+    ScalarDiv d;
+    d.s = s;
+    d.inv = 1.0f / s;
+    d.rcp = div_mode;
+    return d;
+}
+
+// util.py:334-339  2*c/(size-1) - 1
+__device__ __forceinline__ float norm_coord(float c, const ScalarDiv& d) { return sub(d(mul(2.0f, c)), 1.0f); }
+// util.py:343-348  2*f/(size-1)
+__device__ __forceinline__ float norm_flow(float f, const ScalarDiv& d) { return d(mul(2.0f, f)); }
+// util.py:352-357  (f*(size-1))/2
+__device__ __forceinline__ float denorm_flow(float f, float size_m1) { return mul(mul(f, size_m1), 0.5f); }
+
+// ---- ATen grid_sampler_2d (bilinear, zeros padding, align_corners=True) -------------------
+// Unnormalise + corner weights.  half_w = (W-1)/2 exactly representable for W < 2^24.
+struct Taps {
+    int x0, y0;          // north-west corner
+    float nw, ne, sw, se;
+    bool inx0, inx1, iny0, iny1;
+};
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int W, int H, float half_w, float half_h) {
+    Taps t;
+    float ix = mul(add(gx, 1.0f), half_w);
+    float iy = mul(add(gy, 1.0f), half_h);
+    float xw = floorf(ix), yn = floorf(iy);
+    float xe = add(xw, 1.0f), ys = add(yn, 1.0f);
+    float w = sub(ix, xw), e = sub(xe, ix), n = sub(iy, yn), s = sub(ys, iy);
+    t.nw = mul(s, e);
+    t.ne = mul(s, w);
+    t.sw = mul(n, e);
+    t.se = mul(n, w);
+    // float comparisons so that NaN / huge coordinates select no tap, like ATen's masks
+    t.inx0 = (xw > -1.0f) && (xw < (float)W);
+    t.inx1 = (xe > -1.0f) && (xe < (float)W);
+    t.iny0 = (yn > -1.0f) && (yn < (float)H);
+    t.iny1 = (ys > -1.0f) && (ys < (float)H);
+    t.x0 = t.inx0 ? (int)xw : ((t.inx1) ? -1 : 0);
+    t.y0 = t.iny0 ? (int)yn : ((t.iny1) ? -1 : 0);
+    return t;
+}
+// out = fma(v_se,se, fma(v_sw,sw, fma(v_ne,ne, v_nw*nw)))
+__device__ __forceinline__ float combine(const Taps& t, float vnw, float vne, float vsw, float vse) {
+    return fma_(vse, t.se, fma_(vsw, t.sw, fma_(vne, t.ne, mul(vnw, t.nw))));
+}
+
+// ---- ATen upsample_bilinear2d (align_corners=True) axis taps ------------------------------
+struct AxisTap {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ AxisTap axis_tap(int d, float scale, int in) {
+    AxisTap t;
+    float s = mul(scale, (float)d);
+    int i0 = (int)s;  // s >= 0: trunc == floor
+    i0 = min(i0, in - 1);
+    float l1 = sub(s, (float)i0);
+    l1 = fminf(fmaxf(l1, 0.0f), 1.0f);
+    t.i0 = i0;
+    t.i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    t.l1 = l1;
+    t.l0 = sub(1.0f, l1);
+    return t;
+}
+// val = fma(l0y, fma(l0x,a, l1x*b), l1y*fma(l0x,c, l1x*d))
+__device__ __forceinline__ float up_combine(const AxisTap& ty, const AxisTap& tx, float a, float b, float c, float d) {
+    float top = fma_(tx.l0, a, mul(tx.l1, b));
+    float bot = fma_(tx.l0, c, mul(tx.l1, d));
+    return fma_(ty.l0, top, mul(ty.l1, bot));
+}
+static inline float up_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.0f; }
+
+}  // namespace pp

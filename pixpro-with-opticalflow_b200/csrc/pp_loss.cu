@@ -1,0 +1,359 @@
+// pp_loss.cu — flow-guided correspondence, positive mask and masked cosine regression loss
+// (sm_100a), forward and backward in one pass.
+//
+// Reference functions restated (paths relative to the reference repo):
+//   add_optical_flow   contrast/models/PixPro.py:46-89
+//   regression_loss    contrast/models/PixPro.py:92-247
+//
+// Formulation.  The reference materialises logit = qᵀk [B,P,P], multiplies by the positive
+// mask and reduces.  Here   loss_b = Σ_i q_i · m_i / den_b   with   m_i = Σ_j pos_ij k_j ,
+// and  d loss / d q_i = -2/(B den_b) m_i , so ONE masked contraction M = K·posᵀ gives both
+// the loss and its gradient; the [B,P,P] logits and mask never touch HBM.  The mask is
+// recomputed per tile from the 5·P per-sample centre/mask scalars (bit-exact arithmetic,
+// see pp_common.cuh).
+#include <math.h>
+
+#include "pp_common.cuh"
+
+namespace pp {
+
+// ---- a7: warp one grid point through the flow ----------------------------------------------
+struct WarpArgs {
+    int Hin, Win;
+    float half_w, half_h;       // (Win-1)/2, (Hin-1)/2
+    ScalarDiv dwo, dho;         // / (W_orig-1), / (H_orig-1)
+    ScalarDiv drw, drh;         // / ratio_w, / ratio_h
+    float rw, rh;               // ratio_w = Win/W_orig, ratio_h = Hin/H_orig  (fp32 of the python double)
+    int diff;                   // flow resolution != original resolution
+};
+
+__device__ __forceinline__ void warp_point(const float* __restrict__ flow, const uint8_t* __restrict__ mask, const WarpArgs& a,
+                                           float xg, float yg, float& ox, float& oy, bool& mg) {
+    // PixPro.py:61-62   2 * (x / (W_orig-1)) - 1
+    float gx = sub(mul(2.0f, a.dwo(xg)), 1.0f);
+    float gy = sub(mul(2.0f, a.dho(yg)), 1.0f);
+    int64_t HW = (int64_t)a.Hin * a.Win;
+    Taps t = make_taps(gx, gy, a.Win, a.Hin, a.half_w, a.half_h);
+    float vx[4], vy[4];
+    const bool in[4] = {t.inx0 && t.iny0, t.inx1 && t.iny0, t.inx0 && t.iny1, t.inx1 && t.iny1};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int64_t o = (int64_t)(t.y0 + (c >> 1)) * a.Win + (t.x0 + (c & 1));
+        vx[c] = in[c] ? __ldg(flow + o) : 0.0f;
+        vy[c] = in[c] ? __ldg(flow + HW + o) : 0.0f;
+    }
+    float fgx = combine(t, vx[0], vx[1], vx[2], vx[3]);  // PixPro.py:64
+    float fgy = combine(t, vy[0], vy[1], vy[2], vy[3]);
+    mg = true;
+    if (mask) {  // PixPro.py:65-70 nearest lookup (nearbyint, zeros padding)
+        float ix = mul(add(gx, 1.0f), a.half_w), iy = mul(add(gy, 1.0f), a.half_h);
+        float xr = rintf(ix), yr = rintf(iy);
+        bool inb = (xr > -1.0f) && (xr < (float)a.Win) && (yr > -1.0f) && (yr < (float)a.Hin);
+        mg = inb ? (mask[(int64_t)yr * a.Win + (int64_t)xr] != 0) : false;
+    }
+    if (a.diff) {  // PixPro.py:76-80
+        ox = a.drw(add(mul(xg, a.rw), fgx));
+        oy = a.drh(add(mul(yg, a.rh), fgy));
+    } else {  // PixPro.py:82-83
+        ox = add(xg, fgx);
+        oy = add(yg, fgy);
+    }
+}
+
+static WarpArgs make_warp_args(int Hin, int Win, int H_orig, int W_orig, int div_mode) {
+    WarpArgs a;
+    a.Hin = Hin; a.Win = Win;
+    a.half_w = (float)(Win - 1) / 2.0f; a.half_h = (float)(Hin - 1) / 2.0f;
+    a.dwo = make_div((float)(W_orig - 1), div_mode); a.dho = make_div((float)(H_orig - 1), div_mode);
+    a.rw = (float)((double)Win / (double)W_orig); a.rh = (float)((double)Hin / (double)H_orig);
+    a.drw = make_div(a.rw, div_mode); a.drh = make_div(a.rh, div_mode);
+    a.diff = (Hin != H_orig) || (Win != W_orig);
+    return a;
+}
+
+__global__ void __launch_bounds__(128) add_flow_kernel(const float* __restrict__ flow, const uint8_t* __restrict__ mask,
+                                                        const float* __restrict__ xg, const float* __restrict__ yg,
+                                                        int64_t total, int P, WarpArgs a, float* __restrict__ out_x,
+                                                        float* __restrict__ out_y, uint8_t* __restrict__ mask_grid) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t b = i / P;
+    int64_t HW = (int64_t)a.Hin * a.Win;
+    float ox, oy;
+    bool mg;
+    warp_point(flow + b * 2 * HW, mask ? mask + b * HW : nullptr, a, xg[i], yg[i], ox, oy, mg);
+    out_x[i] = ox;
+    out_y[i] = oy;
+    if (mask_grid) mask_grid[i] = mg ? 1 : 0;
+}
+
+// ---- a8 stage 1: centres, flow warp, positive count ----------------------------------------
+// Workspace (floats): [0] cqx[B,P] [1] cqy [2] ckx [3] cky [4] mg (0/1) ; then md[B], den[B],
+// partial[B,ntile].
+struct LossWs {
+    float *cqx, *cqy, *ckx, *cky, *mg, *md, *den, *partial;
+};
+static int loss_ntile(int P) { return (P + 6) / 7; }
+static LossWs carve_ws(void* ws, int64_t B, int P) {
+    LossWs w;
+    float* f = (float*)ws;
+    w.cqx = f; f += B * P;
+    w.cqy = f; f += B * P;
+    w.ckx = f; f += B * P;
+    w.cky = f; f += B * P;
+    w.mg = f; f += B * P;
+    w.md = f; f += B;
+    w.den = f; f += B;
+    w.partial = f;
+    return w;
+}
+
+__device__ __forceinline__ bool pair_pos(float qx, float qy, float kx, float ky, float md, float pr) {
+    float dx = sub(qx, kx), dy = sub(qy, ky);                       // PixPro.py:217
+    float d = __fdiv_rn(__fsqrt_rn(add(mul(dx, dx), mul(dy, dy))), md);  // :217-218
+    return d < pr;                                                  // :219
+}
+
+struct PrepArgs {
+    const float *coord_q, *coord_k, *flow;
+    const uint8_t* mask;
+    int G, P;
+    float wo, ho;       // W_orig-1, H_orig-1
+    ScalarDiv dG;       // / G
+    float pr;
+    WarpArgs warp;
+    LossWs ws;
+    float *pos_num, *pos_mean, *centres;
+    uint8_t* pos_mask;
+    int64_t B;
+};
+
+__global__ void __launch_bounds__(256) loss_prep_kernel(PrepArgs a) {
+    extern __shared__ float sm[];
+    const int P = a.P, G = a.G;
+    float* qx = sm;
+    float* qy = qx + P;
+    float* kx = qy + P;
+    float* ky = kx + P;
+    float* mgs = ky + P;
+    __shared__ float s_md;
+    __shared__ int s_cnt[8];
+    const int64_t b = blockIdx.x;
+    const float* cq = a.coord_q + b * 10;
+    const float* ck = a.coord_k + b * 10;
+    // PixPro.py:140-143 bin sizes
+    float qbw = a.dG(sub(cq[2], cq[0])), qbh = a.dG(sub(cq[3], cq[1]));
+    float kbw = a.dG(sub(ck[2], ck[0])), kbh = a.dG(sub(ck[3], ck[1]));
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        int x = p % G, y = p / G;
+        // :168-175 / :192-199   ((i+0.5)*bin + start) * (size-1)
+        float fx = add((float)x, 0.5f), fy = add((float)y, 0.5f);
+        float vqx = mul(add(mul(fx, qbw), cq[0]), a.wo);
+        float vqy = mul(add(mul(fy, qbh), cq[1]), a.ho);
+        float vkx = mul(add(mul(fx, kbw), ck[0]), a.wo);
+        float vky = mul(add(mul(fy, kbh), ck[1]), a.ho);
+        bool mg = true;
+        if (a.flow) {  // :200
+            int64_t HW = (int64_t)a.warp.Hin * a.warp.Win;
+            float ox, oy;
+            warp_point(a.flow + b * 2 * HW, a.mask ? a.mask + b * HW : nullptr, a.warp, vqx, vqy, ox, oy, mg);
+            vqx = ox;
+            vqy = oy;
+        }
+        qx[p] = vqx; qy[p] = vqy; kx[p] = vkx; ky[p] = vky; mgs[p] = mg ? 1.0f : 0.0f;
+        a.ws.cqx[b * P + p] = vqx; a.ws.cqy[b * P + p] = vqy;
+        a.ws.ckx[b * P + p] = vkx; a.ws.cky[b * P + p] = vky;
+        a.ws.mg[b * P + p] = mg ? 1.0f : 0.0f;
+        if (a.centres) {
+            int64_t BP = a.B * P;
+            a.centres[0 * BP + b * P + p] = vqx; a.centres[1 * BP + b * P + p] = vqy;
+            a.centres[2 * BP + b * P + p] = vkx; a.centres[3 * BP + b * P + p] = vky;
+        }
+    }
+    if (threadIdx.x == 0) {  // :155-157
+        float qdw = mul(qbw, a.wo), qdh = mul(qbh, a.ho), kdw = mul(kbw, a.wo), kdh = mul(kbh, a.ho);
+        float qd = __fsqrt_rn(add(mul(qdw, qdw), mul(qdh, qdh)));
+        float kd = __fsqrt_rn(add(mul(kdw, kdw), mul(kdh, kdh)));
+        s_md = fmaxf(qd, kd);
+    }
+    __syncthreads();
+    const float md = s_md;
+    int cnt = 0;
+    for (int e = threadIdx.x; e < P * P; e += blockDim.x) {
+        int i = e / P, j = e - i * P;
+        bool pos = pair_pos(qx[i], qy[i], kx[j], ky[j], md, a.pr) && (mgs[i] != 0.0f);  // :219-222
+        cnt += pos;
+        if (a.pos_mask) a.pos_mask[(b * P + i) * (int64_t)P + j] = pos ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_cnt[w];
+        float fc = (float)tot;
+        a.ws.md[b] = md;
+        a.ws.den[b] = add(fc, 1e-6f);  // :241 fp32 denominator
+        if (a.pos_num) a.pos_num[b] = fc;
+        if (a.pos_mean) a.pos_mean[b] = __fdiv_rn(fc, (float)(P * P));
+    }
+}
+
+// ---- a8 stage 2: masked contraction M = K posᵀ, loss partials and dq -----------------------
+// grid (ntile, B); block 256.  Tile = TI query cells.  k is staged through shared memory in
+// [256 channels][JT] chunks; thread c owns channel c and TI accumulators.
+constexpr int TI = 7;
+constexpr int JT = 32;
+
+struct MainArgs {
+    const float *q, *k;
+    float* dq;
+    LossWs ws;
+    int C, P, ntile;
+    float pr, scale;  // scale = -2/B
+};
+
+__global__ void __launch_bounds__(256) loss_main_kernel(MainArgs a) {
+    __shared__ float ks[256][JT + 1];
+    __shared__ uint8_t pos[TI][1024];  // P <= 1024
+    __shared__ float red[8];
+    const int P = a.P, C = a.C;
+    const int64_t b = blockIdx.y;
+    const int i0 = blockIdx.x * TI;
+    const int ni = min(TI, P - i0);
+    const float md = a.ws.md[b];
+    const float* kx = a.ws.ckx + b * P;
+    const float* ky = a.ws.cky + b * P;
+    for (int e = threadIdx.x; e < TI * P; e += blockDim.x) {
+        int t = e / P, j = e - t * P;
+        bool p = false;
+        if (t < ni) {
+            int i = i0 + t;
+            p = pair_pos(a.ws.cqx[b * P + i], a.ws.cqy[b * P + i], kx[j], ky[j], md, a.pr) && (a.ws.mg[b * P + i] != 0.0f);
+        }
+        pos[t][j] = p;
+    }
+    const float inv_den = a.scale / a.ws.den[b];  // -2/(B den)
+    float lsum = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += 256) {
+        const int c = c0 + threadIdx.x;
+        float acc[TI];
+#pragma unroll
+        for (int t = 0; t < TI; t++) acc[t] = 0.0f;
+        for (int j0 = 0; j0 < P; j0 += JT) {
+            __syncthreads();  // pos ready / previous chunk consumed
+            const int nj = min(JT, P - j0);
+            for (int e = threadIdx.x; e < 256 * JT; e += blockDim.x) {
+                int cc = e / JT, jj = e - cc * JT;
+                float v = 0.0f;
+                if (c0 + cc < C && jj < nj) v = __ldg(a.k + (b * C + c0 + cc) * (int64_t)P + j0 + jj);
+                ks[cc][jj] = v;
+            }
+            __syncthreads();
+            for (int jj = 0; jj < nj; jj++) {
+                float kv = ks[threadIdx.x][jj];
+#pragma unroll
+                for (int t = 0; t < TI; t++) acc[t] += pos[t][j0 + jj] ? kv : 0.0f;
+            }
+        }
+        if (c < C) {
+            const float* qrow = a.q + (b * C + c) * (int64_t)P + i0;
+            float* drow = a.dq ? a.dq + (b * C + c) * (int64_t)P + i0 : nullptr;
+#pragma unroll
+            for (int t = 0; t < TI; t++) {
+                if (t < ni) {
+                    lsum = fmaf(__ldg(qrow + t), acc[t], lsum);
+                    if (drow) drow[t] = acc[t] * inv_den;
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; w++) s += red[w];
+        a.ws.partial[b * a.ntile + blockIdx.x] = s;
+    }
+}
+
+// ---- a8 stage 3: deterministic final reduction: loss = -2 mean_b( Σ partial_b / den_b ) ----
+__global__ void __launch_bounds__(256) loss_final_kernel(LossWs ws, int64_t B, int ntile, float* __restrict__ loss) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+        float sb = 0.0f;
+        for (int t = 0; t < ntile; t++) sb += ws.partial[b * ntile + t];
+        s += (double)(sb / ws.den[b]);  // PixPro.py:241
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(-2.0 * red[0] / (double)B);  // :247
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_add_optical_flow(const float* flow, int64_t B, int Hin, int Win, const float* x_grid, const float* y_grid, int P,
+                        int H_orig, int W_orig, const uint8_t* mask, int div_mode, float* out_x, float* out_y,
+                        uint8_t* mask_grid, void* stream) {
+    PP_REQUIRE(flow && x_grid && y_grid && out_x && out_y, "pp_add_optical_flow: null pointer");
+    PP_REQUIRE(B >= 0 && Hin > 1 && Win > 1 && P > 0 && H_orig > 1 && W_orig > 1, "pp_add_optical_flow: bad shape");
+    if (B == 0) return PP_OK;
+    int64_t total = B * P;
+    cudaStream_t st = (cudaStream_t)stream;
+    PP_LAUNCH("add_flow", st,
+              add_flow_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+                  flow, mask, x_grid, y_grid, total, P, make_warp_args(Hin, Win, H_orig, W_orig, div_mode), out_x, out_y,
+                  mask_grid));
+    return check_launch("add_flow_kernel");
+}
+
+int64_t pp_regression_loss_workspace(int64_t B, int G) {
+    int64_t P = (int64_t)G * G;
+    return (5 * B * P + 2 * B + B * loss_ntile((int)P)) * (int64_t)sizeof(float);
+}
+
+int pp_regression_loss(const float* q, const float* k, int64_t B, int C, int G, const float* coord_q, const float* coord_k,
+                       const float* flow, int Hin, int Win, const uint8_t* mask, int H_orig, int W_orig, double pos_ratio,
+                       int div_mode, float* loss, float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask,
+                       float* centres, void* workspace, void* stream) {
+    PP_REQUIRE(q && k && coord_q && coord_k && loss && workspace, "pp_regression_loss: null pointer");
+    PP_REQUIRE(B > 0 && B <= 65535 && C > 0 && G > 0, "pp_regression_loss: bad shape B=%lld C=%d G=%d", (long long)B, C, G);
+    PP_REQUIRE(G * G <= 1024, "pp_regression_loss: grid %dx%d exceeds 1024 cells", G, G);
+    PP_REQUIRE(H_orig > 1 && W_orig > 1, "pp_regression_loss: bad original size %dx%d", H_orig, W_orig);
+    PP_REQUIRE(!flow || (Hin > 1 && Win > 1), "pp_regression_loss: bad flow size %dx%d", Hin, Win);
+    PP_REQUIRE(!mask || flow, "pp_regression_loss: mask without flow");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = G * G;
+    PrepArgs pa;
+    pa.coord_q = coord_q; pa.coord_k = coord_k; pa.flow = flow; pa.mask = mask;
+    pa.G = G; pa.P = P;
+    pa.wo = (float)(W_orig - 1); pa.ho = (float)(H_orig - 1);
+    pa.dG = make_div((float)G, div_mode);
+    pa.pr = (float)pos_ratio;
+    pa.warp = make_warp_args(flow ? Hin : 2, flow ? Win : 2, H_orig, W_orig, div_mode);
+    pa.ws = carve_ws(workspace, B, P);
+    pa.pos_num = pos_num; pa.pos_mean = pos_mean; pa.centres = centres; pa.pos_mask = pos_mask; pa.B = B;
+    PP_LAUNCH("loss_prep", st, loss_prep_kernel<<<(unsigned)B, 256, 5 * P * sizeof(float), st>>>(pa));
+    int rc = check_launch("loss_prep_kernel");
+    if (rc) return rc;
+    MainArgs ma;
+    ma.q = q; ma.k = k; ma.dq = dq; ma.ws = pa.ws; ma.C = C; ma.P = P; ma.ntile = loss_ntile(P);
+    ma.pr = pa.pr; ma.scale = (float)(-2.0 / (double)B);
+    PP_LAUNCH("loss_main", st, loss_main_kernel<<<dim3(ma.ntile, (unsigned)B), 256, 0, st>>>(ma));
+    rc = check_launch("loss_main_kernel");
+    if (rc) return rc;
+    PP_LAUNCH("loss_final", st, loss_final_kernel<<<1, 256, 0, st>>>(pa.ws, B, ma.ntile, loss));
+    return check_launch("loss_final_kernel");
+}
+
+}  // extern "C"

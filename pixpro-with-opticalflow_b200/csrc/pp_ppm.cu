@@ -1,0 +1,346 @@
+// pp_ppm.cu — Pixel Propagation Module forward/backward (sm_100a), generic-size fp32 path.
+//
+// Reference restated: PixPro.featprop, contrast/models/PixPro.py:339-363, and the caller's
+// F.normalize (:380,385).  For one sample with x = feat [C,P], v = value_transform(feat) [C,P]:
+//     x̂ = x / max(‖x‖_c, 1e-12),  v̂ likewise
+//     S = x̂ᵀ x̂ [P,P];  A = (clamp(S, min=cv) [+1e-6 if γ<1])^γ
+//     Y = v̂ Aᵀ [C,P];  out = Y / max(‖Y‖_c, 1e-12)        (if final_norm)
+// Backward (validated against torch autograd through the oracle):
+//     gy = (g − ŷ (g·ŷ)) / ‖Y‖ ;  gA = gyᵀ v̂ ;  gv̂ = gy A ;  gS = gA ∘ A'(S) [S ≥ cv]
+//     gx̂ = x̂ (gS + gSᵀ) ;  d_feat_sim = normbwd(x, gx̂) ;  d_val = normbwd(v, gv̂)
+//
+// This file is the size-generic fp32 CUDA-core path: a batched 64x64x16 register-tiled GEMM
+// whose operand loads and epilogue are functors, so the normalisations, relu^γ, its
+// derivative and the (gS+gSᵀ) symmetrisation are all fused into the contractions and no
+// normalised copy of x or v is ever written.  Column norms use one warp-shuffle reduction
+// kernel.  saved = [nx | nv | ny | S] per batch (3·B·P + B·P·P floats).
+#include <math.h>
+
+#include "pp_common.cuh"
+
+namespace pp {
+
+constexpr float kNormEps = 1e-12f;
+
+// relu^γ and its derivative (PixPro.py:355-358)
+struct Act {
+    float gamma, cv;
+    int mode;  // 0: γ==1, 1: γ==2, 2: general
+    __device__ __forceinline__ float f(float s) const {
+        float a = fmaxf(s, cv);
+        if (gamma < 1.0f) a += 1e-6f;
+        return mode == 0 ? a : (mode == 1 ? a * a : powf(a, gamma));
+    }
+    __device__ __forceinline__ float df(float s) const {  // d f / d s; torch clamp passes grad where s >= min
+        if (s < cv) return 0.0f;
+        float a = s;
+        if (gamma < 1.0f) a += 1e-6f;
+        return mode == 0 ? 1.0f : (mode == 1 ? 2.0f * a : gamma * powf(a, gamma - 1.0f));
+    }
+};
+static Act make_act(double gamma, double cv) {
+    Act a;
+    a.gamma = (float)gamma;
+    a.cv = (float)cv;
+    a.mode = gamma == 1.0 ? 0 : (gamma == 2.0 ? 1 : 2);
+    return a;
+}
+
+// ---- column norms over C: n[b,i] = max(sqrt(Σ_c u[b,c,i]^2), eps) --------------------------
+// grid (ceil(P/32), B), block (32, 8): threadIdx.x = column, threadIdx.y strides over C.
+__global__ void __launch_bounds__(256) colnorm_kernel(const float* __restrict__ u, int C, int P, float* __restrict__ nrm) {
+    __shared__ float red[8][33];
+    int i = blockIdx.x * 32 + threadIdx.x;
+    int64_t b = blockIdx.y;
+    float s = 0.0f;
+    if (i < P)
+        for (int c = threadIdx.y; c < C; c += 8) {
+            float v = __ldg(u + (b * C + c) * (int64_t)P + i);
+            s = fmaf(v, v, s);
+        }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < P) {
+        float t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t += red[r][threadIdx.x];
+        nrm[b * P + i] = fmaxf(sqrtf(t), kNormEps);
+    }
+}
+
+// out[b,c,i] = y[b,c,i] / n[b,i]
+__global__ void __launch_bounds__(256) coldiv_kernel(const float* y, const float* __restrict__ nrm, int C, int P, int64_t total,
+                                                      float* out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    int i = (int)(e % P);
+    int64_t b = e / ((int64_t)C * P);
+    out[e] = y[e] / nrm[b * P + i];
+}
+
+// normalisation backward: out = (g − û (g·û)) / n, û = u / n_u  (û given by u and its norm,
+// or directly when u is already normalised: pass nu = nullptr).
+// grid (ceil(P/32), B), block (32,8).
+__global__ void __launch_bounds__(256) normbwd_kernel(const float* __restrict__ g, const float* __restrict__ u,
+                                                       const float* __restrict__ nu, const float* __restrict__ ndiv, int C,
+                                                       int P, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    __shared__ float dot[32];
+    int i = blockIdx.x * 32 + threadIdx.x;
+    int64_t b = blockIdx.y;
+    float rn = 1.0f, rdiv = 1.0f;
+    if (i < P) {
+        rn = nu ? 1.0f / nu[b * P + i] : 1.0f;
+        rdiv = 1.0f / ndiv[b * P + i];
+    }
+    float s = 0.0f;
+    if (i < P)
+        for (int c = threadIdx.y; c < C; c += 8) {
+            int64_t o = (b * C + c) * (int64_t)P + i;
+            s = fmaf(__ldg(g + o), __ldg(u + o) * rn, s);
+        }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t += red[r][threadIdx.x];
+        dot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (i < P) {
+        float d = dot[threadIdx.x];
+        for (int c = threadIdx.y; c < C; c += 8) {
+            int64_t o = (b * C + c) * (int64_t)P + i;
+            out[o] = (__ldg(g + o) - __ldg(u + o) * rn * d) * rdiv;
+        }
+    }
+}
+
+// ---- batched register-tiled GEMM with functor operands ------------------------------------
+// Cmn = Σ_k A(m,k) B(k,n);  LA/LB: element loaders (b, m|n, k) -> float;  EP: epilogue.
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <class LA, class LB, class EP>
+__global__ void __launch_bounds__(256) bgemm_kernel(int M, int N, int K, LA la, LB lb, EP ep) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int64_t b = blockIdx.z;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // cooperative loads: 16x64 elements each, 4 per thread
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int e = threadIdx.x + r * 256;
+            if (LA::kMajorM) {
+                int mm = e & 63, kk = e >> 6;
+                As[kk][mm] = (m0 + mm < M && k0 + kk < K) ? la(b, m0 + mm, k0 + kk) : 0.0f;
+            } else {
+                int kk = e & 15, mm = e >> 4;
+                As[kk][mm] = (m0 + mm < M && k0 + kk < K) ? la(b, m0 + mm, k0 + kk) : 0.0f;
+            }
+            if (LB::kMajorN) {
+                int nn = e & 63, kk = e >> 6;
+                Bs[kk][nn] = (n0 + nn < N && k0 + kk < K) ? lb(b, n0 + nn, k0 + kk) : 0.0f;
+            } else {
+                int kk = e & 15, nn = e >> 4;
+                Bs[kk][nn] = (n0 + nn < N && k0 + kk < K) ? lb(b, n0 + nn, k0 + kk) : 0.0f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < N) ep(b, m, n, acc[i][j]);
+        }
+}
+
+// Operand loaders.  kMajorM/kMajorN = the m (or n) index is the contiguous one in memory, so
+// the cooperative load walks it fastest (coalesced).
+// x[b, k=c, m=i] * rn[b,i]      ([C,P] tensor read "transposed": m contiguous)
+struct LoadColScaled {  // element (m=i, k=c) of x̂ᵀ
+    static constexpr bool kMajorM = true, kMajorN = true;
+    const float *x, *rn;  // rn may be null (no scaling)
+    int C, P;
+    __device__ __forceinline__ float operator()(int64_t b, int i, int c) const {
+        float v = __ldg(x + (b * C + c) * (int64_t)P + i);
+        return rn ? v / __ldg(rn + b * P + i) : v;
+    }
+};
+// x[b, m=c, k=j] / n[b,j]        ([C,P] tensor read row-wise: k contiguous)
+struct LoadRowScaled {
+    static constexpr bool kMajorM = false, kMajorN = false;
+    const float *x, *rn;
+    int C, P;
+    __device__ __forceinline__ float operator()(int64_t b, int c, int j) const {
+        float v = __ldg(x + (b * C + c) * (int64_t)P + j);
+        return rn ? v / __ldg(rn + b * P + j) : v;
+    }
+};
+// B(k=j, n=i) = f(S[b,i,j])      (S row i contiguous in j = k)
+struct LoadActS {
+    static constexpr bool kMajorM = false, kMajorN = false;
+    const float* S;
+    int P;
+    Act act;
+    __device__ __forceinline__ float operator()(int64_t b, int i, int j) const {
+        return act.f(__ldg(S + (b * P + i) * (int64_t)P + j));
+    }
+};
+// B(k=i, n=j) = f(S[b,i,j])      (n contiguous)
+struct LoadActS_T {
+    static constexpr bool kMajorM = true, kMajorN = true;
+    const float* S;
+    int P;
+    Act act;
+    __device__ __forceinline__ float operator()(int64_t b, int j, int i) const {
+        return act.f(__ldg(S + (b * P + i) * (int64_t)P + j));
+    }
+};
+// B(k=j, n=i) = gS[b,i,j] + gS[b,j,i]
+struct LoadSym {
+    static constexpr bool kMajorM = false, kMajorN = false;
+    const float* gS;
+    int P;
+    __device__ __forceinline__ float operator()(int64_t b, int i, int j) const {
+        return __ldg(gS + (b * P + i) * (int64_t)P + j) + __ldg(gS + (b * P + j) * (int64_t)P + i);
+    }
+};
+
+struct EpStore {  // out[b,m,n] = v
+    float* out;
+    int M, N;
+    __device__ __forceinline__ void operator()(int64_t b, int m, int n, float v) const { out[(b * M + m) * (int64_t)N + n] = v; }
+};
+struct EpGradS {  // gS[b,i,j] = v * A'(S[b,i,j])
+    float* gS;
+    const float* S;
+    int P;
+    Act act;
+    __device__ __forceinline__ void operator()(int64_t b, int i, int j, float v) const {
+        int64_t o = (b * P + i) * (int64_t)P + j;
+        gS[o] = v * act.df(__ldg(S + o));
+    }
+};
+
+template <class LA, class LB, class EP>
+static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (unsigned)B);
+    PP_LAUNCH(what, st, (bgemm_kernel<LA, LB, EP><<<grid, 256, 0, st>>>(M, N, K, la, lb, ep)));
+    return check_launch(what);
+}
+
+struct Saved {
+    float *nx, *nv, *ny, *S;
+};
+static Saved carve_saved(void* p, int64_t B, int P) {
+    Saved s;
+    float* f = (float*)p;
+    s.nx = f; f += B * P;
+    s.nv = f; f += B * P;
+    s.ny = f; f += B * P;
+    s.S = f;
+    return s;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int64_t pp_ppm_saved_bytes(int64_t B, int C, int P) {
+    (void)C;
+    return (3 * B * P + B * (int64_t)P * P) * (int64_t)sizeof(float);
+}
+
+int64_t pp_ppm_bwd_workspace(int64_t B, int C, int P) {
+    // gy [B,C,P] + gS [B,P,P] + gvh [B,C,P] + gxh [B,C,P]
+    return (3 * B * (int64_t)C * P + B * (int64_t)P * P) * (int64_t)sizeof(float);
+}
+
+int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, double gamma, double clamp_value, int final_norm,
+               float* out, void* saved, void* stream) {
+    PP_REQUIRE(feat && val && out && saved, "pp_ppm_fwd: null pointer");
+    PP_REQUIRE(B > 0 && B <= 65535 && C > 0 && P > 0, "pp_ppm_fwd: bad shape B=%lld C=%d P=%d", (long long)B, C, P);
+    cudaStream_t st = (cudaStream_t)stream;
+    Saved sv = carve_saved(saved, B, P);
+    Act act = make_act(gamma, clamp_value);
+    dim3 nb((P + 31) / 32, (unsigned)B), nt(32, 8);
+    PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(feat, C, P, sv.nx));
+    PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(val, C, P, sv.nv));
+    int rc = check_launch("colnorm_kernel");
+    if (rc) return rc;
+    // S[i][j] = Σ_c x̂[c][i] x̂[c][j]
+    rc = launch_bgemm("ppm S", B, P, P, C, LoadColScaled{feat, sv.nx, C, P}, LoadColScaled{feat, sv.nx, C, P},
+                      EpStore{sv.S, P, P}, st);
+    if (rc) return rc;
+    // Y[c][i] = Σ_j v̂[c][j] A[i][j]
+    rc = launch_bgemm("ppm Y", B, C, P, P, LoadRowScaled{val, sv.nv, C, P}, LoadActS{sv.S, P, act}, EpStore{out, C, P}, st);
+    if (rc) return rc;
+    if (final_norm) {
+        PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(out, C, P, sv.ny));
+        int64_t total = B * (int64_t)C * P;
+        PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, sv.ny, C, P, total, out));
+        rc = check_launch("ppm final normalize");
+    }
+    return rc;
+}
+
+int pp_ppm_bwd(const float* feat, const float* val, const float* out, const float* g, const void* saved, int64_t B, int C,
+               int P, double gamma, double clamp_value, int final_norm, float* d_feat_sim, float* d_val, void* workspace,
+               void* stream) {
+    PP_REQUIRE(feat && val && out && g && saved && d_feat_sim && d_val && workspace, "pp_ppm_bwd: null pointer");
+    PP_REQUIRE(B > 0 && B <= 65535 && C > 0 && P > 0, "pp_ppm_bwd: bad shape B=%lld C=%d P=%d", (long long)B, C, P);
+    cudaStream_t st = (cudaStream_t)stream;
+    Saved sv = carve_saved(const_cast<void*>(saved), B, P);
+    Act act = make_act(gamma, clamp_value);
+    float* gy = (float*)workspace;
+    float* gS = gy + B * (int64_t)C * P;
+    float* gvh = gS + B * (int64_t)P * P;
+    float* gxh = gvh + B * (int64_t)C * P;
+    dim3 nb((P + 31) / 32, (unsigned)B), nt(32, 8);
+    int rc;
+    const float* gyp = g;
+    if (final_norm) {  // gy = (g − ŷ (g·ŷ)) / ny ; `out` is ŷ
+        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(g, out, nullptr, sv.ny, C, P, gy));
+        rc = check_launch("ppm normbwd(out)");
+        if (rc) return rc;
+        gyp = gy;
+    }
+    // gS[i][j] = (Σ_c gy[c][i] v̂[c][j]) A'(S[i][j])
+    rc = launch_bgemm("ppm gS", B, P, P, C, LoadColScaled{gyp, nullptr, C, P}, LoadColScaled{val, sv.nv, C, P},
+                      EpGradS{gS, sv.S, P, act}, st);
+    if (rc) return rc;
+    // gv̂[c][j] = Σ_i gy[c][i] A[i][j]
+    rc = launch_bgemm("ppm gvh", B, C, P, P, LoadRowScaled{gyp, nullptr, C, P}, LoadActS_T{sv.S, P, act}, EpStore{gvh, C, P}, st);
+    if (rc) return rc;
+    // gx̂[c][i] = Σ_j x̂[c][j] (gS[i][j] + gS[j][i])
+    rc = launch_bgemm("ppm gxh", B, C, P, P, LoadRowScaled{feat, sv.nx, C, P}, LoadSym{gS, P}, EpStore{gxh, C, P}, st);
+    if (rc) return rc;
+    PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gxh, feat, sv.nx, sv.nx, C, P, d_feat_sim));
+    PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gvh, val, sv.nv, sv.nv, C, P, d_val));
+    return check_launch("ppm normbwd(in)");
+}
+
+}  // extern "C"

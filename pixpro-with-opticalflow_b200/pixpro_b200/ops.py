@@ -1,0 +1,294 @@
+"""torch-facing wrappers of the C ABI (include/pixpro_b200.h).
+
+torch supplies device memory (the caching allocator) and the current CUDA stream; all
+arithmetic runs in libpixpro_b200.so.  Every wrapper validates device / dtype / layout and
+raises — there is no CPU or eager-PyTorch fallback.
+"""
+import os
+
+import torch
+
+from . import _cabi
+
+_DIV_MODES = {"ieee": 0, "rcp": 1}
+_div_mode = _DIV_MODES[os.environ.get("PIXPRO_B200_DIV", "ieee")]
+
+
+def set_div_mode(mode):
+    """'ieee': tensor/scalar sites round like the reference on CPU (true division; the pinned
+    oracle).  'rcp': like torch's CUDA true-divide kernel (x * fl32(1/s))."""
+    global _div_mode
+    _div_mode = _DIV_MODES[mode]
+
+
+def get_div_mode():
+    return {v: k for k, v in _DIV_MODES.items()}[_div_mode]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise _cabi.PixProB200Error(f"{name}: tensor is on {t.device}; the pixel-pretext kernels are CUDA-only "
+                                    "(no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _f32(t, name):
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in (torch.float16, torch.bfloat16, torch.float64):
+        t = t.float()
+    return _req(t, name)
+
+
+def _mask_u8(m, name):
+    if m.dtype == torch.bool:
+        m = m.contiguous().view(torch.uint8)
+    return _req(m, name, torch.uint8)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------ flow --
+
+def upflow8(flow):
+    """contrast/flow/utils/utils.py:87-89 (bilinear mode)."""
+    flow = _f32(flow, "flow")
+    assert flow.ndim == 4, "upflow8 expects [N,C,h,w]"
+    N, C, h, w = flow.shape
+    out = torch.empty((N, C, 8 * h, 8 * w), device=flow.device, dtype=torch.float32)
+    with torch.cuda.device(flow.device):
+        _cabi.check(_cabi.lib().pp_upflow8(_ptr(flow), N * C, h, w, _ptr(out), _stream()), "pp_upflow8")
+    return out
+
+
+def _normalize(x, kind, name):
+    x = _f32(x, name)
+    assert x.ndim == 4 and x.shape[1] == 2, f"{name} expects [B,2,H,W]"
+    B, _, H, W = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().pp_normalize(_ptr(x), B, H, W, kind, _div_mode, _ptr(out), _stream()), "pp_normalize")
+    return out
+
+
+def normalize_coord(coords):
+    """contrast/util.py:334-339"""
+    return _normalize(coords, 0, "coords")
+
+
+def normalize_flow(flow):
+    """contrast/util.py:343-348"""
+    return _normalize(flow, 1, "flow")
+
+
+def denormalize_flow(flow_norm):
+    """contrast/util.py:352-357"""
+    return _normalize(flow_norm, 2, "flow_norm")
+
+
+def concat_flow(flows, is_norm=False):
+    """contrast/util.py:301-330.  flows [n,B,2,H,W] (any strides over n and B, e.g. the permuted
+    loader tensor) -> [B,2,H,W]."""
+    if not (isinstance(flows, torch.Tensor) and flows.is_cuda):
+        raise _cabi.PixProB200Error("flows: CUDA tensor required (no CPU fallback)")
+    assert flows.ndim == 5 and flows.shape[2] == 2, "concat_flow expects [n,B,2,H,W]"
+    if flows.dtype != torch.float32:
+        flows = flows.float()
+    n, B, _, H, W = flows.shape
+    if flows.stride()[2:] != (H * W, W, 1):
+        flows = flows.contiguous()
+    out = torch.empty((B, 2, H, W), device=flows.device, dtype=torch.float32)
+    with torch.cuda.device(flows.device):
+        _cabi.check(_cabi.lib().pp_concat_flow(_ptr(flows), n, B, H, W, flows.stride(0), flows.stride(1), int(is_norm),
+                                               _div_mode, _ptr(out), _stream()), "pp_concat_flow")
+    return out
+
+
+def forward_backward_consistency(flow_fwd, flow_bwd, alpha_1=0.01, alpha_2=0.5, is_norm=False, want_cycle=True,
+                                 want_coords=True):
+    """contrast/util.py:253-297 -> (coords1_norm or None, mask bool [B,H,W], cycle or None)."""
+    f = _f32(flow_fwd, "flow_fwd")
+    b = _f32(flow_bwd, "flow_bwd")
+    assert f.shape == b.shape and f.ndim == 4 and f.shape[1] == 2
+    B, _, H, W = f.shape
+    mask = torch.empty((B, H, W), device=f.device, dtype=torch.uint8)
+    cyc = torch.empty_like(f) if want_cycle else None
+    c1 = torch.empty_like(f) if want_coords else None
+    with torch.cuda.device(f.device):
+        _cabi.check(_cabi.lib().pp_fb_consistency(_ptr(f), _ptr(b), B, H, W, float(alpha_1), float(alpha_2), int(is_norm),
+                                                  _div_mode, _ptr(mask), _ptr(cyc), _ptr(c1), _stream()),
+                    "pp_fb_consistency")
+    return c1, mask.view(torch.bool), cyc
+
+
+def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=False):
+    """Flow stage of contrast/util.py:175-248 (use_flow_file, not use_flow_frames), fused.
+
+    lo_fwd/lo_bwd: loader layout [B,n,2,h,w].  Returns (flow_fwd, flow_bwd [B,2,H,W],
+    mask_fwd, mask_bwd bool [B,H,W] or None when alpha_1/alpha_2 is None)."""
+    f = _f32(lo_fwd, "lo_fwd")
+    b = _f32(lo_bwd, "lo_bwd")
+    assert f.ndim == 5 and f.shape == b.shape and f.shape[2] == 2, "flow_stage expects [B,n,2,h,w]"
+    B, n, _, h, w = f.shape
+    H, W = (8 * h, 8 * w) if flow_up else (h, w)
+    use_mask = alpha_1 is not None and alpha_2 is not None
+    ff = torch.empty((B, 2, H, W), device=f.device, dtype=torch.float32)
+    fb = torch.empty((B, 2, H, W), device=f.device, dtype=torch.float32)
+    mf = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
+    mb = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
+    with torch.cuda.device(f.device):
+        _cabi.check(_cabi.lib().pp_flow_stage(_ptr(f), _ptr(b), B, n, h, w, int(flow_up), int(use_mask),
+                                              float(alpha_1 or 0.0), float(alpha_2 or 0.0), int(is_norm), _div_mode,
+                                              _ptr(ff), _ptr(fb), _ptr(mf), _ptr(mb), _stream()), "pp_flow_stage")
+    return ff, fb, (mf.view(torch.bool) if use_mask else None), (mb.view(torch.bool) if use_mask else None)
+
+
+def calc_mask_ratio(mask):
+    """contrast/util.py:361-366"""
+    m = _mask_u8(mask, "mask")
+    assert m.ndim == 3
+    B, H, W = m.shape
+    out = torch.empty((B,), device=m.device, dtype=torch.float32)
+    with torch.cuda.device(m.device):
+        _cabi.check(_cabi.lib().pp_calc_mask_ratio(_ptr(m), B, H, W, _ptr(out), _stream()), "pp_calc_mask_ratio")
+    return out
+
+
+# ------------------------------------------------------------------------------------ loss --
+
+def _size_hw(size):
+    if isinstance(size, torch.Tensor):
+        size = size.tolist()  # the reference does the same host read (PixPro.py:116)
+    return int(size[0]), int(size[1])
+
+
+def add_optical_flow(flow, x_grid, y_grid, size, mask=None):
+    """contrast/models/PixPro.py:46-89 -> (out_x, out_y, mask_grid [B,1,G,G] bool or None)."""
+    flow = _f32(flow, "flow")
+    xg = _f32(x_grid, "x_grid")
+    yg = _f32(y_grid, "y_grid")
+    B, _, Hin, Win = flow.shape
+    H_orig, W_orig = _size_hw(size)
+    P = xg[0].numel()
+    ox = torch.empty_like(xg)
+    oy = torch.empty_like(yg)
+    m = _mask_u8(mask, "mask") if mask is not None else None
+    mg = torch.empty(xg.shape, device=flow.device, dtype=torch.uint8) if mask is not None else None
+    with torch.cuda.device(flow.device):
+        _cabi.check(_cabi.lib().pp_add_optical_flow(_ptr(flow), B, Hin, Win, _ptr(xg), _ptr(yg), P, H_orig, W_orig, _ptr(m),
+                                                    _div_mode, _ptr(ox), _ptr(oy), _ptr(mg), _stream()),
+                    "pp_add_optical_flow")
+    if mg is not None:
+        mg = mg.view(torch.bool).unsqueeze(1)
+    return ox, oy, mg
+
+
+class _RegressionLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, coord_q, coord_k, flow, mask, size, pos_ratio, debug):
+        q = _f32(q, "q")
+        k = _f32(k, "k")
+        cq = _f32(coord_q, "coord_q")
+        ck = _f32(coord_k, "coord_k")
+        B, C, G, G2 = q.shape
+        assert G == G2 and k.shape == q.shape and cq.shape == (B, 10) and ck.shape == (B, 10)
+        P = G * G
+        dev = q.device
+        if flow is not None:
+            flow = _f32(flow, "flow")
+            Hin, Win = flow.shape[-2:]
+        else:
+            Hin = Win = 0
+        m = _mask_u8(mask, "mask") if mask is not None else None
+        H_orig, W_orig = size
+        L = _cabi.lib()
+        ws = torch.empty((L.pp_regression_loss_workspace(B, G),), device=dev, dtype=torch.uint8)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        pos_num = torch.empty((B,), device=dev, dtype=torch.float32)
+        pos_mean = torch.empty((B,), device=dev, dtype=torch.float32)
+        dq = torch.empty_like(q)
+        pos_mask = torch.empty((B, P, P), device=dev, dtype=torch.uint8) if debug else None
+        centres = torch.empty((4, B, P), device=dev, dtype=torch.float32) if debug else None
+        with torch.cuda.device(dev):
+            _cabi.check(L.pp_regression_loss(_ptr(q), _ptr(k), B, C, G, _ptr(cq), _ptr(ck), _ptr(flow), Hin, Win, _ptr(m),
+                                             H_orig, W_orig, float(pos_ratio), _div_mode, _ptr(loss), _ptr(pos_num),
+                                             _ptr(pos_mean), _ptr(dq), _ptr(pos_mask), _ptr(centres), _ptr(ws), _stream()),
+                        "pp_regression_loss")
+        ctx.save_for_backward(dq)
+        ctx.mark_non_differentiable(pos_num, pos_mean)
+        if debug:
+            pm = pos_mask.view(torch.bool)
+            ctx.mark_non_differentiable(pm, centres)
+            return loss, pos_num, pos_mean, pm, centres
+        return loss, pos_num, pos_mean
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        (dq,) = ctx.saved_tensors
+        return (dq * g_loss,) + (None,) * 8
+
+
+def regression_loss(q, k, coord_q, coord_k, pos_ratio=0.5, flow=None, size=None, mask=None, debug=False):
+    """contrast/models/PixPro.py:92-247 with the nested-list arguments already unpacked.
+
+    Returns (loss, pos_num, pos_mean) — plus (pos_mask [B,P,P] bool, centres [4,B,P]) if debug."""
+    if size is None:
+        if flow is not None:
+            size = tuple(flow.shape[-2:])                          # PixPro.py:121
+        else:
+            size = (coord_q[0][9].item(), coord_q[0][8].item())    # PixPro.py:123 (same host read)
+    size = _size_hw(size)
+    return _RegressionLoss.apply(q, k.detach(), coord_q, coord_k, flow, mask, size, pos_ratio, debug)
+
+
+# ------------------------------------------------------------------------------------- PPM --
+
+class _PPM(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, feat, val, gamma, clamp_value, final_norm):
+        feat = _f32(feat, "feat")
+        val = _f32(val, "val")
+        assert feat.shape == val.shape and feat.ndim == 4
+        B, C, H, W = feat.shape
+        P = H * W
+        L = _cabi.lib()
+        out = torch.empty_like(feat)
+        saved = torch.empty((L.pp_ppm_saved_bytes(B, C, P),), device=feat.device, dtype=torch.uint8)
+        with torch.cuda.device(feat.device):
+            _cabi.check(L.pp_ppm_fwd(_ptr(feat), _ptr(val), B, C, P, float(gamma), float(clamp_value), int(final_norm),
+                                     _ptr(out), _ptr(saved), _stream()), "pp_ppm_fwd")
+        ctx.save_for_backward(feat, val, out, saved)
+        ctx.cfg = (float(gamma), float(clamp_value), int(final_norm))
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        feat, val, out, saved = ctx.saved_tensors
+        gamma, cv, final_norm = ctx.cfg
+        g = _f32(g, "grad_out")
+        B, C, H, W = feat.shape
+        P = H * W
+        L = _cabi.lib()
+        d_feat = torch.empty_like(feat)
+        d_val = torch.empty_like(val)
+        ws = torch.empty((L.pp_ppm_bwd_workspace(B, C, P),), device=feat.device, dtype=torch.uint8)
+        with torch.cuda.device(feat.device):
+            _cabi.check(L.pp_ppm_bwd(_ptr(feat), _ptr(val), _ptr(out), _ptr(g), _ptr(saved), B, C, P, gamma, cv, final_norm,
+                                     _ptr(d_feat), _ptr(d_val), _ptr(ws), _stream()), "pp_ppm_bwd")
+        return d_feat, d_val, None, None, None
+
+
+def ppm(feat, val, gamma=2.0, clamp_value=0.0, final_norm=True):
+    """PixPro.featprop after value_transform (contrast/models/PixPro.py:343-363) fused with the
+    caller's F.normalize (:380) when final_norm.  feat, val [B,C,H,W] -> [B,C,H,W]."""
+    return _PPM.apply(feat, val, gamma, clamp_value, final_norm)

@@ -1,0 +1,327 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (ctypes), against
+  (1) the golden vectors produced by the real reference (tests/golden, bit-exact where the
+      output is a coordinate / mask / count, 1e-5 relative for loss values and gradients —
+      the tolerance BASELINE.json's north_star states),
+  (2) the CPU oracle on seeded inputs, at sizes the oracle finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes (B=64, 720x1280).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_bits_equal, load_golden, rel_err, unpack_mask
+from test_oracle_golden import LOSS_TAGS
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from pixpro_b200 import synth as s
+    return s
+
+
+# --------------------------------------------------------------------------- golden vectors
+
+def test_library_loaded_and_counts_launches(ops):
+    from pixpro_b200 import _cabi
+    n0 = _cabi.launch_count()
+    ops.upflow8(torch.zeros(1, 2, 4, 4, device=DEV))
+    assert _cabi.launch_count() == n0 + 1
+
+
+def test_upflow8_golden(ops):
+    g = load_golden("upflow8")
+    assert_bits_equal(npy(ops.upflow8(cu(g["inp"]))), g["out"], "upflow8")
+    g = load_golden("upflow8_full")
+    assert sha(npy(ops.upflow8(cu(g["inp"].reshape(-1, 2, 90, 160))))) == str(g["out_sha"])
+
+
+@pytest.mark.parametrize("name", ["normalize_coord", "normalize_flow", "denormalize_flow"])
+def test_normalize_golden(ops, name):
+    g = load_golden(name)
+    assert_bits_equal(npy(getattr(ops, name)(cu(g["inp"]))), g["out"], name)
+
+
+@pytest.mark.parametrize("tag", ["n1", "n2", "n5", "n5_oob", "n3_norm", "n1_norm"])
+def test_concat_flow_golden(ops, tag):
+    g = load_golden("concat_flow_" + tag)
+    out = ops.concat_flow(cu(g["flows"]), is_norm=bool(g["is_norm"]))
+    assert_bits_equal(npy(out), g["out"], "concat_flow " + tag)
+    # the same links in the loader layout [B,n,...] passed as a permuted view (no copy)
+    lo = cu(np.ascontiguousarray(g["flows"].transpose(1, 0, 2, 3, 4)))
+    out2 = ops.concat_flow(lo.permute(1, 0, 2, 3, 4), is_norm=bool(g["is_norm"]))
+    assert_bits_equal(npy(out2), g["out"], "concat_flow strided " + tag)
+
+
+@pytest.mark.parametrize("tag", ["a", "oob", "norm"])
+def test_fb_consistency_golden(ops, tag):
+    g = load_golden("fb_" + tag)
+    c1, m, cyc = ops.forward_backward_consistency(cu(g["fwd"]), cu(g["bwd"]), 0.01, 0.5, is_norm=bool(g["is_norm"]))
+    assert_bits_equal(npy(m), g["mask"], "mask")
+    assert_bits_equal(npy(cyc), g["cycle"], "cycle")
+    assert_bits_equal(npy(c1), g["coords1"], "coords1")
+
+
+@pytest.mark.parametrize("tag", ["n1_up", "n5_up", "n2_noup", "n5_nomask", "n3_catnorm"])
+def test_flow_stage_golden(ops, tag):
+    g = load_golden("flow_stage_" + tag)
+    use_mask = bool(g["use_mask"])
+    ff, fb, mf, mb = ops.flow_stage(cu(g["lo_fwd"]), cu(g["lo_bwd"]), flow_up=bool(g["flow_up"]),
+                                    alpha_1=0.01 if use_mask else None, alpha_2=0.5 if use_mask else None,
+                                    is_norm=bool(g["is_norm"]))
+    assert_bits_equal(npy(ff), g["flow_fwd"], "flow_fwd")
+    assert_bits_equal(npy(fb), g["flow_bwd"], "flow_bwd")
+    if use_mask:
+        assert_bits_equal(npy(mf), unpack_mask(g["mask_fwd"], mf.shape), "mask_fwd")
+        assert_bits_equal(npy(mb), unpack_mask(g["mask_bwd"], mb.shape), "mask_bwd")
+        assert rel_err(npy(ops.calc_mask_ratio(mf)), g["mask_ratio_fwd"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["full_n1", "full_n5"])
+def test_flow_stage_full_size_golden(ops, tag):
+    g = load_golden("flow_stage_" + tag)
+    ff, fb, mf, mb = ops.flow_stage(cu(g["lo_fwd"]), cu(g["lo_bwd"]))
+    assert sha(npy(ff)) == str(g["flow_fwd_sha"])
+    assert sha(npy(fb)) == str(g["flow_bwd_sha"])
+    assert_bits_equal(npy(mf), unpack_mask(g["mask_fwd"], mf.shape), "mask_fwd")
+    assert_bits_equal(npy(mb), unpack_mask(g["mask_bwd"], mb.shape), "mask_bwd")
+
+
+def _loss_inputs(ops, g):
+    flow = mask = None
+    if "lo_fwd" in g:
+        um = bool(g["use_mask"])
+        flow, _, mask, _ = ops.flow_stage(cu(g["lo_fwd"]), cu(g["lo_bwd"]), alpha_1=0.01 if um else None,
+                                          alpha_2=0.5 if um else None)
+    return flow, mask
+
+
+@pytest.mark.parametrize("tag", LOSS_TAGS)
+def test_regression_loss_golden(ops, tag):
+    g = load_golden("loss_" + tag)
+    flow, mask = _loss_inputs(ops, g)
+    q = cu(g["q"]).requires_grad_(True)
+    B, C, G, _ = q.shape
+    P = G * G
+    loss, pos_num, pos_mean, pos_mask, centres = ops.regression_loss(
+        q, cu(g["k"]), cu(g["coord_q"]), cu(g["coord_k"]), float(g["pos_ratio"]), flow=flow, size=tuple(int(s) for s in g["size"]),
+        mask=mask, debug=True)
+    loss.backward()
+    assert_bits_equal(npy(pos_mask), unpack_mask(g["pos_mask"], (B, P, P)), "pos_mask (correspondence indices)")
+    assert_bits_equal(npy(pos_num), g["pos_num"], "pos_num")
+    assert rel_err(npy(pos_mean), g["pos_mean"]) < 1e-6
+    assert abs(loss.item() - float(g["loss"])) <= TOL * max(abs(float(g["loss"])), 1e-3)
+    assert rel_err(npy(q.grad), g["dq"]) < TOL
+    if "cqx" in g:
+        assert_bits_equal(npy(centres[0]), g["cqx"], "warped centre x")
+        assert_bits_equal(npy(centres[1]), g["cqy"], "warped centre y")
+        if "mask_grid" in g:
+            # a7 through its own entry point
+            from oracle import oracle as orc
+            o = orc.regression_loss(g["q"][:, :1], g["k"][:, :1], g["coord_q"], g["coord_q"], 0.7, size=tuple(g["size"]),
+                                    want_grad=False)
+            ox, oy, mg = ops.add_optical_flow(flow, cu(o["cqx"]).view(B, G, G), cu(o["cqy"]).view(B, G, G),
+                                              tuple(int(s) for s in g["size"]), mask)
+            assert_bits_equal(npy(ox).reshape(B, P), g["cqx"], "add_optical_flow x")
+            assert_bits_equal(npy(oy).reshape(B, P), g["cqy"], "add_optical_flow y")
+            assert_bits_equal(npy(mg).reshape(B, P), g["mask_grid"], "add_optical_flow mask_grid")
+
+
+@pytest.mark.parametrize("tag", ["l1_p2_g7", "l0_p1_g7", "l1_p2_g14", "l0_p05_cv01", "l0_p3_g7"])
+def test_featprop_golden(ops, tag):
+    g = load_golden("featprop_" + tag)
+    feat = cu(g["feat"]).requires_grad_(True)
+    conv = None
+    if "weight" in g:
+        conv = torch.nn.Conv2d(256, 256, 1).to(DEV)
+        with torch.no_grad():
+            conv.weight.copy_(cu(g["weight"]))
+            conv.bias.copy_(cu(g["bias"]))
+    # the 1x1 value transform stays on cuDNN: keep it in true fp32 for the 1e-5 comparison
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        val = conv(feat) if conv is not None else feat
+        out = ops.ppm(feat, val, float(g["gamma"]), float(g["clamp"]), final_norm=True)
+        out.backward(cu(g["gout"]))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    assert rel_err(npy(out), g["out"]) < TOL
+    assert rel_err(npy(feat.grad), g["d_feat"]) < 2e-5
+    if "weight" in g:
+        assert rel_err(npy(conv.weight.grad), g["d_weight"]) < 2e-5
+        assert rel_err(npy(conv.bias.grad), g["d_bias"]) < 2e-5
+
+
+# --------------------------------------------------------------------------- vs the oracle, seeded
+
+@pytest.mark.parametrize("B,n,h,w,flow_up,is_norm,mag", [
+    (2, 5, 90, 160, True, False, 1.5),      # published shape, nframe=6
+    (3, 1, 90, 160, True, False, 1.5),      # nframe=2
+    (2, 3, 45, 77, True, False, 2.0),       # ragged low-res size
+    (2, 2, 100, 180, False, False, 8.0),    # dense links, no up-sampling
+    (1, 4, 33, 47, True, True, 1.0),        # flow_cat_norm
+    (1, 2, 16, 16, True, False, 40.0),      # flows that leave the frame
+])
+def test_flow_stage_vs_oracle(ops, orc, synth, B, n, h, w, flow_up, is_norm, mag):
+    f, b = synth.flow_fields(B, n, h=h, w=w, seed=7 * n + h, magnitude=mag)
+    want = orc.flow_stage(f.numpy(), b.numpy(), flow_up=flow_up, is_norm=is_norm)
+    got = ops.flow_stage(f.to(DEV), b.to(DEV), flow_up=flow_up, is_norm=is_norm)
+    for name, gt, wt in zip(["flow_fwd", "flow_bwd", "mask_fwd", "mask_bwd"], got, want):
+        assert_bits_equal(npy(gt), wt, name)
+    valid = want[2].mean()
+    assert 0.0 <= valid <= 1.0
+
+
+def test_flow_stage_empty_batch(ops):
+    z = torch.zeros(0, 2, 2, 8, 8, device=DEV)
+    ff, fb, mf, mb = ops.flow_stage(z, z)
+    assert ff.shape == (0, 2, 64, 64) and mf.shape == (0, 64, 64)
+
+
+@pytest.mark.parametrize("G,C,B,use_flow,use_mask", [(7, 256, 8, True, True), (14, 256, 4, True, True),
+                                                     (28, 256, 2, True, False), (7, 64, 5, False, False),
+                                                     (5, 19, 3, False, False)])
+def test_regression_loss_vs_oracle(ops, orc, synth, G, C, B, use_flow, use_mask):
+    cq = synth.crop_coords(B, seed=100 + G)
+    ck = synth.crop_coords(B, seed=200 + G)
+    gen = torch.Generator().manual_seed(G * 31 + C)
+    q = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1)
+    flow = mask = None
+    if use_flow:
+        f, b = synth.flow_fields(B, 2, seed=300 + G)
+        flow, _, mask, _ = ops.flow_stage(f.to(DEV), b.to(DEV), alpha_1=0.01 if use_mask else None,
+                                          alpha_2=0.5 if use_mask else None)
+    o = orc.regression_loss(q.numpy(), k.numpy(), cq.numpy(), ck.numpy(), 0.7,
+                            flow=None if flow is None else npy(flow), size=(720, 1280),
+                            mask=None if mask is None else npy(mask))
+    qg = q.to(DEV).requires_grad_(True)
+    loss, pos_num, pos_mean, pos_mask, centres = ops.regression_loss(qg, k.to(DEV), cq.to(DEV), ck.to(DEV), 0.7, flow=flow,
+                                                                     size=(720, 1280), mask=mask, debug=True)
+    loss.backward()
+    assert_bits_equal(npy(pos_mask), o["pos_mask"], "pos_mask")
+    assert_bits_equal(npy(pos_num), o["pos_num"], "pos_num")
+    for i, key in enumerate(["cqx", "cqy", "ckx", "cky"]):
+        assert_bits_equal(npy(centres[i]), o[key], key)
+    assert abs(loss.item() - o["loss"]) <= TOL * max(abs(o["loss"]), 1e-3)
+    assert rel_err(npy(qg.grad), o["dq"]) < TOL
+    # non-unit upstream gradient
+    qg.grad = None
+    loss2, _, _ = ops.regression_loss(qg, k.to(DEV), cq.to(DEV), ck.to(DEV), 0.7, flow=flow, size=(720, 1280), mask=mask)
+    (loss2 * 3.0).backward()
+    assert rel_err(npy(qg.grad), 3.0 * o["dq"]) < TOL
+
+
+@pytest.mark.parametrize("G,B,gamma,cv", [(7, 6, 2.0, 0.0), (14, 3, 2.0, 0.0), (28, 1, 2.0, 0.0), (7, 2, 1.0, 0.0),
+                                          (7, 2, 0.5, 0.1), (9, 2, 3.0, 0.05)])
+@pytest.mark.parametrize("final_norm", [True, False])
+def test_ppm_vs_oracle(ops, orc, G, B, gamma, cv, final_norm):
+    gen = torch.Generator().manual_seed(G * 7 + B)
+    C = 256
+    feat = torch.randn(B, C, G, G, generator=gen)
+    val = torch.randn(B, C, G, G, generator=gen)
+    gout = torch.randn(B, C, G, G, generator=gen)
+    want = orc.featprop(feat.numpy(), val.numpy(), gamma, cv, final_norm)
+    wdf, wdv = orc.featprop_bwd(feat.numpy(), val.numpy(), gout.numpy(), gamma, cv, final_norm)
+    f = feat.to(DEV).requires_grad_(True)
+    v = val.to(DEV).requires_grad_(True)
+    out = ops.ppm(f, v, gamma, cv, final_norm)
+    out.backward(gout.to(DEV))
+    assert rel_err(npy(out), want) < TOL
+    assert rel_err(npy(f.grad), wdf) < 2e-5
+    assert rel_err(npy(v.grad), wdv) < 2e-5
+
+
+# --------------------------------------------------------------------------- full-size properties
+
+def test_full_size_flow_stage_properties(ops, synth):
+    """BASELINE.json configs[1] size: B=64, n_frames=2, 90x160 -> 720x1280."""
+    B = 64
+    f, b = synth.flow_fields(B, 1, seed=99)
+    f, b = f.to(DEV), b.to(DEV)
+    ff, fb, mf, mb = ops.flow_stage(f, b)
+    # (1) the fused path equals the step-by-step path through the separate kernels, bit for bit
+    up_f = ops.upflow8(f.reshape(-1, 2, 90, 160)).reshape(B, 1, 2, 720, 1280)
+    up_b = ops.upflow8(b.reshape(-1, 2, 90, 160)).reshape(B, 1, 2, 720, 1280)
+    cf = ops.concat_flow(up_f.permute(1, 0, 2, 3, 4))
+    cb = ops.concat_flow(up_b.permute(1, 0, 2, 3, 4))
+    assert torch.equal(cf, ff) and torch.equal(cb, fb)
+    _, m1, _ = ops.forward_backward_consistency(cf, cb, 0.01, 0.5, want_cycle=False, want_coords=False)
+    _, m2, _ = ops.forward_backward_consistency(cb, cf, 0.01, 0.5, want_cycle=False, want_coords=False)
+    assert torch.equal(m1, mf) and torch.equal(m2, mb)
+    # (2) samples are independent: any sub-batch gives the same bits
+    sub = [5, 17, 63]
+    ff2, fb2, mf2, mb2 = ops.flow_stage(f[sub], b[sub])
+    assert torch.equal(ff2, ff[sub]) and torch.equal(mb2, mb[sub])
+    # (3) mask ratio == 1 - mean(mask)
+    r = ops.calc_mask_ratio(mf)
+    assert torch.allclose(r, 1.0 - mf.float().mean((1, 2)), atol=1e-6)
+
+
+def test_full_size_chain_properties(ops):
+    """Zero links chain to zero; an integer translation chains to n*t wherever every
+    intermediate point stays inside the frame, and is fully FB-consistent there."""
+    B, n, h, w = 4, 5, 90, 160
+    z = torch.zeros(B, n, 2, h, w, device=DEV)
+    ff, fb, mf, mb = ops.flow_stage(z, z)
+    assert ff.abs().max().item() == 0.0 and bool(mf.all()) and bool(mb.all())
+    t = torch.zeros(B, n, 2, h, w, device=DEV)
+    t[:, :, 0] = 2.0   # low-res px -> 16 full-res px per link
+    t[:, :, 1] = -1.0  # -8 full-res px per link
+    ff, fb, mf, mb = ops.flow_stage(t, -t)
+    H, W = 8 * h, 8 * w
+    inside = ff[:, :, 8 * n + 1:, : W - 16 * n - 1]
+    # (sampling a constant field at a re-normalised integer position is exact only up to the
+    #  reference's own normalise/unnormalise rounding, ~1e-4 px: SURVEY.md A.1)
+    assert torch.allclose(inside[:, 0], torch.full_like(inside[:, 0], 16.0 * n), atol=2e-3)
+    assert torch.allclose(inside[:, 1], torch.full_like(inside[:, 1], -8.0 * n), atol=2e-3)
+    assert bool(mf[:, 8 * n + 1:, : W - 16 * n - 1].all())
+    assert not bool(mf[:, : 8 * n, :].any())  # points warped above the frame are invalid
+
+
+def test_full_size_loss_checksum(ops, synth):
+    """loss == sum(q * dq) (both are contractions of the same masked K·posᵀ), pos_num ==
+    pos_mask row sums, at the bench batch size."""
+    B, C, G = 64, 256, 7
+    feat1, feat2, k1, k2 = synth.features(B, C, G, seed=5)
+    q = torch.nn.functional.normalize(feat1, dim=1).to(DEV).requires_grad_(True)
+    cq, ck = synth.crop_coords(B, seed=1).to(DEV), synth.crop_coords(B, seed=2).to(DEV)
+    f, b = synth.flow_fields(B, 1, seed=3)
+    flow, _, mask, _ = ops.flow_stage(f.to(DEV), b.to(DEV))
+    loss, pos_num, pos_mean, pos_mask, _ = ops.regression_loss(q, k2.to(DEV), cq, ck, 0.7, flow=flow, size=(720, 1280),
+                                                               mask=mask, debug=True)
+    loss.backward()
+    assert torch.equal(pos_mask.sum((1, 2)).float(), pos_num)
+    chk = (q.detach().double() * q.grad.double()).sum().item()
+    assert abs(chk - loss.item()) <= 1e-5 * max(abs(loss.item()), 1e-3)
+
+
+# --------------------------------------------------------------------------- error behaviour
+
+def test_no_cpu_fallback(ops):
+    from pixpro_b200._cabi import PixProB200Error
+    with pytest.raises(PixProB200Error):
+        ops.upflow8(torch.zeros(1, 2, 4, 4))
+    with pytest.raises(PixProB200Error):
+        ops.flow_stage(torch.zeros(1, 1, 2, 4, 4), torch.zeros(1, 1, 2, 4, 4))
+    with pytest.raises(PixProB200Error):
+        ops.regression_loss(torch.zeros(1, 4, 33, 33, device=DEV), torch.zeros(1, 4, 33, 33, device=DEV),
+                            torch.zeros(1, 10, device=DEV), torch.zeros(1, 10, device=DEV), size=(8, 8))

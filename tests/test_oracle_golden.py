@@ -1,0 +1,113 @@
+"""CPU: the oracle (oracle/pixpro_oracle.c) against the golden vectors produced by the REAL
+reference (oracle/pin_against_reference.py, run in the build container where /root/reference
+exists).  Bit-exact for coordinates / masks / counts; 1e-5 relative for float reductions."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal, load_golden, rel_err, unpack_mask
+
+TOL = 1e-5  # BASELINE.json north_star: loss values and gradients within 1e-5 relative in fp32
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_upflow8(orc):
+    g = load_golden("upflow8")
+    assert_bits_equal(orc.upflow8(g["inp"]), g["out"], "upflow8")
+    g = load_golden("upflow8_full")
+    assert sha(orc.upflow8(g["inp"].reshape(-1, 2, 90, 160))) == str(g["out_sha"])
+
+
+@pytest.mark.parametrize("name", ["normalize_coord", "normalize_flow", "denormalize_flow"])
+def test_normalize(orc, name):
+    g = load_golden(name)
+    assert_bits_equal(getattr(orc, name)(g["inp"]), g["out"], name)
+
+
+@pytest.mark.parametrize("tag", ["n1", "n2", "n5", "n5_oob", "n3_norm", "n1_norm"])
+def test_concat_flow(orc, tag):
+    g = load_golden("concat_flow_" + tag)
+    assert_bits_equal(orc.concat_flow(g["flows"], is_norm=bool(g["is_norm"])), g["out"], "concat_flow " + tag)
+
+
+@pytest.mark.parametrize("tag", ["a", "oob", "norm"])
+def test_fb_consistency(orc, tag):
+    g = load_golden("fb_" + tag)
+    c1, m, cyc = orc.forward_backward_consistency(g["fwd"], g["bwd"], 0.01, 0.5, is_norm=bool(g["is_norm"]))
+    assert_bits_equal(m, g["mask"], "mask")
+    assert_bits_equal(cyc, g["cycle"], "cycle")
+    assert_bits_equal(c1, g["coords1"], "coords1")
+
+
+@pytest.mark.parametrize("tag", ["n1_up", "n5_up", "n2_noup", "n5_nomask", "n3_catnorm"])
+def test_flow_stage(orc, tag):
+    g = load_golden("flow_stage_" + tag)
+    use_mask = bool(g["use_mask"])
+    ff, fb, mf, mb = orc.flow_stage(g["lo_fwd"], g["lo_bwd"], flow_up=bool(g["flow_up"]),
+                                    alpha_1=0.01 if use_mask else None, alpha_2=0.5 if use_mask else None,
+                                    is_norm=bool(g["is_norm"]))
+    assert_bits_equal(ff, g["flow_fwd"], "flow_fwd")
+    assert_bits_equal(fb, g["flow_bwd"], "flow_bwd")
+    if use_mask:
+        assert_bits_equal(mf, unpack_mask(g["mask_fwd"], mf.shape), "mask_fwd")
+        assert_bits_equal(mb, unpack_mask(g["mask_bwd"], mb.shape), "mask_bwd")
+        assert rel_err(orc.calc_mask_ratio(mf), g["mask_ratio_fwd"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["full_n1", "full_n5"])
+def test_flow_stage_full_size(orc, tag):
+    g = load_golden("flow_stage_" + tag)
+    ff, fb, mf, mb = orc.flow_stage(g["lo_fwd"], g["lo_bwd"])
+    assert sha(ff) == str(g["flow_fwd_sha"])
+    assert sha(fb) == str(g["flow_bwd_sha"])
+    assert_bits_equal(mf, unpack_mask(g["mask_fwd"], mf.shape), "mask_fwd")
+    assert_bits_equal(mb, unpack_mask(g["mask_bwd"], mb.shape), "mask_bwd")
+
+
+LOSS_TAGS = ["noflow_g7", "noflow_g14", "flow_g7_n1_mask", "flow_g7_n5_mask", "flow_g14_n2_nomask",
+             "flow_g7_diffsize", "flow_g7_big", "noflow_g7_ratio03"]
+
+
+def oracle_loss_inputs(orc, g):
+    """Rebuild the dense flow / mask inputs of a loss fixture from its low-res links."""
+    flow = mask = None
+    if "lo_fwd" in g:
+        um = bool(g["use_mask"])
+        ff, _, mf, _ = orc.flow_stage(g["lo_fwd"], g["lo_bwd"], alpha_1=0.01 if um else None, alpha_2=0.5 if um else None)
+        flow, mask = ff, mf
+    return flow, mask
+
+
+@pytest.mark.parametrize("tag", LOSS_TAGS)
+def test_regression_loss(orc, tag):
+    g = load_golden("loss_" + tag)
+    flow, mask = oracle_loss_inputs(orc, g)
+    o = orc.regression_loss(g["q"], g["k"], g["coord_q"], g["coord_k"], float(g["pos_ratio"]), flow=flow,
+                            size=tuple(g["size"]), mask=mask)
+    assert_bits_equal(o["pos_num"], g["pos_num"], "pos_num")
+    assert rel_err(o["pos_mean"], g["pos_mean"]) < 1e-6
+    assert abs(o["loss"] - float(g["loss"])) <= TOL * max(abs(float(g["loss"])), 1e-3)
+    assert rel_err(o["dq"], g["dq"]) < TOL
+    if "cqx" in g:
+        assert_bits_equal(o["cqx"], g["cqx"], "warped centre x")
+        assert_bits_equal(o["cqy"], g["cqy"], "warped centre y")
+
+
+@pytest.mark.parametrize("tag", ["l1_p2_g7", "l0_p1_g7", "l1_p2_g14", "l0_p05_cv01", "l0_p3_g7"])
+def test_featprop(orc, tag):
+    g = load_golden("featprop_" + tag)
+    out = orc.featprop(g["feat"], g["val"], gamma=float(g["gamma"]), clamp_value=float(g["clamp"]))
+    assert rel_err(out, g["out"]) < TOL
+    dfs, dv = orc.featprop_bwd(g["feat"], g["val"], g["gout"], gamma=float(g["gamma"]), clamp_value=float(g["clamp"]))
+    if "weight" in g:
+        w = g["weight"][:, :, 0, 0].astype(np.float64)
+        dfeat = dfs + np.einsum("oc,bohw->bchw", w, dv.astype(np.float64))
+        assert rel_err(np.einsum("bohw,bchw->oc", dv.astype(np.float64), g["feat"].astype(np.float64)),
+                       g["d_weight"][:, :, 0, 0]) < 2e-5
+    else:
+        dfeat = dfs + dv
+    assert rel_err(dfeat, g["d_feat"]) < 2e-5
