@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) chain_kernel(ChainArgs a) {
     if (X >= a.W || Y >= a.H) return;
     int dir = blockIdx.z % a.ndir;
     int64_t b = blockIdx.z / a.ndir;
-    const float* links = a.links[dir] + b * a.stride_b;
+    const float* links = (dir ? a.links[1] : a.links[0]) + b * a.stride_b;
     int64_t HW = (int64_t)a.H * a.W;
     float ox, oy;
     if (a.n == 1) {  // util.py:303-308: clone (normalised when is_norm)
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) chain_kernel(ChainArgs a) {
         ox = sub(cx, c0x);  // util.py:326,328
         oy = sub(cy, c0y);
     }
-    float* o = a.out[dir] + b * 2 * HW + (int64_t)Y * a.W + X;
+    float* o = (dir ? a.out[1] : a.out[0]) + b * 2 * HW + (int64_t)Y * a.W + X;
     o[0] = ox;
     o[HW] = oy;
 }
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(256) fb_kernel(FbArgs a) {
     int dir = blockIdx.z % a.ndir;
     int64_t b = blockIdx.z / a.ndir;
     int64_t HW = (int64_t)a.H * a.W;
-    const float* f = a.flow[dir] + b * 2 * HW;
-    const float* g = a.flow[dir ^ 1] + b * 2 * HW;
+    const float* f = (dir ? a.flow[1] : a.flow[0]) + b * 2 * HW;
+    const float* g = (dir ? a.flow[0] : a.flow[1]) + b * 2 * HW;
     int64_t i = (int64_t)Y * a.W + X;
     float fx = __ldg(f + i), fy = __ldg(f + HW + i);
     float fnx = IS_NORM ? fx : norm_flow(fx, a.dw);  // :264
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) fb_kernel(FbArgs a) {
     float b2 = add(mul(bi.x, bi.x), mul(bi.y, bi.y));
     float eps = add(mul(a.a1, add(f2, b2)), a.a2);                    // :294
     bool ok = inb && (sub(cyc2, eps) <= 0.0f);                        // :296
-    a.mask[dir][b * HW + i] = ok ? 1 : 0;
+    (dir ? a.mask[1] : a.mask[0])[b * HW + i] = ok ? 1 : 0;
     if (dir == 0) {
         if (a.cycle) { a.cycle[b * 2 * HW + i] = cyx; a.cycle[b * 2 * HW + HW + i] = cyy; }
         if (a.coords1) { a.coords1[b * 2 * HW + i] = c1x; a.coords1[b * 2 * HW + HW + i] = c1y; }
@@ -294,9 +294,9 @@ using namespace pp;
 extern "C" {
 
 int pp_upflow8(const float* in, int64_t planes, int h, int w, float* out, void* stream) {
-    PP_REQUIRE(in && out, "pp_upflow8: null pointer");
     PP_REQUIRE(planes >= 0 && h > 0 && w > 0, "pp_upflow8: bad shape planes=%lld h=%d w=%d", (long long)planes, h, w);
-    if (planes == 0) return PP_OK;
+    if (planes == 0) return PP_OK;  // empty batch: nothing to do (pointers may be null)
+    PP_REQUIRE(in && out, "pp_upflow8: null pointer");
     int64_t total = planes * 8 * h * (2 * w);
     cudaStream_t st = (cudaStream_t)stream;
     PP_LAUNCH("upflow8", st,
@@ -306,10 +306,10 @@ int pp_upflow8(const float* in, int64_t planes, int h, int w, float* out, void* 
 }
 
 int pp_normalize(const float* x, int64_t B, int H, int W, int kind, int div_mode, float* out, void* stream) {
-    PP_REQUIRE(x && out, "pp_normalize: null pointer");
     PP_REQUIRE(B >= 0 && H > 1 && W > 1, "pp_normalize: bad shape B=%lld H=%d W=%d", (long long)B, H, W);
     PP_REQUIRE(kind >= 0 && kind <= 2, "pp_normalize: bad kind %d", kind);
     if (B == 0) return PP_OK;
+    PP_REQUIRE(x && out, "pp_normalize: null pointer");
     int64_t HW = (int64_t)H * W, total = B * 2 * HW;
     cudaStream_t st = (cudaStream_t)stream;
     PP_LAUNCH("normalize", st,
@@ -320,20 +320,20 @@ int pp_normalize(const float* x, int64_t B, int H, int W, int kind, int div_mode
 
 int pp_concat_flow(const float* flows, int n, int64_t B, int H, int W, int64_t stride_n, int64_t stride_b, int is_norm,
                    int div_mode, float* out, void* stream) {
-    PP_REQUIRE(flows && out, "pp_concat_flow: null pointer");
     PP_REQUIRE(n >= 1 && B >= 0 && H > 1 && W > 1, "pp_concat_flow: bad shape n=%d B=%lld H=%d W=%d", n, (long long)B, H, W);
     PP_REQUIRE(B <= 65535, "pp_concat_flow: B=%lld exceeds 65535", (long long)B);
     if (B == 0) return PP_OK;
+    PP_REQUIRE(flows && out, "pp_concat_flow: null pointer");
     return launch_chain(flows, nullptr, out, nullptr, 1, n, B, H, W, 0, 0, false, stride_n, stride_b, is_norm, div_mode,
                         (cudaStream_t)stream);
 }
 
 int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int W, double alpha_1, double alpha_2,
                       int is_norm, int div_mode, uint8_t* mask, float* cycle, float* coords1_norm, void* stream) {
-    PP_REQUIRE(fwd && bwd && mask, "pp_fb_consistency: null pointer");
     PP_REQUIRE(B >= 0 && H > 1 && W > 1, "pp_fb_consistency: bad shape B=%lld H=%d W=%d", (long long)B, H, W);
     PP_REQUIRE(B <= 65535, "pp_fb_consistency: B=%lld exceeds 65535", (long long)B);
     if (B == 0) return PP_OK;
+    PP_REQUIRE(fwd && bwd && mask, "pp_fb_consistency: null pointer");
     return launch_fb(fwd, bwd, mask, nullptr, cycle, coords1_norm, 1, B, H, W, alpha_1, alpha_2, is_norm, div_mode,
                      (cudaStream_t)stream);
 }
@@ -341,11 +341,11 @@ int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int 
 int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, int h, int w, int flow_up, int use_mask,
                   double alpha_1, double alpha_2, int is_norm, int div_mode, float* flow_fwd, float* flow_bwd,
                   uint8_t* mask_fwd, uint8_t* mask_bwd, void* stream) {
-    PP_REQUIRE(lo_fwd && lo_bwd && flow_fwd && flow_bwd, "pp_flow_stage: null pointer");
-    PP_REQUIRE(!use_mask || (mask_fwd && mask_bwd), "pp_flow_stage: use_mask set but mask outputs are null");
     PP_REQUIRE(n >= 1 && B >= 0 && h > 1 && w > 1, "pp_flow_stage: bad shape B=%lld n=%d h=%d w=%d", (long long)B, n, h, w);
     PP_REQUIRE(B * 2 <= 65535, "pp_flow_stage: B=%lld exceeds 32767", (long long)B);
     if (B == 0) return PP_OK;
+    PP_REQUIRE(lo_fwd && lo_bwd && flow_fwd && flow_bwd, "pp_flow_stage: null pointer");
+    PP_REQUIRE(!use_mask || (mask_fwd && mask_bwd), "pp_flow_stage: use_mask set but mask outputs are null");
     cudaStream_t st = (cudaStream_t)stream;
     int H = flow_up ? 8 * h : h, W = flow_up ? 8 * w : w;
     int64_t link = 2 * (int64_t)h * w;  // loader layout [B,n,2,h,w]
@@ -367,9 +367,9 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
 }
 
 int pp_calc_mask_ratio(const uint8_t* mask, int64_t B, int H, int W, float* ratio, void* stream) {
-    PP_REQUIRE(mask && ratio, "pp_calc_mask_ratio: null pointer");
     PP_REQUIRE(B >= 0 && H > 0 && W > 0, "pp_calc_mask_ratio: bad shape");
     if (B == 0) return PP_OK;
+    PP_REQUIRE(mask && ratio, "pp_calc_mask_ratio: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     PP_LAUNCH("mask_ratio", st, mask_ratio_kernel<<<(unsigned)B, 256, 0, st>>>(mask, (int64_t)H * W, ratio));
     return check_launch("mask_ratio_kernel");

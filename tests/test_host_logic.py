@@ -1,0 +1,186 @@
+"""CPU: host-side logic of the drop-in mirror (no kernels run): module construction and
+checkpoint key compatibility, argument unpacking, sub-chain enumeration, EMA schedule, error
+behaviour, and the multi-rank bookkeeping of bench.py under a 2-process gloo group."""
+import math
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def pixpro_args(**kw):
+    a = types.SimpleNamespace(pixpro_p=2.0, pixpro_momentum=0.99, pixpro_pos_ratio=0.7, pixpro_clamp_value=0.0,
+                              pixpro_transform_layer=1, pixpro_ins_loss_weight=0.0, output_dir="/tmp",
+                              num_instances=1000, batch_size=4, epochs=10, start_epoch=1, feature_dim=256,
+                              head_type="early_return")
+    a.__dict__.update(kw)
+    return a
+
+
+@pytest.fixture(scope="module")
+def gloo1():
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    yield
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def test_pixpro_constructs_with_reference_state_dict_keys(gloo1):
+    from contrast import resnet
+    from contrast.models import PixPro
+    m = PixPro(resnet.resnet50, pixpro_args())
+    keys = list(m.state_dict().keys())
+    prefixes = {k.split(".")[0] for k in keys}
+    assert prefixes == {"encoder", "projector", "encoder_k", "projector_k", "value_transform"}
+    assert "value_transform.weight" in keys and "value_transform.bias" in keys
+    assert "encoder.layer4.2.bn3.weight" in keys and "projector.linear2.bias" in keys
+    trainable = [p for p in m.parameters() if p.requires_grad]
+    # 167 trainable tensors, 33 023 552 fp32 values (encoder + projector + value_transform)
+    assert len(trainable) == 167
+    assert sum(p.numel() for p in trainable) == 33_023_552
+    # momentum branch starts as a copy and takes no gradient
+    assert all(not p.requires_grad for p in m.encoder_k.parameters())
+    assert torch.equal(m.encoder.conv1.weight, m.encoder_k.conv1.weight)
+    # SyncBN conversion happened in place on the children (PixPro.py:289-292)
+    assert isinstance(m.encoder.bn1, torch.nn.SyncBatchNorm)
+    assert m.K == int(1000 / 1 / 4 * 10) and m.k == 0
+
+
+def test_bad_transform_layer_raises(gloo1):
+    from contrast import resnet
+    from contrast.models import PixPro
+    with pytest.raises(NotImplementedError):
+        PixPro(resnet.resnet18 if False else resnet.resnet50, pixpro_args(pixpro_transform_layer=3))
+
+
+def test_momentum_schedule(gloo1):
+    from contrast import resnet
+    from contrast.models import PixPro
+    m = PixPro(resnet.resnet50, pixpro_args())
+    with torch.no_grad():
+        m.projector.linear2.bias.fill_(1.0)
+        m.projector_k.linear2.bias.fill_(0.0)
+    m.k, m.K = 3, 10
+    mom = 1. - (1. - 0.99) * (math.cos(math.pi * 3 / 10) + 1) / 2.
+    m._momentum_update_key_encoder()
+    assert m.k == 4
+    assert torch.allclose(m.projector_k.linear2.bias, torch.full((256,), 1.0 - mom), atol=1e-7)
+
+
+def test_unpack_coords_conventions():
+    PixProMod = __import__("contrast.models.PixPro", fromlist=["_unpack_coords"])
+    cq, ck = torch.zeros(2, 10), torch.ones(2, 10)
+    flow, flow_b = torch.zeros(2, 2, 8, 8), torch.ones(2, 2, 8, 8)
+    mask = torch.ones(2, 8, 8, dtype=torch.bool)
+    assert PixProMod._unpack_coords(cq, ck)[2:] == (None, None, None)
+    out = PixProMod._unpack_coords([cq, flow], [ck, flow_b])
+    assert out[2] is flow and tuple(out[3]) == (8, 8) and out[4] is None
+    size = torch.tensor([720, 1280])
+    out = PixProMod._unpack_coords([cq, [flow, size, mask]], [ck, [flow_b, size, None]])
+    assert out[0] is cq and out[1] is ck and out[2] is flow and out[3] is size and out[4] is mask
+    out = PixProMod._unpack_coords([cq, [flow, size, [mask, "cycle"]]], [ck, [flow_b, size, None]])
+    assert out[4] is mask
+
+
+def test_all_concat_flow_subchains(monkeypatch):
+    """use_flow_frames=True enumerates every contiguous sub-chain, shortest first, with the
+    bwd slices mirrored (contrast/util.py:111-126)."""
+    import contrast.util as util
+    calls = []
+
+    def fake_concat(flows, is_norm=False):
+        calls.append(flows[:, 0, 0, 0, 0].tolist())
+        return torch.zeros(1, 2, 2, 2)
+
+    monkeypatch.setattr(util, "concat_flow", fake_concat)
+    n = 4
+    fwd = torch.arange(n).float().view(n, 1, 1, 1, 1).expand(n, 1, 2, 2, 2)
+    bwd = (100 + torch.arange(n)).float().view(n, 1, 1, 1, 1).expand(n, 1, 2, 2, 2)
+    f, b = util.all_concat_flow(fwd, bwd, use_flow_frames=True)
+    assert f.shape[0] == n * (n + 1) // 2 == b.shape[0]
+    want = []
+    for i in range(n):            # the reference's own index arithmetic
+        fl = i + 1
+        for s in range(n - fl + 1):
+            bn = n - s
+            want.append(list(range(s, s + fl)))
+            want.append([100 + v for v in range(bn - fl, bn)])
+    assert calls == [[float(v) for v in w] for w in want]
+
+
+def test_apply_optical_flow_rejects_on_the_fly_raft():
+    import contrast.util as util
+    args = types.SimpleNamespace(alpha1=0.01, alpha2=0.5, use_flow_frames=False, use_flow_file=False, flow_up=True,
+                                 flow_cat_norm=False, debug=False)
+    data = [None] * 7
+    data[6] = [torch.tensor([[720, 1280]]), torch.tensor([[2]])]
+    with pytest.raises(NotImplementedError):
+        util.apply_optical_flow(data, None, args)
+
+
+def test_regression_loss_debug_tuple_is_rejected():
+    PixProMod = __import__("contrast.models.PixPro", fromlist=["regression_loss"])
+    with pytest.raises(NotImplementedError):
+        PixProMod.regression_loss(torch.zeros(1, 4, 7, 7), torch.zeros(1, 4, 7, 7), (1, 2), (3, 4))
+
+
+def test_synth_crop_coords_layout():
+    from pixpro_b200 import synth
+    c = synth.crop_coords(64, seed=3)
+    assert c.shape == (64, 10) and c.dtype == torch.float32
+    assert torch.all(c[:, 8] == 1280) and torch.all(c[:, 9] == 720)
+    flipped = c[:, 0] > c[:, 2]
+    assert 0 < int(flipped.sum()) < 64      # both orientations occur
+    x0 = torch.minimum(c[:, 0], c[:, 2]) * 1279
+    assert torch.allclose(x0, c[:, 4], atol=1e-3)
+
+
+def test_algorithmic_bytes_match_survey():
+    import bench
+    # F1 = n*230400 + 14745600 B/sample, F2 = 16.59 MB/sample
+    assert bench.algorithmic_bytes("chain_up", 1, 1) == 230400 + 14745600
+    assert bench.algorithmic_bytes("chain_up", 128, 5) == 128 * (5 * 230400 + 14745600)
+    assert bench.algorithmic_bytes("fb", 1, 1) == 14745600 + 1843200
+
+
+def _rank_main(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "pixpro-with-opticalflow_b200"))
+    import bench
+    a = types.SimpleNamespace(batch=4, n_frames=2, grid=7)
+    inp = bench.make_inputs(a, 1234 + rank)                    # each rank owns different samples
+    ms = bench.max_over_ranks(10.0 + 5.0 * rank, world, torch.device("cpu"))
+    fps = bench.aggregate_frames_per_s(a.batch, world, a.n_frames, ms)
+    q.put((rank, float(inp["lo_f"].sum()), ms, fps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_timing_reduction():
+    """world_size-2 gloo: ranks draw disjoint synthetic shards, the step time is the max over
+    ranks and the reported throughput is the whole-job aggregate."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, 29547, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, s0, ms0, fps0), (_, s1, ms1, fps1) = res
+    assert s0 != s1                                  # different shards
+    assert ms0 == ms1 == 15.0                        # max over ranks
+    assert fps0 == fps1 == pytest.approx(4 * 2 * 2 / 15e-3)
