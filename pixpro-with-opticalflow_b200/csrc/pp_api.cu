@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -32,6 +34,40 @@ int check_launch(const char* what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- certification of the exact constant division (pp_common.cuh, Div<DM_FAST>) -------------
+// For divisor s: check q == x/s for all 2^23 mantissas x in [1,2).  fmaf/division here are the
+// host's IEEE operations (this file is compiled without contraction: -fmad only affects device
+// code and the expressions below are explicit).  ~20 ms per new divisor, cached.
+static std::mutex g_cert_mu;
+static std::map<uint32_t, bool> g_cert;
+
+bool div_certified(float s) {
+    if (!(s >= 9.5367431640625e-07f && s <= 16777216.0f)) return false;  // 2^-20 .. 2^24
+    uint32_t key;
+    memcpy(&key, &s, 4);
+    {
+        std::lock_guard<std::mutex> lk(g_cert_mu);
+        auto it = g_cert.find(key);
+        if (it != g_cert.end()) return it->second;
+    }
+    const volatile float inv_v = 1.0f / s;
+    const float inv = inv_v;
+    bool ok = true;
+    for (uint32_t m = 0; m < (1u << 23) && ok; m++) {
+        uint32_t bits = 0x3f800000u | m;
+        float x;
+        memcpy(&x, &bits, 4);
+        volatile float q0 = x * inv;
+        float r = fmaf(-q0, s, x);
+        float q = fmaf(r, inv, q0);
+        volatile float t = x / s;
+        ok = (q == t);
+    }
+    std::lock_guard<std::mutex> lk(g_cert_mu);
+    g_cert[key] = ok;
+    return ok;
+}
 
 // ---- per-kernel device timing (tracing aid; off by default) --------------------------------
 // When enabled, every launch site brackets its kernel with a cudaEvent pair on the launch

@@ -47,6 +47,19 @@ class ProfScope {
         }                                     \
     } while (0)
 
+// base + off (in floats) as ONE IMAD.WIDE: nvcc otherwise widens index arithmetic on uniform
+// bases into 4-instruction 64-bit add/shift sequences per load (profiles/r01_a_*).
+__device__ __forceinline__ const float* ptr_at(const float* base, int off) {
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(off), "l"((unsigned long long)base));
+    return reinterpret_cast<const float*>(r);
+}
+__device__ __forceinline__ float* ptr_at(float* base, int off) {
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(off), "l"((unsigned long long)base));
+    return reinterpret_cast<float*>(r);
+}
+
 // ---- exactly-rounded scalar ops ----------------------------------------------------------
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
@@ -71,10 +84,57 @@ static inline ScalarDiv make_div(float s, int div_mode) {
     return d;
 }
 
+// Compile-time division flavours for the flow kernels (where divisions dominate the issue
+// slots).  Exact constant division (Markstein):  q0 = RN(x*inv); r = fma(-q0, s, x) (exact
+// residual); q = RN(q0 + r*inv)  equals RN(x/s) for every x in [2^-100, 2^100] ∪ {+0} when the
+// divisor passes div_certified(): the host checks the identity for all 2^23 mantissas of one
+// binade against true division (every step scales exactly by powers of two, so one binade
+// covers the range).  Outside that range (non-finite, denormal-tiny, -0) the unguarded form
+// may differ from IEEE division, so DM_FAST is used only where such inputs provably cannot
+// reach an output bit; DM_FASTG adds the range guard and is exact everywhere.
+enum { DM_IEEE = 0, DM_RCP = 1, DM_FAST = 2, DM_FASTG = 3 };
+
+bool div_certified(float s);  // host, cached (pp_api.cu)
+
+template <int DM>
+struct Div {
+    float s;    // divisor
+    float inv;  // fl32(1/s)
+    __device__ __forceinline__ float operator()(float x) const {
+        if (DM == DM_RCP) return __fmul_rn(x, inv);
+        if (DM == DM_IEEE) return __fdiv_rn(x, s);
+        float q0 = __fmul_rn(x, inv);
+        float r = __fmaf_rn(-q0, s, x);
+        float q = __fmaf_rn(r, inv, q0);
+        if (DM == DM_FASTG) {
+            float ax = fabsf(x);
+            bool plain = (ax >= 7.888609052210118e-31f && ax <= 1.2676506002282294e30f) || (__float_as_uint(x) == 0u);
+            if (!plain) q = __fdiv_rn(x, s);
+        }
+        return q;
+    }
+};
+template <int DM>
+static inline Div<DM> make_div(float s) {
+    Div<DM> d;
+    d.s = s;
+    d.inv = 1.0f / s;
+    return d;
+}
+
 // util.py:334-339  2*c/(size-1) - 1
-__device__ __forceinline__ float norm_coord(float c, const ScalarDiv& d) { return sub(d(mul(2.0f, c)), 1.0f); }
+template <class D>
+__device__ __forceinline__ float norm_coord(float c, const D& d) { return sub(d(mul(2.0f, c)), 1.0f); }
 // util.py:343-348  2*f/(size-1)
-__device__ __forceinline__ float norm_flow(float f, const ScalarDiv& d) { return d(mul(2.0f, f)); }
+template <class D>
+__device__ __forceinline__ float norm_flow(float f, const D& d) { return d(mul(2.0f, f)); }
+// Fused forms for the certified division: 2*v/s and v/(s/2) are the same real quotient, 2*v and
+// s/2 are exact, so RN(RN(2v)/s) == RN(v/(s/2)) (barring overflow of 2v, |v| > 1.7e38).  `dh2`
+// must be a Div over s/2.
+template <class D>
+__device__ __forceinline__ float norm_flow_h(float f, const D& dhalf) { return dhalf(f); }
+template <class D>
+__device__ __forceinline__ float norm_coord_h(float c, const D& dhalf) { return sub(dhalf(c), 1.0f); }
 // util.py:352-357  (f*(size-1))/2
 __device__ __forceinline__ float denorm_flow(float f, float size_m1) { return mul(mul(f, size_m1), 0.5f); }
 

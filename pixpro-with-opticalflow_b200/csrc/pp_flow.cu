@@ -9,10 +9,12 @@
 //   apply_optical_flow (flow stage) contrast/util.py:175-248
 //   calc_mask_ratio                 contrast/util.py:361-366
 //
-// All kernels are HBM-bound pointwise / gather kernels: one thread owns one output pixel
-// (or four consecutive ones where a float4 store is possible), flow links are read through
-// the read-only path, and the chain state lives in registers, so each output byte is
-// written exactly once and no intermediate tensor is materialised.
+// All kernels are pointwise / gather kernels whose DRAM traffic equals the algorithmic bytes
+// (ncu: profiles/r01_a_flow_stage_ncu_summary.txt); what limits them is instruction issue, so
+// the hot variants (a) own four consecutive pixels per thread (float4 / uchar4 accesses, row
+// terms amortised), (b) address with 32-bit offsets from per-thread base pointers, and (c) use
+// the certified 3-instruction exact division of pp_common.cuh instead of the IEEE sequence.
+// The chain state lives in registers; no intermediate tensor is materialised.
 #include <math.h>
 
 #include "pp_common.cuh"
@@ -20,8 +22,39 @@
 namespace pp {
 
 // ------------------------------------------------------------------------------------------
-// a1 upflow8: out[p,Y,X] = 8 * bilinear(in[p], Y, X).  One thread -> 4 consecutive X.
+// a1 upflow8 (stand-alone): out[p,Y,X] = 8 * bilinear(in[p], Y, X).  One thread -> 4 X.
 // ------------------------------------------------------------------------------------------
+// Evaluates 4 consecutive output columns X4..X4+3 of one output row for one low-res plane.
+// The 4 columns touch at most 3 consecutive low-res columns (scale < 1/8), which are loaded
+// once per row and selected per pixel — same values as 16 separate loads.
+struct Up4 {
+    AxisTap tx[4];
+    int c0;
+    bool has1, has2;  // columns c0+1 / c0+2 exist (else the value is the clamped neighbour)
+    __device__ __forceinline__ void init(int X4, float rw, int w) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) tx[j] = axis_tap(X4 + j, rw, w);
+        c0 = tx[0].i0;
+        has1 = c0 + 1 <= w - 1;
+        has2 = c0 + 2 <= w - 1;
+    }
+    // r0/r1: pointers to column c0 of the two low-res rows of one plane
+    __device__ __forceinline__ void eval(const float* __restrict__ r0, const float* __restrict__ r1, const AxisTap& ty,
+                                         float out[4]) const {
+        float a0 = __ldg(r0), b0 = __ldg(r1);
+        float a1 = a0, b1 = b0;
+        if (has1) { a1 = __ldg(r0 + 1); b1 = __ldg(r1 + 1); }
+        float a2 = a1, b2 = b1;
+        if (has2) { a2 = __ldg(r0 + 2); b2 = __ldg(r1 + 2); }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bool d = tx[j].i0 != c0;  // 0 or 1 column to the right of c0
+            float a = d ? a1 : a0, b = d ? a2 : a1, c = d ? b1 : b0, e = d ? b2 : b1;
+            out[j] = mul(8.0f, up_combine(ty, tx[j], a, b, c, e));
+        }
+    }
+};
+
 __global__ void __launch_bounds__(256) upflow8_kernel(const float* __restrict__ in, int64_t planes, int h, int w,
                                                        float rh, float rw, float* __restrict__ out) {
     const int H = 8 * h, W = 8 * w, W4 = W >> 2;
@@ -34,48 +67,41 @@ __global__ void __launch_bounds__(256) upflow8_kernel(const float* __restrict__ 
     int64_t p = r / H;
     const float* src = in + p * (int64_t)h * w;
     AxisTap ty = axis_tap(Y, rh, h);
-    const float* r0 = src + (int64_t)ty.i0 * w;
-    const float* r1 = src + (int64_t)ty.i1 * w;
+    Up4 u;
+    u.init(x4 * 4, rw, w);
     float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        AxisTap tx = axis_tap(x4 * 4 + j, rw, w);
-        float a = __ldg(r0 + tx.i0), b = __ldg(r0 + tx.i1), c = __ldg(r1 + tx.i0), d = __ldg(r1 + tx.i1);
-        v[j] = mul(8.0f, up_combine(ty, tx, a, b, c, d));
-    }
+    u.eval(ptr_at(src, ty.i0 * w + u.c0), ptr_at(src, ty.i1 * w + u.c0), ty, v);
     *reinterpret_cast<float4*>(out + (p * H + Y) * (int64_t)W + x4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // ------------------------------------------------------------------------------------------
-// a2 normalise kernels
+// a2 normalise kernels (stand-alone API; guarded division: exact for every input)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) normalize_kernel(const float* x, int64_t total, int64_t HW, int kind,
-                                                         ScalarDiv dw, ScalarDiv dh, float* out) {
+template <int DM>
+__global__ void __launch_bounds__(256) normalize_kernel(const float* x, int64_t total, int64_t HW, int kind, Div<DM> dw,
+                                                         Div<DM> dh, float* out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     bool is_y = ((i / HW) & 1) != 0;
-    const ScalarDiv& d = is_y ? dh : dw;
     float v = x[i];
     float r;
-    if (kind == PP_NORM_COORD) r = norm_coord(v, d);
-    else if (kind == PP_NORM_FLOW) r = norm_flow(v, d);
-    else r = denorm_flow(v, d.s);
+    if (kind == PP_NORM_COORD) r = is_y ? norm_coord(v, dh) : norm_coord(v, dw);
+    else if (kind == PP_NORM_FLOW) r = is_y ? norm_flow(v, dh) : norm_flow(v, dw);
+    else r = denorm_flow(v, is_y ? dh.s : dw.s);
     out[i] = r;
 }
 
 // ------------------------------------------------------------------------------------------
 // Link accessors.  A "link" is one [2,H,W] flow field of the chain for one sample.
-//   DenseLink  : values are read from a materialised dense field.
-//   UpLink     : values are 8 * bilinear-upsample of a low-res [2,h,w] field, evaluated on
-//                the fly with ATen's exact arithmetic (never materialised).
-// value(c, y, x) returns the (optionally normalised) flow component c at integer pixel.
+//   DenseLink : values are read from a materialised dense field.
+//   UpLink    : values are 8 * bilinear-upsample of a low-res [2,h,w] field, evaluated on the
+//               fly with ATen's exact arithmetic (never materialised).
 // ------------------------------------------------------------------------------------------
 struct DenseLink {
     const float* base;  // [2,H,W]
-    int64_t HW;
-    int W;
+    int HW, W;
     __device__ __forceinline__ float2 value(int y, int x) const {
-        int64_t o = (int64_t)y * W + x;
+        int o = y * W + x;
         return make_float2(__ldg(base + o), __ldg(base + HW + o));
     }
 };
@@ -87,20 +113,20 @@ struct UpLink {
     __device__ __forceinline__ float2 value(int y, int x) const {
         AxisTap ty = axis_tap(y, rh, h);
         AxisTap tx = axis_tap(x, rw, w);
-        const float* r0 = base + ty.i0 * w;
-        const float* r1 = base + ty.i1 * w;
-        int hw = h * w;
-        float ax = __ldg(r0 + tx.i0), bx = __ldg(r0 + tx.i1), cx = __ldg(r1 + tx.i0), dx = __ldg(r1 + tx.i1);
-        float ay = __ldg(r0 + hw + tx.i0), by = __ldg(r0 + hw + tx.i1), cy = __ldg(r1 + hw + tx.i0), dy = __ldg(r1 + hw + tx.i1);
+        int o0 = ty.i0 * w, o1 = ty.i1 * w, hw = h * w;
+        const float* p = base;
+        float ax = __ldg(p + o0 + tx.i0), bx = __ldg(p + o0 + tx.i1), cx = __ldg(p + o1 + tx.i0), dx = __ldg(p + o1 + tx.i1);
+        p += hw;
+        float ay = __ldg(p + o0 + tx.i0), by = __ldg(p + o0 + tx.i1), cy = __ldg(p + o1 + tx.i0), dy = __ldg(p + o1 + tx.i1);
         return make_float2(mul(8.0f, up_combine(ty, tx, ax, bx, cx, dx)), mul(8.0f, up_combine(ty, tx, ay, by, cy, dy)));
     }
 };
 
 // grid_sample of a link at normalised (gx,gy); NORM: taps are normalize_flow()'d first
 // (sampling the normalised field, util.py:316-318 / :278).
-template <bool NORM, class Link>
+template <bool NORM, int DM, class Link>
 __device__ __forceinline__ float2 sample_link(const Link& L, float gx, float gy, int W, int H, float half_w, float half_h,
-                                              const ScalarDiv& dw, const ScalarDiv& dh) {
+                                              const Div<DM>& dw, const Div<DM>& dh) {
     Taps t = make_taps(gx, gy, W, H, half_w, half_h);
     float2 z = make_float2(0.0f, 0.0f);
     float2 vnw = (t.inx0 && t.iny0) ? L.value(t.y0, t.x0) : z;
@@ -115,29 +141,30 @@ __device__ __forceinline__ float2 sample_link(const Link& L, float gx, float gy,
 }
 
 // ------------------------------------------------------------------------------------------
-// a3 / a6 chain kernel.  blockIdx.z = sample * ndir + dir; block = 32x8 pixels.
-//   UP      : links are low-res [2,h,w] fields up-sampled x8 on the fly (flow_up path)
-//   IS_NORM : --flow_cat_norm arithmetic (chain in normalised units)
+// a3 / a6 chain kernels.  blockIdx.z = sample * ndir + dir.
 // ------------------------------------------------------------------------------------------
+template <int DM>
 struct ChainArgs {
     const float* links[2];  // per direction
     float* out[2];          // per direction, [B,2,H,W]
     int64_t stride_n, stride_b;
     int n, H, W, h, w;
     float rh, rw, half_w, half_h;
-    ScalarDiv dw, dh;
+    Div<DM> dw, dh;
     int ndir;
 };
 
-template <bool UP, bool IS_NORM>
-__global__ void __launch_bounds__(256) chain_kernel(ChainArgs a) {
+// generic chain: one thread per pixel; block 32x8.
+//   UP: links are low-res fields up-sampled x8 on the fly;  IS_NORM: --flow_cat_norm arithmetic
+template <bool UP, bool IS_NORM, int DM>
+__global__ void __launch_bounds__(256) chain_kernel(ChainArgs<DM> a) {
     int X = blockIdx.x * 32 + threadIdx.x;
     int Y = blockIdx.y * 8 + threadIdx.y;
     if (X >= a.W || Y >= a.H) return;
-    int dir = blockIdx.z % a.ndir;
-    int64_t b = blockIdx.z / a.ndir;
+    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
     const float* links = (dir ? a.links[1] : a.links[0]) + b * a.stride_b;
-    int64_t HW = (int64_t)a.H * a.W;
+    int HW = a.H * a.W;
     float ox, oy;
     if (a.n == 1) {  // util.py:303-308: clone (normalised when is_norm)
         float2 v;
@@ -175,15 +202,40 @@ __global__ void __launch_bounds__(256) chain_kernel(ChainArgs a) {
         ox = sub(cx, c0x);  // util.py:326,328
         oy = sub(cy, c0y);
     }
-    float* o = (dir ? a.out[1] : a.out[0]) + b * 2 * HW + (int64_t)Y * a.W + X;
+    float* o = (dir ? a.out[1] : a.out[0]) + b * 2 * (int64_t)HW + Y * a.W + X;
     o[0] = ox;
     o[HW] = oy;
+}
+
+// n == 1 with flow_up (the published n_frames=2 setting): the composite IS the up-sampled
+// link.  One thread -> 4 consecutive pixels of both channels; float4 stores.  Block 32x8
+// threads = 128x8 pixels.
+template <int DM>
+__global__ void __launch_bounds__(256) upchain1_kernel(ChainArgs<DM> a) {
+    int X4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    int Y = blockIdx.y * 8 + threadIdx.y;
+    if (X4 >= a.W || Y >= a.H) return;
+    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const float* lo = (dir ? a.links[1] : a.links[0]) + b * a.stride_b;
+    AxisTap ty = axis_tap(Y, a.rh, a.h);
+    Up4 u;
+    u.init(X4, a.rw, a.w);
+    const int o0 = ty.i0 * a.w + u.c0, o1 = ty.i1 * a.w + u.c0, hw = a.h * a.w;
+    float vx[4], vy[4];
+    u.eval(ptr_at(lo, o0), ptr_at(lo, o1), ty, vx);
+    u.eval(ptr_at(lo, hw + o0), ptr_at(lo, hw + o1), ty, vy);
+    const int HW = a.H * a.W;
+    float* o = ptr_at((dir ? a.out[1] : a.out[0]) + b * 2 * (int64_t)HW, Y * a.W + X4);
+    *reinterpret_cast<float4*>(o) = make_float4(vx[0], vx[1], vx[2], vx[3]);
+    *reinterpret_cast<float4*>(ptr_at(o, HW)) = make_float4(vy[0], vy[1], vy[2], vy[3]);
 }
 
 // ------------------------------------------------------------------------------------------
 // a5 forward-backward consistency.  blockIdx.z = sample * ndir + dir.  For dir 0 the pair is
 // (fwd,bwd), for dir 1 it is (bwd,fwd) (util.py:212-213).
 // ------------------------------------------------------------------------------------------
+template <int DM>
 struct FbArgs {
     const float* flow[2];  // [B,2,H,W] each
     uint8_t* mask[2];      // [B,H,W]
@@ -191,21 +243,23 @@ struct FbArgs {
     float* coords1;        // optional (dir 0 only)
     int H, W;
     float half_w, half_h, a1, a2;
-    ScalarDiv dw, dh;
+    Div<DM> dw, dh;    // / (W-1), / (H-1)
+    Div<DM> dw2, dh2;  // / ((W-1)/2), / ((H-1)/2): fused 2*v/s (fbmask4_kernel only)
     int ndir;
 };
 
-template <bool IS_NORM>
-__global__ void __launch_bounds__(256) fb_kernel(FbArgs a) {
+// generic: one thread per pixel, every optional output, any W.
+template <bool IS_NORM, int DM>
+__global__ void __launch_bounds__(256) fb_kernel(FbArgs<DM> a) {
     int X = blockIdx.x * 32 + threadIdx.x;
     int Y = blockIdx.y * 8 + threadIdx.y;
     if (X >= a.W || Y >= a.H) return;
-    int dir = blockIdx.z % a.ndir;
-    int64_t b = blockIdx.z / a.ndir;
-    int64_t HW = (int64_t)a.H * a.W;
-    const float* f = (dir ? a.flow[1] : a.flow[0]) + b * 2 * HW;
-    const float* g = (dir ? a.flow[0] : a.flow[1]) + b * 2 * HW;
-    int64_t i = (int64_t)Y * a.W + X;
+    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    int HW = a.H * a.W;
+    const float* f = (dir ? a.flow[1] : a.flow[0]) + b * 2 * (int64_t)HW;
+    const float* g = (dir ? a.flow[0] : a.flow[1]) + b * 2 * (int64_t)HW;
+    int i = Y * a.W + X;
     float fx = __ldg(f + i), fy = __ldg(f + HW + i);
     float fnx = IS_NORM ? fx : norm_flow(fx, a.dw);  // :264
     float fny = IS_NORM ? fy : norm_flow(fy, a.dh);
@@ -224,9 +278,72 @@ __global__ void __launch_bounds__(256) fb_kernel(FbArgs a) {
     bool ok = inb && (sub(cyc2, eps) <= 0.0f);                        // :296
     (dir ? a.mask[1] : a.mask[0])[b * HW + i] = ok ? 1 : 0;
     if (dir == 0) {
-        if (a.cycle) { a.cycle[b * 2 * HW + i] = cyx; a.cycle[b * 2 * HW + HW + i] = cyy; }
-        if (a.coords1) { a.coords1[b * 2 * HW + i] = c1x; a.coords1[b * 2 * HW + HW + i] = c1y; }
+        if (a.cycle) { a.cycle[b * 2 * (int64_t)HW + i] = cyx; a.cycle[b * 2 * (int64_t)HW + HW + i] = cyy; }
+        if (a.coords1) { a.coords1[b * 2 * (int64_t)HW + i] = c1x; a.coords1[b * 2 * (int64_t)HW + HW + i] = c1y; }
     }
+}
+
+// Mask-only, W % 4 == 0, unnormalised inputs (the flow-stage path): one thread -> 4 consecutive
+// pixels (2 float4 loads, 1 uchar4 store).  Only the boolean leaves this kernel, so
+//  * a pixel whose warped position is outside (-1,1)^2 is 0 without sampling (util.py:276,296);
+//  * inside, ix in (0, W-1] and iy in (0, H-1]: the north-west tap always exists and the
+//    east / south taps can only fall off the frame with an exactly-zero weight, so their index
+//    is clamped instead of predicated (a finite value times 0 adds +-0, invisible to the test);
+//  * DM_FAST (unguarded exact division) is admissible: inputs outside its certified range are
+//    non-finite / < 2^-100 and cannot change the comparison.
+template <int DM>
+__global__ void __launch_bounds__(256) fbmask4_kernel(FbArgs<DM> a) {
+    int X4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    int Y = blockIdx.y * 8 + threadIdx.y;
+    if (X4 >= a.W || Y >= a.H) return;
+    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const int W = a.W, HW = a.H * a.W;
+    const float* f = (dir ? a.flow[1] : a.flow[0]) + b * 2 * (int64_t)HW;
+    const float* g = (dir ? a.flow[0] : a.flow[1]) + b * 2 * (int64_t)HW;
+    const int i = Y * W + X4;
+    const float* fp = ptr_at(f, i);
+    const float4 fx4 = __ldg(reinterpret_cast<const float4*>(fp));
+    const float4 fy4 = __ldg(reinterpret_cast<const float4*>(ptr_at(fp, HW)));
+    const float fxs[4] = {fx4.x, fx4.y, fx4.z, fx4.w}, fys[4] = {fy4.x, fy4.y, fy4.z, fy4.w};
+    const float yn = norm_coord_h((float)Y, a.dh2);
+    const int xmax = W - 1, ymax = a.H - 1;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float fnx = norm_flow_h(fxs[j], a.dw2), fny = norm_flow_h(fys[j], a.dh2);  // :264
+        float c1x = add(norm_coord_h((float)(X4 + j), a.dw2), fnx);               // :271,275
+        float c1y = add(yn, fny);
+        bool inb = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);                    // :276
+        if (inb) {
+            float ix = mul(add(c1x, 1.0f), a.half_w), iy = mul(add(c1y, 1.0f), a.half_h);
+            float xw = floorf(ix), yn_ = floorf(iy);
+            float wgt = sub(ix, xw), e = sub(add(xw, 1.0f), ix), n = sub(iy, yn_), s = sub(add(yn_, 1.0f), iy);
+            float nw = mul(s, e), ne = mul(s, wgt), sw = mul(n, e), se = mul(n, wgt);
+            int x0 = (int)xw, y0 = (int)yn_;
+            const bool hx = x0 < xmax, hy = y0 < ymax;  // east / south neighbour exists (else its weight is 0)
+            const float* p0 = ptr_at(g, y0 * W + x0);   // row y0, x channel
+            const float* p1 = ptr_at(p0, W);            // row y0+1
+            const float* q0 = ptr_at(p0, HW);           // y channel
+            const float* q1 = ptr_at(q0, W);
+            float x00 = __ldg(p0), y00 = __ldg(q0);
+            float x01 = 0.f, y01 = 0.f, x10 = 0.f, y10 = 0.f, x11 = 0.f, y11 = 0.f;
+            if (hx) { x01 = __ldg(p0 + 1); y01 = __ldg(q0 + 1); }
+            if (hy) { x10 = __ldg(p1); y10 = __ldg(q1); }
+            if (hx && hy) { x11 = __ldg(p1 + 1); y11 = __ldg(q1 + 1); }
+            float bx = fma_(norm_flow_h(x11, a.dw2), se,
+                            fma_(norm_flow_h(x10, a.dw2), sw, fma_(norm_flow_h(x01, a.dw2), ne, mul(norm_flow_h(x00, a.dw2), nw))));
+            float by = fma_(norm_flow_h(y11, a.dh2), se,
+                            fma_(norm_flow_h(y10, a.dh2), sw, fma_(norm_flow_h(y01, a.dh2), ne, mul(norm_flow_h(y00, a.dh2), nw))));
+            float cyx = add(fnx, bx), cyy = add(fny, by);                     // :279
+            float cyc2 = add(mul(cyx, cyx), mul(cyy, cyy));                   // :293
+            float f2 = add(mul(fnx, fnx), mul(fny, fny));
+            float b2 = add(mul(bx, bx), mul(by, by));
+            float eps = add(mul(a.a1, add(f2, b2)), a.a2);                    // :294
+            if (sub(cyc2, eps) <= 0.0f) packed |= 1u << (8 * j);              // :296
+        }
+    }
+    *reinterpret_cast<uint32_t*>((dir ? a.mask[1] : a.mask[0]) + b * HW + i) = packed;
 }
 
 // a11 calc_mask_ratio: one block per sample, integer count of zeros (exact), one division.
@@ -250,41 +367,83 @@ static float fb_alpha2_eff(double alpha_2, int H, int W) {
     return (float)(alpha_2 / (double)r);
 }
 
-static int launch_chain(const float* l0, const float* l1, float* o0, float* o1, int ndir, int n, int64_t B, int H, int W,
-                        int h, int w, bool up, int64_t stride_n, int64_t stride_b, int is_norm, int div_mode,
-                        cudaStream_t st) {
-    ChainArgs a;
+template <int DM>
+static int launch_chain_dm(const float* l0, const float* l1, float* o0, float* o1, int ndir, int n, int64_t B, int H, int W,
+                           int h, int w, bool up, int64_t stride_n, int64_t stride_b, int is_norm, cudaStream_t st) {
+    ChainArgs<DM> a;
     a.links[0] = l0; a.links[1] = l1; a.out[0] = o0; a.out[1] = o1;
     a.stride_n = stride_n; a.stride_b = stride_b;
     a.n = n; a.H = H; a.W = W; a.h = h; a.w = w;
     a.rh = up ? up_scale(h, H) : 0.f; a.rw = up ? up_scale(w, W) : 0.f;
     a.half_w = (float)(W - 1) / 2.0f; a.half_h = (float)(H - 1) / 2.0f;
-    a.dw = make_div((float)(W - 1), div_mode); a.dh = make_div((float)(H - 1), div_mode);
+    a.dw = make_div<DM>((float)(W - 1)); a.dh = make_div<DM>((float)(H - 1));
     a.ndir = ndir;
-    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
+    dim3 block(32, 8);
+    if (up && n == 1 && !is_norm) {  // W = 8w is a multiple of 4
+        dim3 grid((W / 4 + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
+        PP_LAUNCH("chain_up", st, upchain1_kernel<DM><<<grid, block, 0, st>>>(a));
+        return check_launch("upchain1_kernel");
+    }
+    dim3 grid((W + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
     if (up) {
-        if (is_norm) PP_LAUNCH("chain_up_norm", st, chain_kernel<true, true><<<grid, block, 0, st>>>(a));
-        else PP_LAUNCH("chain_up", st, chain_kernel<true, false><<<grid, block, 0, st>>>(a));
+        if (is_norm) PP_LAUNCH("chain_up_norm", st, (chain_kernel<true, true, DM><<<grid, block, 0, st>>>(a)));
+        else PP_LAUNCH("chain_up", st, (chain_kernel<true, false, DM><<<grid, block, 0, st>>>(a)));
     } else {
-        if (is_norm) PP_LAUNCH("chain_dense_norm", st, chain_kernel<false, true><<<grid, block, 0, st>>>(a));
-        else PP_LAUNCH("chain_dense", st, chain_kernel<false, false><<<grid, block, 0, st>>>(a));
+        if (is_norm) PP_LAUNCH("chain_dense_norm", st, (chain_kernel<false, true, DM><<<grid, block, 0, st>>>(a)));
+        else PP_LAUNCH("chain_dense", st, (chain_kernel<false, false, DM><<<grid, block, 0, st>>>(a)));
     }
     return check_launch("chain_kernel");
 }
 
-static int launch_fb(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, float* cycle, float* coords1, int ndir,
-                     int64_t B, int H, int W, double alpha_1, double alpha_2, int is_norm, int div_mode, cudaStream_t st) {
-    FbArgs a;
+static int launch_chain(const float* l0, const float* l1, float* o0, float* o1, int ndir, int n, int64_t B, int H, int W,
+                        int h, int w, bool up, int64_t stride_n, int64_t stride_b, int is_norm, int div_mode,
+                        cudaStream_t st) {
+    // The chain's only divisions normalise running coordinates (is_norm: also tap values; that
+    // rarely used mode keeps the IEEE sequence).  DM_FAST is exact there, see pp_common.cuh.
+    if (div_mode == PP_DIV_RCP)
+        return launch_chain_dm<DM_RCP>(l0, l1, o0, o1, ndir, n, B, H, W, h, w, up, stride_n, stride_b, is_norm, st);
+    if (!is_norm && div_certified((float)(W - 1)) && div_certified((float)(H - 1)))
+        return launch_chain_dm<DM_FAST>(l0, l1, o0, o1, ndir, n, B, H, W, h, w, up, stride_n, stride_b, is_norm, st);
+    return launch_chain_dm<DM_IEEE>(l0, l1, o0, o1, ndir, n, B, H, W, h, w, up, stride_n, stride_b, is_norm, st);
+}
+
+template <int DM>
+static int launch_fb_dm(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, float* cycle, float* coords1, int ndir,
+                        int64_t B, int H, int W, double alpha_1, double alpha_2, int is_norm, bool mask_only4,
+                        cudaStream_t st) {
+    FbArgs<DM> a;
     a.flow[0] = f0; a.flow[1] = f1; a.mask[0] = m0; a.mask[1] = m1;
     a.cycle = cycle; a.coords1 = coords1; a.H = H; a.W = W;
     a.half_w = (float)(W - 1) / 2.0f; a.half_h = (float)(H - 1) / 2.0f;
     a.a1 = (float)alpha_1; a.a2 = fb_alpha2_eff(alpha_2, H, W);
-    a.dw = make_div((float)(W - 1), div_mode); a.dh = make_div((float)(H - 1), div_mode);
+    a.dw = make_div<DM>((float)(W - 1)); a.dh = make_div<DM>((float)(H - 1));
+    a.dw2 = make_div<DM>((float)(W - 1) / 2.0f); a.dh2 = make_div<DM>((float)(H - 1) / 2.0f);
     a.ndir = ndir;
-    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
-    if (is_norm) PP_LAUNCH("fb_norm", st, fb_kernel<true><<<grid, block, 0, st>>>(a));
-    else PP_LAUNCH("fb", st, fb_kernel<false><<<grid, block, 0, st>>>(a));
+    dim3 block(32, 8);
+    if (mask_only4) {
+        dim3 grid((W / 4 + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
+        PP_LAUNCH("fb", st, fbmask4_kernel<DM><<<grid, block, 0, st>>>(a));
+        return check_launch("fbmask4_kernel");
+    }
+    dim3 grid((W + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
+    if (is_norm) PP_LAUNCH("fb_norm", st, (fb_kernel<true, DM><<<grid, block, 0, st>>>(a)));
+    else PP_LAUNCH("fb", st, (fb_kernel<false, DM><<<grid, block, 0, st>>>(a)));
     return check_launch("fb_kernel");
+}
+
+static int launch_fb(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, float* cycle, float* coords1, int ndir,
+                     int64_t B, int H, int W, double alpha_1, double alpha_2, int is_norm, int div_mode, cudaStream_t st) {
+    const bool mask_only4 = !cycle && !coords1 && !is_norm && (W % 4 == 0) &&
+                            (((uintptr_t)f0 | (uintptr_t)f1 | (uintptr_t)m0 | (uintptr_t)m1) % 16 == 0);
+    if (div_mode == PP_DIV_RCP)
+        return launch_fb_dm<DM_RCP>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, mask_only4, st);
+    const bool cert = div_certified((float)(W - 1)) && div_certified((float)(H - 1));
+    const bool cert_half = div_certified((float)(W - 1) / 2.0f) && div_certified((float)(H - 1) / 2.0f);
+    if (cert && cert_half && mask_only4)
+        return launch_fb_dm<DM_FAST>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, true, st);
+    if (cert)  // values leave the kernel (cycle / coords1): guarded variant, exact for every input
+        return launch_fb_dm<DM_FASTG>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, false, st);
+    return launch_fb_dm<DM_IEEE>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, mask_only4, st);
 }
 
 }  // namespace pp
@@ -297,6 +456,7 @@ int pp_upflow8(const float* in, int64_t planes, int h, int w, float* out, void* 
     PP_REQUIRE(planes >= 0 && h > 0 && w > 0, "pp_upflow8: bad shape planes=%lld h=%d w=%d", (long long)planes, h, w);
     if (planes == 0) return PP_OK;  // empty batch: nothing to do (pointers may be null)
     PP_REQUIRE(in && out, "pp_upflow8: null pointer");
+    PP_REQUIRE((int64_t)h * w * 64 < (1ll << 31), "pp_upflow8: plane too large");
     int64_t total = planes * 8 * h * (2 * w);
     cudaStream_t st = (cudaStream_t)stream;
     PP_LAUNCH("upflow8", st,
@@ -312,9 +472,14 @@ int pp_normalize(const float* x, int64_t B, int H, int W, int kind, int div_mode
     PP_REQUIRE(x && out, "pp_normalize: null pointer");
     int64_t HW = (int64_t)H * W, total = B * 2 * HW;
     cudaStream_t st = (cudaStream_t)stream;
-    PP_LAUNCH("normalize", st,
-              normalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-                  x, total, HW, kind, make_div((float)(W - 1), div_mode), make_div((float)(H - 1), div_mode), out));
+    unsigned nb = (unsigned)((total + 255) / 256);
+    const float sw = (float)(W - 1), sh = (float)(H - 1);
+    if (div_mode == PP_DIV_RCP)
+        PP_LAUNCH("normalize", st, normalize_kernel<DM_RCP><<<nb, 256, 0, st>>>(x, total, HW, kind, make_div<DM_RCP>(sw), make_div<DM_RCP>(sh), out));
+    else if (div_certified(sw) && div_certified(sh))
+        PP_LAUNCH("normalize", st, normalize_kernel<DM_FASTG><<<nb, 256, 0, st>>>(x, total, HW, kind, make_div<DM_FASTG>(sw), make_div<DM_FASTG>(sh), out));
+    else
+        PP_LAUNCH("normalize", st, normalize_kernel<DM_IEEE><<<nb, 256, 0, st>>>(x, total, HW, kind, make_div<DM_IEEE>(sw), make_div<DM_IEEE>(sh), out));
     return check_launch("normalize_kernel");
 }
 
@@ -322,6 +487,7 @@ int pp_concat_flow(const float* flows, int n, int64_t B, int H, int W, int64_t s
                    int div_mode, float* out, void* stream) {
     PP_REQUIRE(n >= 1 && B >= 0 && H > 1 && W > 1, "pp_concat_flow: bad shape n=%d B=%lld H=%d W=%d", n, (long long)B, H, W);
     PP_REQUIRE(B <= 65535, "pp_concat_flow: B=%lld exceeds 65535", (long long)B);
+    PP_REQUIRE((int64_t)H * W * 2 < (1ll << 31), "pp_concat_flow: frame too large");
     if (B == 0) return PP_OK;
     PP_REQUIRE(flows && out, "pp_concat_flow: null pointer");
     return launch_chain(flows, nullptr, out, nullptr, 1, n, B, H, W, 0, 0, false, stride_n, stride_b, is_norm, div_mode,
@@ -332,6 +498,7 @@ int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int 
                       int is_norm, int div_mode, uint8_t* mask, float* cycle, float* coords1_norm, void* stream) {
     PP_REQUIRE(B >= 0 && H > 1 && W > 1, "pp_fb_consistency: bad shape B=%lld H=%d W=%d", (long long)B, H, W);
     PP_REQUIRE(B <= 65535, "pp_fb_consistency: B=%lld exceeds 65535", (long long)B);
+    PP_REQUIRE((int64_t)H * W * 2 < (1ll << 31), "pp_fb_consistency: frame too large");
     if (B == 0) return PP_OK;
     PP_REQUIRE(fwd && bwd && mask, "pp_fb_consistency: null pointer");
     return launch_fb(fwd, bwd, mask, nullptr, cycle, coords1_norm, 1, B, H, W, alpha_1, alpha_2, is_norm, div_mode,
@@ -343,6 +510,7 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
                   uint8_t* mask_fwd, uint8_t* mask_bwd, void* stream) {
     PP_REQUIRE(n >= 1 && B >= 0 && h > 1 && w > 1, "pp_flow_stage: bad shape B=%lld n=%d h=%d w=%d", (long long)B, n, h, w);
     PP_REQUIRE(B * 2 <= 65535, "pp_flow_stage: B=%lld exceeds 32767", (long long)B);
+    PP_REQUIRE((int64_t)h * w * 128 < (1ll << 31), "pp_flow_stage: frame too large");
     if (B == 0) return PP_OK;
     PP_REQUIRE(lo_fwd && lo_bwd && flow_fwd && flow_bwd, "pp_flow_stage: null pointer");
     PP_REQUIRE(!use_mask || (mask_fwd && mask_bwd), "pp_flow_stage: use_mask set but mask outputs are null");
