@@ -60,6 +60,20 @@ __device__ __forceinline__ float* ptr_at(float* base, int off) {
     return reinterpret_cast<float*>(r);
 }
 
+// Predicated read-only load with an immediate element offset, as `asm volatile`: the compiler
+// keeps volatile asm statements in program order, which is what batches the gathers of several
+// pixels ahead of their uses (it otherwise re-serialises them per pixel to save registers).
+template <int OFF>
+__device__ __forceinline__ float ldg_pred(const float* p, bool pred) {
+    float v;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t"
+        "@q ld.global.nc.f32 %0, [%1+%3];\n\t}"
+        : "=f"(v)
+        : "l"(p), "r"((int)pred), "n"(OFF * 4));
+    return v;
+}
+
 // ---- exactly-rounded scalar ops ----------------------------------------------------------
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }

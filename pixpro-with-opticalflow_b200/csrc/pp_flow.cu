@@ -208,27 +208,73 @@ __global__ void __launch_bounds__(256) chain_kernel(ChainArgs<DM> a) {
 }
 
 // n == 1 with flow_up (the published n_frames=2 setting): the composite IS the up-sampled
-// link.  One thread -> 4 consecutive pixels of both channels; float4 stores.  Block 32x8
-// threads = 128x8 pixels.
+// link.  ATen's bilinear kernel interpolates horizontally first:
+//     val = fma(l0y, T(i0y,X), l1y * T(i1y,X)),   T(r,X) = fma(l0x, L[r][i0x], l1x * L[r][i1x])
+// and T(r,X) depends only on the low-res ROW r, which 8 consecutive output rows share.  One
+// thread therefore owns a 4-pixel-wide, 8-row-tall strip of both channels: it evaluates T
+// for the (at most) 3 low-res rows the strip touches once — bit-identical to recomputing it
+// per pixel — and each output value then costs 3 flops instead of 7; column taps are computed
+// once per strip.  Block = 32x8 threads = a 128x64-pixel tile; every store is a float4 and a
+// warp writes 512 contiguous bytes.  ~15 instructions per output pixel: HBM-write-bound.
 template <int DM>
 __global__ void __launch_bounds__(256) upchain1_kernel(ChainArgs<DM> a) {
-    int X4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    int Y = blockIdx.y * 8 + threadIdx.y;
-    if (X4 >= a.W || Y >= a.H) return;
-    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
-    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const int X4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int Y0 = (blockIdx.y * 8 + threadIdx.y) * 8;
+    if (X4 >= a.W || Y0 >= a.H) return;
+    const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    const int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
     const float* lo = (dir ? a.links[1] : a.links[0]) + b * a.stride_b;
-    AxisTap ty = axis_tap(Y, a.rh, a.h);
-    Up4 u;
-    u.init(X4, a.rw, a.w);
-    const int o0 = ty.i0 * a.w + u.c0, o1 = ty.i1 * a.w + u.c0, hw = a.h * a.w;
-    float vx[4], vy[4];
-    u.eval(ptr_at(lo, o0), ptr_at(lo, o1), ty, vx);
-    u.eval(ptr_at(lo, hw + o0), ptr_at(lo, hw + o1), ty, vy);
+    const int w = a.w, hw = a.h * a.w;
+    // column taps of the 4 pixels; they touch low-res columns c0 .. c0+2 (clamped)
+    AxisTap tx[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) tx[j] = axis_tap(X4 + j, a.rw, w);
+    const int c0 = tx[0].i0;
+    const bool has1 = c0 + 1 <= w - 1, has2 = c0 + 2 <= w - 1;
+    // low-res rows r0 .. r0+2 (clamped) cover the 8 output rows
+    const int r0 = axis_tap(Y0, a.rh, a.h).i0;
+    float T[2][3][4];  // [channel][low-res row][pixel]
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const int rr = min(r0 + r, a.h - 1);
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+            const float* p = ptr_at(lo, ch * hw + rr * w + c0);
+            float v0 = __ldg(p), v1 = v0, v2;
+            if (has1) v1 = __ldg(p + 1);
+            v2 = v1;
+            if (has2) v2 = __ldg(p + 2);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool d = tx[j].i0 != c0;  // 0 or 1 column to the right of c0
+                T[ch][r][j] = fma_(tx[j].l0, d ? v1 : v0, mul(tx[j].l1, d ? v2 : v1));
+            }
+        }
+    }
     const int HW = a.H * a.W;
-    float* o = ptr_at((dir ? a.out[1] : a.out[0]) + b * 2 * (int64_t)HW, Y * a.W + X4);
-    *reinterpret_cast<float4*>(o) = make_float4(vx[0], vx[1], vx[2], vx[3]);
-    *reinterpret_cast<float4*>(ptr_at(o, HW)) = make_float4(vy[0], vy[1], vy[2], vy[3]);
+    float* o = ptr_at((dir ? a.out[1] : a.out[0]) + b * 2 * (int64_t)HW, Y0 * a.W + X4);
+    // T[.][dy] / T[.][dy+1] are the rows i0y / i1y of output row k (the clamp of i1y at the last
+    // low-res row is already in T).  dy is uniform across the block row, so the two cases are a
+    // uniform branch around straight-line code, not per-value selects.
+    auto emit_row = [&](int k, const AxisTap& ty, const float (&A0)[4], const float (&A1)[4], const float (&B0)[4],
+                        const float (&B1)[4]) {
+        float vx[4], vy[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            vx[j] = mul(8.0f, fma_(ty.l0, A0[j], mul(ty.l1, A1[j])));
+            vy[j] = mul(8.0f, fma_(ty.l0, B0[j], mul(ty.l1, B1[j])));
+        }
+        float* ok = ptr_at(o, k * a.W);
+        *reinterpret_cast<float4*>(ok) = make_float4(vx[0], vx[1], vx[2], vx[3]);
+        *reinterpret_cast<float4*>(ptr_at(ok, HW)) = make_float4(vy[0], vy[1], vy[2], vy[3]);
+    };
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (Y0 + k >= a.H) break;
+        const AxisTap ty = axis_tap(Y0 + k, a.rh, a.h);
+        if (ty.i0 != r0) emit_row(k, ty, T[0][1], T[0][2], T[1][1], T[1][2]);
+        else emit_row(k, ty, T[0][0], T[0][1], T[1][0], T[1][1]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -283,67 +329,84 @@ __global__ void __launch_bounds__(256) fb_kernel(FbArgs<DM> a) {
     }
 }
 
-// Mask-only, W % 4 == 0, unnormalised inputs (the flow-stage path): one thread -> 4 consecutive
-// pixels (2 float4 loads, 1 uchar4 store).  Only the boolean leaves this kernel, so
-//  * a pixel whose warped position is outside (-1,1)^2 is 0 without sampling (util.py:276,296);
-//  * inside, ix in (0, W-1] and iy in (0, H-1]: the north-west tap always exists and the
-//    east / south taps can only fall off the frame with an exactly-zero weight, so their index
-//    is clamped instead of predicated (a finite value times 0 adds +-0, invisible to the test);
+// One pixel of the FB test with fully predicated taps (frame-edge cases of fbmask4_kernel).
+template <int DM>
+__device__ __noinline__ bool fb_pixel_edge(const float* g, int W, int H, int HW, float c1x, float c1y, float fnx, float fny,
+                                           float half_w, float half_h, float a1, float a2, Div<DM> dw, Div<DM> dh) {
+    DenseLink L{g, HW, W};
+    float2 bi = sample_link<true>(L, c1x, c1y, W, H, half_w, half_h, dw, dh);
+    float cyx = add(fnx, bi.x), cyy = add(fny, bi.y);
+    float cyc2 = add(mul(cyx, cyx), mul(cyy, cyy));
+    float f2 = add(mul(fnx, fnx), mul(fny, fny));
+    float b2 = add(mul(bi.x, bi.x), mul(bi.y, bi.y));
+    float eps = add(mul(a1, add(f2, b2)), a2);
+    return sub(cyc2, eps) <= 0.0f;
+}
+
+// Mask-only, W % 128 == 0, unnormalised inputs (the flow-stage path).  Block = 32x8 threads =
+// a 128x8-pixel tile; one thread -> the 4 pixels X0 + lane + 32*j of its row, so that every
+// load instruction of a warp covers 32 CONSECUTIVE pixels: own flow and mask accesses are
+// fully coalesced, and each tap gather touches 1-2 lines instead of the 4+ of a 4-px-per-lane
+// layout (profiles/r01_c_*: that layout was LSU-bound, lg_throttle 7.5).  Only the boolean
+// leaves this kernel, so
+//  * a pixel whose warped position is outside (-1,1)^2 is 0 (util.py:276,296); its taps are
+//    still fetched, from a clamped (valid) address, and ignored: no divergent control flow;
+//  * inside, ix in (0, W-1] and iy in (0, H-1]: all four taps exist unless ix == W-1 or
+//    iy == H-1 exactly, which takes the predicated edge routine;
 //  * DM_FAST (unguarded exact division) is admissible: inputs outside its certified range are
 //    non-finite / < 2^-100 and cannot change the comparison.
 template <int DM>
 __global__ void __launch_bounds__(256) fbmask4_kernel(FbArgs<DM> a) {
-    int X4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    int Y = blockIdx.y * 8 + threadIdx.y;
-    if (X4 >= a.W || Y >= a.H) return;
-    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
-    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const int X0 = blockIdx.x * 128 + threadIdx.x;
+    const int Y = blockIdx.y * 8 + threadIdx.y;
+    if (Y >= a.H) return;
+    const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    const int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
     const int W = a.W, HW = a.H * a.W;
     const float* f = (dir ? a.flow[1] : a.flow[0]) + b * 2 * (int64_t)HW;
     const float* g = (dir ? a.flow[0] : a.flow[1]) + b * 2 * (int64_t)HW;
-    const int i = Y * W + X4;
-    const float* fp = ptr_at(f, i);
-    const float4 fx4 = __ldg(reinterpret_cast<const float4*>(fp));
-    const float4 fy4 = __ldg(reinterpret_cast<const float4*>(ptr_at(fp, HW)));
-    const float fxs[4] = {fx4.x, fx4.y, fx4.z, fx4.w}, fys[4] = {fy4.x, fy4.y, fy4.z, fy4.w};
+    const int i = Y * W + X0;
+    const float* fpx = ptr_at(f, i);
+    const float* fpy = ptr_at(fpx, HW);
+    float fxs[4], fys[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { fxs[j] = __ldg(fpx + 32 * j); fys[j] = __ldg(fpy + 32 * j); }
     const float yn = norm_coord_h((float)Y, a.dh2);
-    const int xmax = W - 1, ymax = a.H - 1;
-    uint32_t packed = 0;
+    const unsigned xlim = W - 2, ylim = a.H - 2;
+    uint8_t* mp = (dir ? a.mask[1] : a.mask[0]) + b * HW + i;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        float fnx = norm_flow_h(fxs[j], a.dw2), fny = norm_flow_h(fys[j], a.dh2);  // :264
-        float c1x = add(norm_coord_h((float)(X4 + j), a.dw2), fnx);               // :271,275
+        float fnx = norm_flow_h(fxs[j], a.dw2), fny = norm_flow_h(fys[j], a.dh2);   // :264
+        float c1x = add(norm_coord_h((float)(X0 + 32 * j), a.dw2), fnx);           // :271,275
         float c1y = add(yn, fny);
-        bool inb = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);                    // :276
-        if (inb) {
-            float ix = mul(add(c1x, 1.0f), a.half_w), iy = mul(add(c1y, 1.0f), a.half_h);
-            float xw = floorf(ix), yn_ = floorf(iy);
-            float wgt = sub(ix, xw), e = sub(add(xw, 1.0f), ix), n = sub(iy, yn_), s = sub(add(yn_, 1.0f), iy);
-            float nw = mul(s, e), ne = mul(s, wgt), sw = mul(n, e), se = mul(n, wgt);
-            int x0 = (int)xw, y0 = (int)yn_;
-            const bool hx = x0 < xmax, hy = y0 < ymax;  // east / south neighbour exists (else its weight is 0)
-            const float* p0 = ptr_at(g, y0 * W + x0);   // row y0, x channel
-            const float* p1 = ptr_at(p0, W);            // row y0+1
-            const float* q0 = ptr_at(p0, HW);           // y channel
-            const float* q1 = ptr_at(q0, W);
-            float x00 = __ldg(p0), y00 = __ldg(q0);
-            float x01 = 0.f, y01 = 0.f, x10 = 0.f, y10 = 0.f, x11 = 0.f, y11 = 0.f;
-            if (hx) { x01 = __ldg(p0 + 1); y01 = __ldg(q0 + 1); }
-            if (hy) { x10 = __ldg(p1); y10 = __ldg(q1); }
-            if (hx && hy) { x11 = __ldg(p1 + 1); y11 = __ldg(q1 + 1); }
-            float bx = fma_(norm_flow_h(x11, a.dw2), se,
-                            fma_(norm_flow_h(x10, a.dw2), sw, fma_(norm_flow_h(x01, a.dw2), ne, mul(norm_flow_h(x00, a.dw2), nw))));
-            float by = fma_(norm_flow_h(y11, a.dh2), se,
-                            fma_(norm_flow_h(y10, a.dh2), sw, fma_(norm_flow_h(y01, a.dh2), ne, mul(norm_flow_h(y00, a.dh2), nw))));
-            float cyx = add(fnx, bx), cyy = add(fny, by);                     // :279
-            float cyc2 = add(mul(cyx, cyx), mul(cyy, cyy));                   // :293
-            float f2 = add(mul(fnx, fnx), mul(fny, fny));
-            float b2 = add(mul(bx, bx), mul(by, by));
-            float eps = add(mul(a.a1, add(f2, b2)), a.a2);                    // :294
-            if (sub(cyc2, eps) <= 0.0f) packed |= 1u << (8 * j);              // :296
-        }
+        bool inb = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);                     // :276
+        float ix = mul(add(c1x, 1.0f), a.half_w), iy = mul(add(c1y, 1.0f), a.half_h);
+        float xw = floorf(ix), yn_ = floorf(iy);
+        float wgt = sub(ix, xw), e = sub(add(xw, 1.0f), ix), n = sub(iy, yn_), s_ = sub(add(yn_, 1.0f), iy);
+        float nw = mul(s_, e), ne = mul(s_, wgt), sw = mul(n, e), se = mul(n, wgt);
+        int x0 = (int)xw, y0 = (int)yn_;
+        bool edge = inb && ((unsigned)x0 > xlim || (unsigned)y0 > ylim);
+        // clamp: garbage coordinates of out-of-frame pixels still address valid memory
+        unsigned xc = min((unsigned)x0, xlim), yc = min((unsigned)y0, ylim);
+        const float* p0 = ptr_at(g, (int)(yc * W + xc));  // row y0, x channel
+        const float* p1 = ptr_at(p0, W);                  // row y0+1
+        const float* q0 = ptr_at(p0, HW);                 // y channel
+        const float* q1 = ptr_at(q0, W);
+        float x00 = __ldg(p0), x01 = __ldg(p0 + 1), x10 = __ldg(p1), x11 = __ldg(p1 + 1);
+        float y00 = __ldg(q0), y01 = __ldg(q0 + 1), y10 = __ldg(q1), y11 = __ldg(q1 + 1);
+        float bx = fma_(norm_flow_h(x11, a.dw2), se,
+                        fma_(norm_flow_h(x10, a.dw2), sw, fma_(norm_flow_h(x01, a.dw2), ne, mul(norm_flow_h(x00, a.dw2), nw))));
+        float by = fma_(norm_flow_h(y11, a.dh2), se,
+                        fma_(norm_flow_h(y10, a.dh2), sw, fma_(norm_flow_h(y01, a.dh2), ne, mul(norm_flow_h(y00, a.dh2), nw))));
+        float cyx = add(fnx, bx), cyy = add(fny, by);                     // :279
+        float cyc2 = add(mul(cyx, cyx), mul(cyy, cyy));                   // :293
+        float f2 = add(mul(fnx, fnx), mul(fny, fny));
+        float b2 = add(mul(bx, bx), mul(by, by));
+        float eps = add(mul(a.a1, add(f2, b2)), a.a2);                    // :294
+        bool ok = inb && (sub(cyc2, eps) <= 0.0f);                        // :296
+        if (edge) ok = fb_pixel_edge<DM>(g, W, a.H, HW, c1x, c1y, fnx, fny, a.half_w, a.half_h, a.a1, a.a2, a.dw, a.dh);
+        mp[32 * j] = ok ? 1 : 0;
     }
-    *reinterpret_cast<uint32_t*>((dir ? a.mask[1] : a.mask[0]) + b * HW + i) = packed;
 }
 
 // a11 calc_mask_ratio: one block per sample, integer count of zeros (exact), one division.
@@ -379,8 +442,8 @@ static int launch_chain_dm(const float* l0, const float* l1, float* o0, float* o
     a.dw = make_div<DM>((float)(W - 1)); a.dh = make_div<DM>((float)(H - 1));
     a.ndir = ndir;
     dim3 block(32, 8);
-    if (up && n == 1 && !is_norm) {  // W = 8w is a multiple of 4
-        dim3 grid((W / 4 + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
+    if (up && n == 1 && !is_norm) {  // W = 8w is a multiple of 4; H = 8h a multiple of 8
+        dim3 grid((W / 4 + 31) / 32, (H / 8 + 7) / 8, (unsigned)(B * ndir));
         PP_LAUNCH("chain_up", st, upchain1_kernel<DM><<<grid, block, 0, st>>>(a));
         return check_launch("upchain1_kernel");
     }
@@ -421,7 +484,7 @@ static int launch_fb_dm(const float* f0, const float* f1, uint8_t* m0, uint8_t* 
     a.ndir = ndir;
     dim3 block(32, 8);
     if (mask_only4) {
-        dim3 grid((W / 4 + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
+        dim3 grid(W / 128, (H + 7) / 8, (unsigned)(B * ndir));
         PP_LAUNCH("fb", st, fbmask4_kernel<DM><<<grid, block, 0, st>>>(a));
         return check_launch("fbmask4_kernel");
     }
@@ -433,8 +496,7 @@ static int launch_fb_dm(const float* f0, const float* f1, uint8_t* m0, uint8_t* 
 
 static int launch_fb(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, float* cycle, float* coords1, int ndir,
                      int64_t B, int H, int W, double alpha_1, double alpha_2, int is_norm, int div_mode, cudaStream_t st) {
-    const bool mask_only4 = !cycle && !coords1 && !is_norm && (W % 4 == 0) &&
-                            (((uintptr_t)f0 | (uintptr_t)f1 | (uintptr_t)m0 | (uintptr_t)m1) % 16 == 0);
+    const bool mask_only4 = !cycle && !coords1 && !is_norm && (W % 128 == 0) && H >= 2;
     if (div_mode == PP_DIV_RCP)
         return launch_fb_dm<DM_RCP>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, mask_only4, st);
     const bool cert = div_certified((float)(W - 1)) && div_certified((float)(H - 1));
