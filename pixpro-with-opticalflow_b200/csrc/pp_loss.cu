@@ -14,6 +14,7 @@
 #include <math.h>
 
 #include "pp_common.cuh"
+#include "pp_small.cuh"
 
 namespace pp {
 
@@ -296,6 +297,117 @@ __global__ void __launch_bounds__(256) loss_final_kernel(LossWs ws, int64_t B, i
     if (threadIdx.x == 0) loss[0] = (float)(-2.0 * red[0] / (double)B);  // :247
 }
 
+// ---- a8 for small grids (P <= 64): ONE block per sample does stages 1 and 2 ------------------
+// centres + flow warp + positive matrix (as 0/1 floats, transposed) in shared memory, then
+// M = K·posᵀ with the thread-per-channel contraction of pp_small.cuh, the loss partial Σ q∘M and
+// dq, all without leaving the SM.  Same arithmetic as loss_prep_kernel / loss_main_kernel.
+struct SmallLossArgs {
+    PrepArgs p;
+    const float *q, *k;
+    float* dq;
+    int C;
+    float scale;  // -2/B
+};
+
+__host__ __device__ inline size_t small_loss_smem_bytes(int C, int P) {
+    return ((size_t)2 * ((size_t)C * P + SLACK) + (size_t)PMAX * PS + 5 * PMAX + 4 * PMAX + 16) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs sa) {
+    extern __shared__ __align__(16) float smem[];
+    const PrepArgs& a = sa.p;
+    const int C = sa.C, P = a.P, G = a.G, CP = C * P;
+    float* ks = smem;                // k rows, later M
+    float* qs = ks + CP + SLACK;     // q rows
+    float* Pm = qs + CP + SLACK;     // Pm[j][i] = pos(i,j) as 0/1
+    float* qx = Pm + PMAX * PS;
+    float* qy = qx + PMAX;
+    float* kx = qy + PMAX;
+    float* ky = kx + PMAX;
+    float* mgs = ky + PMAX;
+    float* red = mgs + PMAX;       // 4*PMAX scratch
+    float* sc = red + 4 * PMAX;    // [0] md, [1] den
+    const int64_t b = blockIdx.x;
+    const int64_t off = b * (int64_t)C * P;
+    stage_dense(ks, sa.k + off, CP);
+    stage_dense(qs, sa.q + off, CP);
+    for (int e = threadIdx.x; e < PMAX * PS; e += SM_THREADS) Pm[e] = 0.0f;
+    const float* cq = a.coord_q + b * 10;
+    const float* ck = a.coord_k + b * 10;
+    float qbw = a.dG(sub(cq[2], cq[0])), qbh = a.dG(sub(cq[3], cq[1]));  // PixPro.py:140-143
+    float kbw = a.dG(sub(ck[2], ck[0])), kbh = a.dG(sub(ck[3], ck[1]));
+    if (threadIdx.x < P) {
+        const int p = threadIdx.x, x = p % G, y = p / G;
+        float fx = add((float)x, 0.5f), fy = add((float)y, 0.5f);        // :168-175 / :192-199
+        float vqx = mul(add(mul(fx, qbw), cq[0]), a.wo), vqy = mul(add(mul(fy, qbh), cq[1]), a.ho);
+        float vkx = mul(add(mul(fx, kbw), ck[0]), a.wo), vky = mul(add(mul(fy, kbh), ck[1]), a.ho);
+        bool mg = true;
+        if (a.flow) {  // :200
+            int64_t HW = (int64_t)a.warp.Hin * a.warp.Win;
+            float ox, oy;
+            warp_point(a.flow + b * 2 * HW, a.mask ? a.mask + b * HW : nullptr, a.warp, vqx, vqy, ox, oy, mg);
+            vqx = ox;
+            vqy = oy;
+        }
+        qx[p] = vqx; qy[p] = vqy; kx[p] = vkx; ky[p] = vky; mgs[p] = mg ? 1.0f : 0.0f;
+        if (a.centres) {
+            int64_t BP = a.B * P;
+            a.centres[0 * BP + b * P + p] = vqx; a.centres[1 * BP + b * P + p] = vqy;
+            a.centres[2 * BP + b * P + p] = vkx; a.centres[3 * BP + b * P + p] = vky;
+        }
+    }
+    if (threadIdx.x == 0) {  // :155-157
+        float qdw = mul(qbw, a.wo), qdh = mul(qbh, a.ho), kdw = mul(kbw, a.wo), kdh = mul(kbh, a.ho);
+        float qd = __fsqrt_rn(add(mul(qdw, qdw), mul(qdh, qdh)));
+        float kd = __fsqrt_rn(add(mul(kdw, kdw), mul(kdh, kdh)));
+        sc[0] = fmaxf(qd, kd);
+    }
+    __syncthreads();
+    const float md = sc[0];
+    float cnt = 0.0f;
+    for (int e = threadIdx.x; e < P * P; e += SM_THREADS) {
+        int i = e / P, j = e - i * P;
+        bool pos = pair_pos(qx[i], qy[i], kx[j], ky[j], md, a.pr) && (mgs[i] != 0.0f);  // :219-222
+        Pm[j * PS + i] = pos ? 1.0f : 0.0f;
+        cnt += pos ? 1.0f : 0.0f;
+        if (a.pos_mask) a.pos_mask[(b * P + i) * (int64_t)P + j] = pos ? 1 : 0;
+    }
+    red[threadIdx.x] = cnt;  // 4*PMAX = 256 slots
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = 0.0f;
+        for (int u = threadIdx.x; u < SM_THREADS; u += 32) t += red[u];  // small integers: exact in fp32
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) {
+            sc[1] = add(t, 1e-6f);  // :241 fp32 denominator
+            if (a.pos_num) a.pos_num[b] = t;
+            if (a.pos_mean) a.pos_mean[b] = __fdiv_rn(t, (float)(P * P));
+            a.ws.md[b] = md;
+            a.ws.den[b] = sc[1];
+        }
+    }
+    __syncthreads();
+    // M[c][i] = Σ_j k[c][j] pos(i,j)  (in place over the k rows)
+    row_times_mat(ks, Pm, C, P, ks);
+    __syncthreads();
+    const float inv_den = sa.scale / sc[1];  // -2/(B den)
+    float lsum = 0.0f;
+    for (int e = threadIdx.x; e < CP; e += SM_THREADS) {
+        float m = ks[e];
+        lsum = fmaf(qs[e], m, lsum);
+        if (sa.dq) sa.dq[off + e] = m * inv_den;
+    }
+    __syncthreads();
+    red[threadIdx.x] = lsum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = 0.0f;
+        for (int u = threadIdx.x; u < SM_THREADS; u += 32) t += red[u];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) a.ws.partial[b] = t;  // ntile = 1
+    }
+}
+
 }  // namespace pp
 
 using namespace pp;
@@ -343,16 +455,33 @@ int pp_regression_loss(const float* q, const float* k, int64_t B, int C, int G, 
     pa.warp = make_warp_args(flow ? Hin : 2, flow ? Win : 2, H_orig, W_orig, div_mode);
     pa.ws = carve_ws(workspace, B, P);
     pa.pos_num = pos_num; pa.pos_mean = pos_mean; pa.centres = centres; pa.pos_mask = pos_mask; pa.B = B;
-    PP_LAUNCH("loss_prep", st, loss_prep_kernel<<<(unsigned)B, 256, 5 * P * sizeof(float), st>>>(pa));
-    int rc = check_launch("loss_prep_kernel");
-    if (rc) return rc;
-    MainArgs ma;
-    ma.q = q; ma.k = k; ma.dq = dq; ma.ws = pa.ws; ma.C = C; ma.P = P; ma.ntile = loss_ntile(P);
-    ma.pr = pa.pr; ma.scale = (float)(-2.0 / (double)B);
-    PP_LAUNCH("loss_main", st, loss_main_kernel<<<dim3(ma.ntile, (unsigned)B), 256, 0, st>>>(ma));
-    rc = check_launch("loss_main_kernel");
-    if (rc) return rc;
-    PP_LAUNCH("loss_final", st, loss_final_kernel<<<1, 256, 0, st>>>(pa.ws, B, ma.ntile, loss));
+    const float scale = (float)(-2.0 / (double)B);
+    int ntile = loss_ntile(P);
+    int rc;
+    if (P <= PMAX && ((C * P) % 4 == 0) && small_loss_smem_bytes(C, P) <= 226 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(loss_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_set = true;
+        }
+        SmallLossArgs sa;
+        sa.p = pa; sa.q = q; sa.k = k; sa.dq = dq; sa.C = C; sa.scale = scale;
+        ntile = 1;
+        PP_LAUNCH("loss_small", st, loss_small_kernel<<<(unsigned)B, SM_THREADS, small_loss_smem_bytes(C, P), st>>>(sa));
+        rc = check_launch("loss_small_kernel");
+        if (rc) return rc;
+    } else {
+        PP_LAUNCH("loss_prep", st, loss_prep_kernel<<<(unsigned)B, 256, 5 * P * sizeof(float), st>>>(pa));
+        rc = check_launch("loss_prep_kernel");
+        if (rc) return rc;
+        MainArgs ma;
+        ma.q = q; ma.k = k; ma.dq = dq; ma.ws = pa.ws; ma.C = C; ma.P = P; ma.ntile = ntile;
+        ma.pr = pa.pr; ma.scale = scale;
+        PP_LAUNCH("loss_main", st, loss_main_kernel<<<dim3(ma.ntile, (unsigned)B), 256, 0, st>>>(ma));
+        rc = check_launch("loss_main_kernel");
+        if (rc) return rc;
+    }
+    PP_LAUNCH("loss_final", st, loss_final_kernel<<<1, 256, 0, st>>>(pa.ws, B, ntile, loss));
     return check_launch("loss_final_kernel");
 }
 

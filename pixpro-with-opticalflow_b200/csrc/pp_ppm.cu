@@ -17,34 +17,9 @@
 #include <math.h>
 
 #include "pp_common.cuh"
+#include "pp_ppm.cuh"
 
 namespace pp {
-
-constexpr float kNormEps = 1e-12f;
-
-// relu^γ and its derivative (PixPro.py:355-358)
-struct Act {
-    float gamma, cv;
-    int mode;  // 0: γ==1, 1: γ==2, 2: general
-    __device__ __forceinline__ float f(float s) const {
-        float a = fmaxf(s, cv);
-        if (gamma < 1.0f) a += 1e-6f;
-        return mode == 0 ? a : (mode == 1 ? a * a : powf(a, gamma));
-    }
-    __device__ __forceinline__ float df(float s) const {  // d f / d s; torch clamp passes grad where s >= min
-        if (s < cv) return 0.0f;
-        float a = s;
-        if (gamma < 1.0f) a += 1e-6f;
-        return mode == 0 ? 1.0f : (mode == 1 ? 2.0f * a : gamma * powf(a, gamma - 1.0f));
-    }
-};
-static Act make_act(double gamma, double cv) {
-    Act a;
-    a.gamma = (float)gamma;
-    a.cv = (float)cv;
-    a.mode = gamma == 1.0 ? 0 : (gamma == 2.0 ? 1 : 2);
-    return a;
-}
 
 // ---- column norms over C: n[b,i] = max(sqrt(Σ_c u[b,c,i]^2), eps) --------------------------
 // grid (ceil(P/32), B), block (32, 8): threadIdx.x = column, threadIdx.y strides over C.
@@ -286,6 +261,8 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
     cudaStream_t st = (cudaStream_t)stream;
     Saved sv = carve_saved(saved, B, P);
     Act act = make_act(gamma, clamp_value);
+    if (ppm_small_supported(C, P))  // e.g. the 7x7 grid: one block per sample, one launch
+        return ppm_fwd_small(feat, val, B, C, P, act, final_norm, out, sv.nx, sv.nv, sv.ny, sv.S, st);
     dim3 nb((P + 31) / 32, (unsigned)B), nt(32, 8);
     PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(feat, C, P, sv.nx));
     PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(val, C, P, sv.nv));
@@ -315,6 +292,8 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
     cudaStream_t st = (cudaStream_t)stream;
     Saved sv = carve_saved(const_cast<void*>(saved), B, P);
     Act act = make_act(gamma, clamp_value);
+    if (ppm_small_supported(C, P))
+        return ppm_bwd_small(feat, val, out, g, B, C, P, act, final_norm, sv.nx, sv.nv, sv.ny, sv.S, d_feat_sim, d_val, st);
     float* gy = (float*)workspace;
     float* gS = gy + B * (int64_t)C * P;
     float* gvh = gS + B * (int64_t)P * P;

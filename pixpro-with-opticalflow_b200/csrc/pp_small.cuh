@@ -1,0 +1,146 @@
+// pp_small.cuh — building blocks of the one-block-per-sample kernels for small grids
+// (P = G*G <= 64).  Everything lives in shared memory.  [C x P] operands keep the DENSE global
+// layout (row stride P), so a sample is staged with straight float4 copies whose loads are all
+// issued before the first store (one block per SM has only 8 warps: memory-level parallelism
+// has to come from each thread).  P x P matrices use a row stride of PS (float4 rows).
+#pragma once
+#include "pp_common.cuh"
+
+namespace pp {
+
+constexpr int SM_THREADS = 256;
+constexpr int PMAX = 64;
+constexpr int PS = PMAX + 4;   // row stride of the P x P matrices (multiple of 4: float4 rows)
+constexpr int SLACK = 8;       // floats of slack after each [C x P] buffer (4-wide tile reads overrun a row end)
+
+// smem <- global, n floats.  Vector path when n % 4 == 0 and src is 16-byte aligned.
+__device__ __forceinline__ void stage_dense(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int base = 0; base < n4; base += SM_THREADS * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int e = base + u * SM_THREADS + threadIdx.x;
+                if (e < n4) v[u] = __ldg(s4 + e);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int e = base + u * SM_THREADS + threadIdx.x;
+                if (e < n4) d4[e] = v[u];
+            }
+        }
+    } else {
+        for (int e = threadIdx.x; e < n; e += SM_THREADS) dst[e] = __ldg(src + e);
+    }
+}
+
+// column reduction over C of f(row c, column i); result in res[i], i < P.  All threads call.
+template <class F>
+__device__ __forceinline__ void col_reduce(int C, int P, float* red /*[4][PMAX]*/, float* res /*[PMAX]*/, F f) {
+    const int i = threadIdx.x & 63, part = threadIdx.x >> 6;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (i < P) {
+        int c = part;
+        for (; c + 12 < C; c += 16) {  // 4 independent accumulators: loads of f() overlap
+            s0 += f(c, i);
+            s1 += f(c + 4, i);
+            s2 += f(c + 8, i);
+            s3 += f(c + 12, i);
+        }
+        for (; c < C; c += 4) s0 += f(c, i);
+    }
+    red[part * PMAX + i] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.x < PMAX) res[threadIdx.x] = (red[threadIdx.x] + red[PMAX + threadIdx.x]) + (red[2 * PMAX + threadIdx.x] + red[3 * PMAX + threadIdx.x]);
+    __syncthreads();
+}
+
+// M[i][j] = sum_c a[c][i] * b[c][j] for i,j < P (4x4 register tile per thread, 16x16 threads);
+// ep(i, j, value) consumes the result.  Rows are dense (stride P): the 4-wide reads of the last
+// tile run past the row end into the next row (finite data, results discarded).
+template <class EP>
+__device__ __forceinline__ void gram_tile(const float* __restrict__ a, const float* __restrict__ b, int C, int P, EP ep) {
+    const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+    const int i0 = ti * 4, j0 = tj * 4;
+    if (i0 >= P || j0 >= P) return;
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[u][v] = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < C; c++) {
+        const float* ar = a + c * P + i0;
+        const float* br = b + c * P + j0;
+        const float av[4] = {ar[0], ar[1], ar[2], ar[3]}, bv[4] = {br[0], br[1], br[2], br[3]};
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if (i0 + u < P && j0 + v < P) ep(i0 + u, j0 + v, acc[u][v]);
+}
+
+// dst[c][i] = sum_j src[c][j] * M[j][i]   (thread = channel; M rows contiguous, stride PS).
+// All NP*16 output columns of a row are accumulated in registers before anything is written,
+// so dst may alias src (thread-private rows).  Row stride P is odd for odd grids: the per-thread
+// row reads are bank-conflict free; M rows are warp broadcasts.
+template <int NP>
+__device__ __forceinline__ void row_times_mat_np(const float* src, const float* __restrict__ M, int C, int P, float* dst) {
+    for (int c = threadIdx.x; c < C; c += SM_THREADS) {
+        const float* s = src + c * P;
+        float acc[NP][16];
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int u = 0; u < 16; u++) acc[p][u] = 0.0f;
+        for (int j = 0; j < P; j++) {
+            const float sj = s[j];
+            const float4* m4 = reinterpret_cast<const float4*>(M + j * PS);
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 m = m4[4 * p + q];
+                    acc[p][4 * q + 0] = fmaf(sj, m.x, acc[p][4 * q + 0]);
+                    acc[p][4 * q + 1] = fmaf(sj, m.y, acc[p][4 * q + 1]);
+                    acc[p][4 * q + 2] = fmaf(sj, m.z, acc[p][4 * q + 2]);
+                    acc[p][4 * q + 3] = fmaf(sj, m.w, acc[p][4 * q + 3]);
+                }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                if (16 * p + u < P) dst[c * P + 16 * p + u] = acc[p][u];
+    }
+}
+__device__ __forceinline__ void row_times_mat(const float* src, const float* __restrict__ M, int C, int P, float* dst) {
+    if (P <= 16) row_times_mat_np<1>(src, M, C, P, dst);
+    else if (P <= 32) row_times_mat_np<2>(src, M, C, P, dst);
+    else if (P <= 48) row_times_mat_np<3>(src, M, C, P, dst);
+    else row_times_mat_np<4>(src, M, C, P, dst);
+}
+
+// out[e] = fn(e, c, i) for every element of a dense [C x P] tile (e = c*P + i), no divisions:
+// each thread walks its strided elements keeping (c, i) incrementally.
+template <class F>
+__device__ __forceinline__ void for_each_ci(int C, int P, F fn) {
+    int e = threadIdx.x, c = e / P, i = e - c * P;
+    const int dc = SM_THREADS / P, di = SM_THREADS - dc * P;
+    for (; e < C * P; e += SM_THREADS) {
+        fn(e, c, i);
+        c += dc;
+        i += di;
+        if (i >= P) { i -= P; c += 1; }
+    }
+}
+
+}  // namespace pp
