@@ -187,11 +187,13 @@ def run_b200(a):
             ff, fb, mf, mb = ops.flow_stage(t["lo_f"], t["lo_b"], flow_up=True, alpha_1=ALPHA1, alpha_2=ALPHA2)
         else:
             ff = fb = mf = mb = None
-        pred1 = ops.ppm(f1, F.conv2d(f1, w, bias), GAMMA, CLAMP, final_norm=True)
-        pred2 = ops.ppm(f2, F.conv2d(f2, w, bias), GAMMA, CLAMP, final_norm=True)
-        l1, pn1, _ = ops.regression_loss(pred1, t["k2"], t["c1"], t["c2"], POS_RATIO, flow=ff, size=size, mask=mf)
-        l2, pn2, _ = ops.regression_loss(pred2, t["k1"], t["c2"], t["c1"], POS_RATIO, flow=fb, size=size, mask=mb)
-        loss = l1 + l2
+        # as PixPro.forward does: both views through the PPM as one batch, both loss directions in one launch
+        f12 = torch.cat([f1, f2], dim=0)
+        pred1, pred2 = ops.ppm(f12, F.conv2d(f12, w, bias), GAMMA, CLAMP, final_norm=True).chunk(2, dim=0)
+        l12, pn, _ = ops.regression_loss_pair(pred1, t["k2"], t["c1"], t["c2"], pred2, t["k1"], t["c2"], t["c1"], POS_RATIO,
+                                              flow1=ff, flow2=fb, size=size, mask1=mf, mask2=mb)
+        loss = l12[0] + l12[1]
+        pn1, pn2 = pn[0], pn[1]
         loss.backward()
         return loss.detach(), pn1, pn2, f1.grad, f2.grad
 

@@ -111,6 +111,16 @@ PP_API int pp_regression_loss(const float* q, const float* k, int64_t B, int C, 
                        int div_mode, float* loss, float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask,
                        float* centres, void* workspace, void* stream);
 
+/* Both loss directions of PixPro.forward (contrast/models/PixPro.py:429-430) in ONE launch:
+ * every argument that differs between the two regression_loss calls is a table of two
+ * pointers (entries of flow[] / mask[] may be NULL).  Same results as two pp_regression_loss
+ * calls; workspace[i] each pp_regression_loss_workspace(B,G) bytes.                         */
+PP_API int pp_regression_loss_pair(const float* const* q, const float* const* k, int64_t B, int C, int G,
+                                   const float* const* coord_q, const float* const* coord_k, const float* const* flow,
+                                   int Hin, int Win, const uint8_t* const* mask, int H_orig, int W_orig, double pos_ratio,
+                                   int div_mode, float* const* loss, float* const* pos_num, float* const* pos_mean,
+                                   float* const* dq, void* const* workspace, void* stream);
+
 /* ---- a9: PixPro.featprop (+ the caller's F.normalize) — contrast/models/PixPro.py:339-363,380
  * feat,val [B,C,P] (val = value_transform(feat), computed by the caller) -> out [B,C,P].
  * final_norm: also apply the L2 normalisation of PixPro.py:380.  saved: device scratch of

@@ -27,6 +27,8 @@
  *       val = fma(l0y, fma(l0x,a, l1x*b), l1y*fma(l0x,c, l1x*d))   [verified bitwise]
  *   - tensor / python_scalar: true IEEE division on CPU (div_mode 0); torch's CUDA
  *     kernel multiplies by the fp32 reciprocal instead (div_mode 1).
+ *     div_mode 1 reproduces the reference run through torch's NATIVE CUDA kernels (checked
+ *     bitwise on a B200 with cuDNN disabled; cuDNN's own grid sampler rounds differently).
  * Reductions that only feed tolerance-checked floats (q·k logits, PPM contractions,
  * norms) are accumulated in double: the oracle is the more accurate side there.
  */
@@ -75,8 +77,17 @@ static inline float denorm_flow1(float f, int size) {
 
 /* ATen grid_sampler_2d, bilinear, zeros padding, align_corners=True, C channels of one
  * sample.  in: [C,H,W] with channel stride cs; (gx,gy) normalised; out[c] written. */
+/* tap accumulation order of ATen's CPU kernel (and of its native CUDA kernel: same order in the
+ * sm_100 SASS).  cuDNN's sampler, which torch prefers on CUDA when cuDNN is enabled, rounds
+ * differently and is not restated. */
+static inline float tap_combine(float vnw, float vne, float vsw, float vse, float nw, float ne, float sw, float se,
+                                int unused) {
+    (void)unused;
+    return fmaf(vse, se, fmaf(vsw, sw, fmaf(vne, ne, vnw * nw)));
+}
+
 static inline void grid_sample_bilinear_pt(const float* in, long cs, int C, int H, int W,
-                                           float gx, float gy, float* out) {
+                                           float gx, float gy, float* out, int cuda_order) {
     float ix = (gx + 1.0f) * ((float)(W - 1) / 2.0f);
     float iy = (gy + 1.0f) * ((float)(H - 1) / 2.0f);
     float xw = floorf(ix), yn = floorf(iy);
@@ -96,7 +107,7 @@ static inline void grid_sample_bilinear_pt(const float* in, long cs, int C, int 
         float vne = (inx1 && iny0) ? p[y0 * W + x1] : 0.0f;
         float vsw = (inx0 && iny1) ? p[y1 * W + x0] : 0.0f;
         float vse = (inx1 && iny1) ? p[y1 * W + x1] : 0.0f;
-        out[c] = fmaf(vse, se, fmaf(vsw, sw, fmaf(vne, ne, vnw * nw)));
+        out[c] = tap_combine(vnw, vne, vsw, vse, nw, ne, sw, se, cuda_order);
     }
 }
 
@@ -188,7 +199,7 @@ ORC_API void orc_grid_sample_bilinear(const float* in, long N, int C, int H, int
             const float* g = grid + (n * Ho * Wo + i) * 2;
             for (int c0 = 0; c0 < C; c0 += 16) {
                 int cc = C - c0 < 16 ? C - c0 : 16;
-                grid_sample_bilinear_pt(in + (n * C + c0) * (long)H * W, (long)H * W, cc, H, W, g[0], g[1], tmp);
+                grid_sample_bilinear_pt(in + (n * C + c0) * (long)H * W, (long)H * W, cc, H, W, g[0], g[1], tmp, 0);
                 for (int c = 0; c < cc; c++) out[(n * C + c0 + c) * (long)Ho * Wo + i] = tmp[c];
             }
         }
@@ -228,7 +239,7 @@ ORC_API void orc_concat_flow(const float* flows, int n, long B, int H, int W,
                     for (int i = 0; i < n; i++) { /* util.py:321-323 */
                         const float* f = flows + i * stride_n + b * stride_b;
                         float gx = norm_coord1(cx, W, div_mode), gy = norm_coord1(cy, H, div_mode);
-                        grid_sample_bilinear_pt(f, HW, 2, H, W, gx, gy, s);
+                        grid_sample_bilinear_pt(f, HW, 2, H, W, gx, gy, s, div_mode);
                         cx = cx + s[0];
                         cy = cy + s[1];
                     }
@@ -258,7 +269,7 @@ ORC_API void orc_concat_flow(const float* flows, int n, long B, int H, int W,
                             float vne = (inx1 && iny0) ? norm_flow1(p[y0 * W + x1], size, div_mode) : 0.0f;
                             float vsw = (inx0 && iny1) ? norm_flow1(p[y1 * W + x0], size, div_mode) : 0.0f;
                             float vse = (inx1 && iny1) ? norm_flow1(p[y1 * W + x1], size, div_mode) : 0.0f;
-                            s[c] = fmaf(vse, se, fmaf(vsw, sw, fmaf(vne, ne, vnw * nw)));
+                            s[c] = tap_combine(vnw, vne, vsw, vse, nw, ne, sw, se, div_mode);
                         }
                         cx = cx + s[0];
                         cy = cy + s[1];
@@ -325,7 +336,7 @@ ORC_API void orc_fb_consistency(const float* fwd, const float* bwd, long B, int 
                         vsw = norm_flow1(vsw, size, div_mode);
                         vse = norm_flow1(vse, size, div_mode);
                     }
-                    bi[c] = fmaf(vse, se, fmaf(vsw, sw, fmaf(vne, ne, vnw * nw)));
+                    bi[c] = tap_combine(vnw, vne, vsw, vse, nw, ne, sw, se, div_mode);
                 }
                 float cyx = fnx + bi[0], cyy = fny + bi[1];                    /* :279 */
                 float cyc2 = cyx * cyx + cyy * cyy;                            /* :293 */
@@ -369,7 +380,7 @@ ORC_API void orc_add_optical_flow(const float* flow, long B, int Hin, int Win,
             float gx = 2.0f * div_scalar(xg, (float)(W_orig - 1), div_mode) - 1.0f;
             float gy = 2.0f * div_scalar(yg, (float)(H_orig - 1), div_mode) - 1.0f;
             float fg[2];
-            grid_sample_bilinear_pt(flow + b * 2 * HW, HW, 2, Hin, Win, gx, gy, fg); /* :64 */
+            grid_sample_bilinear_pt(flow + b * 2 * HW, HW, 2, Hin, Win, gx, gy, fg, div_mode); /* :64 */
             if (mask_grid) mask_grid[b * P + p] = mask ? grid_sample_nearest_mask(mask + b * HW, Hin, Win, gx, gy) : 1;
             if (diff) { /* :76-80 */
                 float ox = xg * rw + fg[0];

@@ -77,6 +77,19 @@ def regression_loss(q, k, coord_q, coord_k, pos_ratio=0.5):
     return loss, [pos_num, pos_mean]
 
 
+def regression_loss_pair(q1, k1, coord_q1, coord_k1, q2, k2, coord_q2, coord_k2, pos_ratio=0.5):
+    """loss_1 + loss_2 of PixPro.forward (PixPro.py:429-432) in one launch.  Arguments follow
+    regression_loss; returns (loss_1 + loss_2, [[pos_num, pos_mean], [pos_num, pos_mean]])."""
+    if isinstance(coord_q1, tuple):
+        raise NotImplementedError("the --debug image dump of the reference (debug_utils) is out of scope")
+    cq1, ck1, flow1, size1, mask1 = _unpack_coords(coord_q1, coord_k1)
+    cq2, ck2, flow2, size2, mask2 = _unpack_coords(coord_q2, coord_k2)
+    loss, pos_num, pos_mean = _ops.regression_loss_pair(q1, k1, cq1, ck1, q2, k2, cq2, ck2, pos_ratio, flow1=flow1,
+                                                        flow2=flow2, size=size1 if size1 is not None else size2,
+                                                        mask1=mask1, mask2=mask2)
+    return loss[0] + loss[1], [[pos_num[0], pos_mean[0]], [pos_num[1], pos_mean[1]]]
+
+
 def Proj_Head(in_dim=2048, inner_dim=4096, out_dim=256):
     return MLP2d(in_dim, inner_dim, out_dim)
 
@@ -160,13 +173,13 @@ class PixPro(BaseModel):
         return -2. * torch.einsum('nc, nc->n', [x, y]).mean()
 
     def forward(self, im_1, im_2, coord1, coord2, is_update_momentum=True):
-        # online branch (PixPro.py:377-385)
+        # online branch (PixPro.py:377-385).  The two views go through the PPM as ONE batch of 2B
+        # samples (one launch instead of two: each sample is an independent thread block).
         feat_1 = self.encoder(im_1)
         proj_1 = self.projector(feat_1)
-        pred_1 = self._featprop_normalized(proj_1)
         feat_2 = self.encoder(im_2)
         proj_2 = self.projector(feat_2)
-        pred_2 = self._featprop_normalized(proj_2)
+        pred_1, pred_2 = self._featprop_normalized(torch.cat([proj_1, proj_2], dim=0)).chunk(2, dim=0)
 
         ins = self.pixpro_ins_loss_weight > 0.
         if ins:
@@ -187,11 +200,9 @@ class PixPro(BaseModel):
                 proj_instance_1_ng = _ins(self.projector_instance_k(feat_1_ng))
                 proj_instance_2_ng = _ins(self.projector_instance_k(feat_2_ng))
 
-        # pixel-level loss, both directions (PixPro.py:429-432)
-        loss_1 = regression_loss(pred_1, proj_2_ng, coord1, coord2, self.pixpro_pos_ratio)
-        loss_2 = regression_loss(pred_2, proj_1_ng, coord2, coord1, self.pixpro_pos_ratio)
-        loss = loss_1[0] + loss_2[0]
-        pos_num_list = [loss_1[1], loss_2[1]]
+        # pixel-level loss, both directions (PixPro.py:429-432), fused into one launch
+        loss, pos_num_list = regression_loss_pair(pred_1, proj_2_ng, coord1, coord2, pred_2, proj_1_ng, coord2, coord1,
+                                                  self.pixpro_pos_ratio)
 
         if ins:
             loss_instance = self.regression_loss(pred_instance_1, proj_instance_2_ng) + \

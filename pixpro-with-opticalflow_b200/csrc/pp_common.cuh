@@ -179,9 +179,17 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int W, int H, floa
     t.y0 = t.iny0 ? (int)yn : ((t.iny1) ? -1 : 0);
     return t;
 }
-// out = fma(v_se,se, fma(v_sw,sw, fma(v_ne,ne, v_nw*nw)))
+// Tap accumulation of ATen's grid_sampler_2d (CPU kernel, pinned bitwise; the native CUDA kernel
+// has the same order — sm_100 SASS of torch 2.11: @!P0 FFMA acc=nw*v_nw+0; @!P1 FFMA ne; @!P2 sw;
+// @!P3 se):  out = fma(v_se,se, fma(v_sw,sw, fma(v_ne,ne, v_nw*nw))).
+// NOTE: with cuDNN enabled, torch dispatches bilinear/zeros/align_corners=True grid_sample on CUDA
+// to cudnnSpatialTfSamplerForward instead, whose rounding differs (north-east tap first in the
+// interior, another pattern at the frame border; measured on a B200) and is not reproduced here.
+__device__ __forceinline__ float combine4(float vnw, float vne, float vsw, float vse, float nw, float ne, float sw, float se) {
+    return fma_(vse, se, fma_(vsw, sw, fma_(vne, ne, mul(vnw, nw))));
+}
 __device__ __forceinline__ float combine(const Taps& t, float vnw, float vne, float vsw, float vse) {
-    return fma_(vse, t.se, fma_(vsw, t.sw, fma_(vne, t.ne, mul(vnw, t.nw))));
+    return combine4(vnw, vne, vsw, vse, t.nw, t.ne, t.sw, t.se);
 }
 
 // ---- ATen upsample_bilinear2d (align_corners=True) axis taps ------------------------------

@@ -394,10 +394,10 @@ __global__ void __launch_bounds__(256) fbmask4_kernel(FbArgs<DM> a) {
         const float* q1 = ptr_at(q0, W);
         float x00 = __ldg(p0), x01 = __ldg(p0 + 1), x10 = __ldg(p1), x11 = __ldg(p1 + 1);
         float y00 = __ldg(q0), y01 = __ldg(q0 + 1), y10 = __ldg(q1), y11 = __ldg(q1 + 1);
-        float bx = fma_(norm_flow_h(x11, a.dw2), se,
-                        fma_(norm_flow_h(x10, a.dw2), sw, fma_(norm_flow_h(x01, a.dw2), ne, mul(norm_flow_h(x00, a.dw2), nw))));
-        float by = fma_(norm_flow_h(y11, a.dh2), se,
-                        fma_(norm_flow_h(y10, a.dh2), sw, fma_(norm_flow_h(y01, a.dh2), ne, mul(norm_flow_h(y00, a.dh2), nw))));
+        float bx = combine4(norm_flow_h(x00, a.dw2), norm_flow_h(x01, a.dw2), norm_flow_h(x10, a.dw2),
+                                          norm_flow_h(x11, a.dw2), nw, ne, sw, se);
+        float by = combine4(norm_flow_h(y00, a.dh2), norm_flow_h(y01, a.dh2), norm_flow_h(y10, a.dh2),
+                                          norm_flow_h(y11, a.dh2), nw, ne, sw, se);
         float cyx = add(fnx, bx), cyy = add(fny, by);                     // :279
         float cyc2 = add(mul(cyx, cyx), mul(cyy, cyy));                   // :293
         float f2 = add(mul(fnx, fnx), mul(fny, fny));

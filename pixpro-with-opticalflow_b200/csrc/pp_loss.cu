@@ -280,7 +280,13 @@ __global__ void __launch_bounds__(256) loss_main_kernel(MainArgs a) {
 }
 
 // ---- a8 stage 3: deterministic final reduction: loss = -2 mean_b( Σ partial_b / den_b ) ----
-__global__ void __launch_bounds__(256) loss_final_kernel(LossWs ws, int64_t B, int ntile, float* __restrict__ loss) {
+struct FinalArgs {
+    LossWs ws[2];
+    float* loss[2];
+};
+__global__ void __launch_bounds__(256) loss_final_kernel(FinalArgs fa, int64_t B, int ntile) {
+    const LossWs& ws = blockIdx.x ? fa.ws[1] : fa.ws[0];
+    float* loss = blockIdx.x ? fa.loss[1] : fa.loss[0];
     __shared__ double red[256];
     double s = 0.0;
     for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
@@ -308,13 +314,20 @@ struct SmallLossArgs {
     int C;
     float scale;  // -2/B
 };
+// up to two independent calls (the two loss directions of PixPro.forward) in one launch:
+// blocks [0,B) serve seg[0], blocks [B,2B) serve seg[1]
+struct SmallLossArgs2 {
+    SmallLossArgs seg[2];
+    int B;
+};
 
 __host__ __device__ inline size_t small_loss_smem_bytes(int C, int P) {
     return ((size_t)2 * ((size_t)C * P + SLACK) + (size_t)PMAX * PS + 5 * PMAX + 4 * PMAX + 16) * sizeof(float);
 }
 
-__global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs sa) {
+__global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs2 sa2) {
     extern __shared__ __align__(16) float smem[];
+    const SmallLossArgs& sa = ((int)blockIdx.x < sa2.B) ? sa2.seg[0] : sa2.seg[1];
     const PrepArgs& a = sa.p;
     const int C = sa.C, P = a.P, G = a.G, CP = C * P;
     float* ks = smem;                // k rows, later M
@@ -327,7 +340,7 @@ __global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs sa
     float* mgs = ky + PMAX;
     float* red = mgs + PMAX;       // 4*PMAX scratch
     float* sc = red + 4 * PMAX;    // [0] md, [1] den
-    const int64_t b = blockIdx.x;
+    const int64_t b = ((int)blockIdx.x < sa2.B) ? blockIdx.x : blockIdx.x - sa2.B;
     const int64_t off = b * (int64_t)C * P;
     stage_dense(ks, sa.k + off, CP);
     stage_dense(qs, sa.q + off, CP);
@@ -434,28 +447,39 @@ int64_t pp_regression_loss_workspace(int64_t B, int G) {
     return (5 * B * P + 2 * B + B * loss_ntile((int)P)) * (int64_t)sizeof(float);
 }
 
-int pp_regression_loss(const float* q, const float* k, int64_t B, int C, int G, const float* coord_q, const float* coord_k,
-                       const float* flow, int Hin, int Win, const uint8_t* mask, int H_orig, int W_orig, double pos_ratio,
-                       int div_mode, float* loss, float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask,
-                       float* centres, void* workspace, void* stream) {
-    PP_REQUIRE(q && k && coord_q && coord_k && loss && workspace, "pp_regression_loss: null pointer");
-    PP_REQUIRE(B > 0 && B <= 65535 && C > 0 && G > 0, "pp_regression_loss: bad shape B=%lld C=%d G=%d", (long long)B, C, G);
+struct LossCall {
+    const float *q, *k, *coord_q, *coord_k, *flow;
+    const uint8_t* mask;
+    float *loss, *pos_num, *pos_mean, *dq;
+    uint8_t* pos_mask;
+    float* centres;
+    void* workspace;
+};
+
+static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int C, int G, int Hin, int Win, int H_orig,
+                                int W_orig, double pos_ratio, int div_mode, void* stream) {
+    PP_REQUIRE(B > 0 && B <= 32767 && C > 0 && G > 0, "pp_regression_loss: bad shape B=%lld C=%d G=%d", (long long)B, C, G);
     PP_REQUIRE(G * G <= 1024, "pp_regression_loss: grid %dx%d exceeds 1024 cells", G, G);
     PP_REQUIRE(H_orig > 1 && W_orig > 1, "pp_regression_loss: bad original size %dx%d", H_orig, W_orig);
-    PP_REQUIRE(!flow || (Hin > 1 && Win > 1), "pp_regression_loss: bad flow size %dx%d", Hin, Win);
-    PP_REQUIRE(!mask || flow, "pp_regression_loss: mask without flow");
     cudaStream_t st = (cudaStream_t)stream;
     const int P = G * G;
-    PrepArgs pa;
-    pa.coord_q = coord_q; pa.coord_k = coord_k; pa.flow = flow; pa.mask = mask;
-    pa.G = G; pa.P = P;
-    pa.wo = (float)(W_orig - 1); pa.ho = (float)(H_orig - 1);
-    pa.dG = make_div((float)G, div_mode);
-    pa.pr = (float)pos_ratio;
-    pa.warp = make_warp_args(flow ? Hin : 2, flow ? Win : 2, H_orig, W_orig, div_mode);
-    pa.ws = carve_ws(workspace, B, P);
-    pa.pos_num = pos_num; pa.pos_mean = pos_mean; pa.centres = centres; pa.pos_mask = pos_mask; pa.B = B;
     const float scale = (float)(-2.0 / (double)B);
+    PrepArgs pa[2];
+    for (int c = 0; c < ncall; c++) {
+        const LossCall& L = calls[c];
+        PP_REQUIRE(L.q && L.k && L.coord_q && L.coord_k && L.loss && L.workspace, "pp_regression_loss: null pointer");
+        PP_REQUIRE(!L.flow || (Hin > 1 && Win > 1), "pp_regression_loss: bad flow size %dx%d", Hin, Win);
+        PP_REQUIRE(!L.mask || L.flow, "pp_regression_loss: mask without flow");
+        PrepArgs& a = pa[c];
+        a.coord_q = L.coord_q; a.coord_k = L.coord_k; a.flow = L.flow; a.mask = L.mask;
+        a.G = G; a.P = P;
+        a.wo = (float)(W_orig - 1); a.ho = (float)(H_orig - 1);
+        a.dG = make_div((float)G, div_mode);
+        a.pr = (float)pos_ratio;
+        a.warp = make_warp_args(L.flow ? Hin : 2, L.flow ? Win : 2, H_orig, W_orig, div_mode);
+        a.ws = carve_ws(L.workspace, B, P);
+        a.pos_num = L.pos_num; a.pos_mean = L.pos_mean; a.centres = L.centres; a.pos_mask = L.pos_mask; a.B = B;
+    }
     int ntile = loss_ntile(P);
     int rc;
     if (P <= PMAX && ((C * P) % 4 == 0) && small_loss_smem_bytes(C, P) <= 226 * 1024) {
@@ -464,25 +488,60 @@ int pp_regression_loss(const float* q, const float* k, int64_t B, int C, int G, 
             cudaFuncSetAttribute(loss_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             attr_set = true;
         }
-        SmallLossArgs sa;
-        sa.p = pa; sa.q = q; sa.k = k; sa.dq = dq; sa.C = C; sa.scale = scale;
+        SmallLossArgs2 sa2;
+        for (int c = 0; c < ncall; c++) {
+            SmallLossArgs& sa = sa2.seg[c];
+            sa.p = pa[c]; sa.q = calls[c].q; sa.k = calls[c].k; sa.dq = calls[c].dq; sa.C = C; sa.scale = scale;
+        }
+        if (ncall == 1) sa2.seg[1] = sa2.seg[0];
+        sa2.B = (int)B;
         ntile = 1;
-        PP_LAUNCH("loss_small", st, loss_small_kernel<<<(unsigned)B, SM_THREADS, small_loss_smem_bytes(C, P), st>>>(sa));
+        PP_LAUNCH("loss_small", st,
+                  loss_small_kernel<<<(unsigned)(B * ncall), SM_THREADS, small_loss_smem_bytes(C, P), st>>>(sa2));
         rc = check_launch("loss_small_kernel");
         if (rc) return rc;
     } else {
-        PP_LAUNCH("loss_prep", st, loss_prep_kernel<<<(unsigned)B, 256, 5 * P * sizeof(float), st>>>(pa));
-        rc = check_launch("loss_prep_kernel");
-        if (rc) return rc;
-        MainArgs ma;
-        ma.q = q; ma.k = k; ma.dq = dq; ma.ws = pa.ws; ma.C = C; ma.P = P; ma.ntile = ntile;
-        ma.pr = pa.pr; ma.scale = scale;
-        PP_LAUNCH("loss_main", st, loss_main_kernel<<<dim3(ma.ntile, (unsigned)B), 256, 0, st>>>(ma));
-        rc = check_launch("loss_main_kernel");
-        if (rc) return rc;
+        for (int c = 0; c < ncall; c++) {
+            PP_LAUNCH("loss_prep", st, loss_prep_kernel<<<(unsigned)B, 256, 5 * P * sizeof(float), st>>>(pa[c]));
+            rc = check_launch("loss_prep_kernel");
+            if (rc) return rc;
+            MainArgs ma;
+            ma.q = calls[c].q; ma.k = calls[c].k; ma.dq = calls[c].dq; ma.ws = pa[c].ws; ma.C = C; ma.P = P; ma.ntile = ntile;
+            ma.pr = pa[c].pr; ma.scale = scale;
+            PP_LAUNCH("loss_main", st, loss_main_kernel<<<dim3(ma.ntile, (unsigned)B), 256, 0, st>>>(ma));
+            rc = check_launch("loss_main_kernel");
+            if (rc) return rc;
+        }
     }
-    PP_LAUNCH("loss_final", st, loss_final_kernel<<<1, 256, 0, st>>>(pa.ws, B, ntile, loss));
+    FinalArgs fa;
+    for (int c = 0; c < 2; c++) {
+        fa.ws[c] = pa[c < ncall ? c : 0].ws;
+        fa.loss[c] = calls[c < ncall ? c : 0].loss;
+    }
+    PP_LAUNCH("loss_final", st, loss_final_kernel<<<ncall, 256, 0, st>>>(fa, B, ntile));
     return check_launch("loss_final_kernel");
+}
+
+int pp_regression_loss(const float* q, const float* k, int64_t B, int C, int G, const float* coord_q, const float* coord_k,
+                       const float* flow, int Hin, int Win, const uint8_t* mask, int H_orig, int W_orig, double pos_ratio,
+                       int div_mode, float* loss, float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask,
+                       float* centres, void* workspace, void* stream) {
+    LossCall c{q, k, coord_q, coord_k, flow, mask, loss, pos_num, pos_mean, dq, pos_mask, centres, workspace};
+    return regression_loss_impl(&c, 1, B, C, G, Hin, Win, H_orig, W_orig, pos_ratio, div_mode, stream);
+}
+
+int pp_regression_loss_pair(const float* const* q, const float* const* k, int64_t B, int C, int G,
+                            const float* const* coord_q, const float* const* coord_k, const float* const* flow, int Hin,
+                            int Win, const uint8_t* const* mask, int H_orig, int W_orig, double pos_ratio, int div_mode,
+                            float* const* loss, float* const* pos_num, float* const* pos_mean, float* const* dq,
+                            void* const* workspace, void* stream) {
+    PP_REQUIRE(q && k && coord_q && coord_k && flow && mask && loss && pos_num && pos_mean && dq && workspace,
+               "pp_regression_loss_pair: null pointer table");
+    LossCall c[2];
+    for (int i = 0; i < 2; i++)
+        c[i] = LossCall{q[i], k[i], coord_q[i], coord_k[i], flow[i], mask[i], loss[i], pos_num[i], pos_mean[i], dq[i],
+                        nullptr, nullptr, workspace[i]};
+    return regression_loss_impl(c, 2, B, C, G, Hin, Win, H_orig, W_orig, pos_ratio, div_mode, stream);
 }
 
 }  // extern "C"

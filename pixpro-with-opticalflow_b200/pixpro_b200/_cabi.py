@@ -33,6 +33,8 @@ SIGNATURES = {
     "pp_regression_loss_workspace": (_l, [_l, _i]),
     "pp_regression_loss": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _d, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pp_regression_loss_pair": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _d, _i,
+                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     "pp_ppm_saved_bytes": (_l, [_l, _i, _i]),
     "pp_ppm_fwd": (_i, [_vp, _vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _vp]),
     "pp_ppm_bwd_workspace": (_l, [_l, _i, _i]),

@@ -249,6 +249,70 @@ def regression_loss(q, k, coord_q, coord_k, pos_ratio=0.5, flow=None, size=None,
     return _RegressionLoss.apply(q, k.detach(), coord_q, coord_k, flow, mask, size, pos_ratio, debug)
 
 
+class _RegressionLossPair(torch.autograd.Function):
+    """Both directions of the pixel loss (PixPro.py:429-430) in one launch."""
+
+    @staticmethod
+    def forward(ctx, q1, q2, k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2, size, pos_ratio):
+        import ctypes
+        qs = [_f32(q1, "q1"), _f32(q2, "q2")]
+        ks = [_f32(k1, "k1"), _f32(k2, "k2")]
+        cqs = [_f32(cq1, "coord_q1"), _f32(cq2, "coord_q2")]
+        cks = [_f32(ck1, "coord_k1"), _f32(ck2, "coord_k2")]
+        B, C, G, G2 = qs[0].shape
+        assert G == G2 and all(t.shape == qs[0].shape for t in qs + ks) and all(t.shape == (B, 10) for t in cqs + cks)
+        dev = qs[0].device
+        flows = [None if f is None else _f32(f, "flow") for f in (flow1, flow2)]
+        masks = [None if m is None else _mask_u8(m, "mask") for m in (mask1, mask2)]
+        Hin = Win = 0
+        for f in flows:
+            if f is not None:
+                Hin, Win = f.shape[-2:]
+        H_orig, W_orig = size
+        L = _cabi.lib()
+        wsz = L.pp_regression_loss_workspace(B, G)
+        ws = [torch.empty((wsz,), device=dev, dtype=torch.uint8) for _ in range(2)]
+        loss = torch.empty((2,), device=dev, dtype=torch.float32)
+        pos_num = torch.empty((2, B), device=dev, dtype=torch.float32)
+        pos_mean = torch.empty((2, B), device=dev, dtype=torch.float32)
+        dqs = [torch.empty_like(qs[0]), torch.empty_like(qs[1])]
+
+        def table(ts):
+            return (ctypes.c_void_p * 2)(*[None if t is None else t.data_ptr() for t in ts])
+
+        keep = [table(qs), table(ks), table(cqs), table(cks), table(flows), table(masks), table([loss[0:], loss[1:]]),
+                table([pos_num[0], pos_num[1]]), table([pos_mean[0], pos_mean[1]]), table(dqs), table(ws)]
+        ptrs = [ctypes.cast(t, ctypes.c_void_p) for t in keep]
+        with torch.cuda.device(dev):
+            _cabi.check(L.pp_regression_loss_pair(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3], ptrs[4], Hin, Win, ptrs[5],
+                                                  H_orig, W_orig, float(pos_ratio), _div_mode, ptrs[6], ptrs[7], ptrs[8],
+                                                  ptrs[9], ptrs[10], _stream()), "pp_regression_loss_pair")
+        ctx.save_for_backward(dqs[0], dqs[1])
+        ctx.mark_non_differentiable(pos_num, pos_mean)
+        return loss, pos_num, pos_mean
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        dq1, dq2 = ctx.saved_tensors
+        return (dq1 * g_loss[0], dq2 * g_loss[1]) + (None,) * 12
+
+
+def regression_loss_pair(q1, k1, coord_q1, coord_k1, q2, k2, coord_q2, coord_k2, pos_ratio=0.5, flow1=None, flow2=None,
+                         size=None, mask1=None, mask2=None):
+    """Two regression_loss calls (the two directions of PixPro.forward) fused into one launch.
+
+    Returns (loss [2], pos_num [2,B], pos_mean [2,B]); loss[i] equals regression_loss(q_i, k_i, ...)."""
+    if size is None:
+        f = flow1 if flow1 is not None else flow2
+        if f is not None:
+            size = tuple(f.shape[-2:])
+        else:
+            size = (coord_q1[0][9].item(), coord_q1[0][8].item())
+    size = _size_hw(size)
+    return _RegressionLossPair.apply(q1, q2, k1.detach(), k2.detach(), coord_q1, coord_k1, coord_q2, coord_k2, flow1, flow2,
+                                     mask1, mask2, size, pos_ratio)
+
+
 # ------------------------------------------------------------------------------------- PPM --
 
 class _PPM(torch.autograd.Function):

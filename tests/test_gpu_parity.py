@@ -328,3 +328,51 @@ def test_no_cpu_fallback(ops):
     with pytest.raises(PixProB200Error):
         ops.regression_loss(torch.zeros(1, 4, 33, 33, device=DEV), torch.zeros(1, 4, 33, 33, device=DEV),
                             torch.zeros(1, 10, device=DEV), torch.zeros(1, 10, device=DEV), size=(8, 8))
+
+
+# --------------------------------------------------------------------------- fused launches
+
+def test_loss_pair_equals_two_single_calls(ops, synth):
+    B, C, G = 6, 256, 7
+    f1, f2, k1, k2 = [t.to(DEV) for t in synth.features(B, C, G, seed=11)]
+    q1 = torch.nn.functional.normalize(f1, dim=1).requires_grad_(True)
+    q2 = torch.nn.functional.normalize(f2, dim=1).requires_grad_(True)
+    c1, c2 = synth.crop_coords(B, seed=12).to(DEV), synth.crop_coords(B, seed=13).to(DEV)
+    lf, lb = synth.flow_fields(B, 2, seed=14)
+    ff, fb, mf, mb = ops.flow_stage(lf.to(DEV), lb.to(DEV))
+    la, pna, pma = ops.regression_loss(q1, k2, c1, c2, 0.7, flow=ff, size=(720, 1280), mask=mf)
+    lb_, pnb, pmb = ops.regression_loss(q2, k1, c2, c1, 0.7, flow=fb, size=(720, 1280), mask=mb)
+    (la + lb_).backward()
+    g1, g2 = q1.grad.clone(), q2.grad.clone()
+    q1.grad = q2.grad = None
+    l12, pn, pm = ops.regression_loss_pair(q1, k2, c1, c2, q2, k1, c2, c1, 0.7, flow1=ff, flow2=fb, size=(720, 1280),
+                                           mask1=mf, mask2=mb)
+    (l12[0] + l12[1]).backward()
+    assert torch.equal(l12[0], la) and torch.equal(l12[1], lb_)
+    assert torch.equal(pn[0], pna) and torch.equal(pn[1], pnb) and torch.equal(pm[1], pmb)
+    assert torch.equal(q1.grad, g1) and torch.equal(q2.grad, g2)
+
+
+def test_ppm_batched_views_equal_separate_calls(ops, synth):
+    B, C, G = 5, 256, 7
+    f1, f2, _, _ = [t.to(DEV) for t in synth.features(B, C, G, seed=21)]
+    a = ops.ppm(f1, f1, 2.0, 0.0, True)
+    b = ops.ppm(f2, f2, 2.0, 0.0, True)
+    ab = ops.ppm(torch.cat([f1, f2]), torch.cat([f1, f2]), 2.0, 0.0, True)
+    assert torch.equal(ab[:B], a) and torch.equal(ab[B:], b)
+
+
+def test_rcp_mode_matches_oracle_rcp_mode(ops, orc, synth):
+    """The 'torch CUDA' arithmetic mode (scalar division by reciprocal multiply) is restated by the
+    oracle too: kernels and oracle agree bit for bit in it."""
+    f, b = synth.flow_fields(2, 3, seed=77)
+    want = orc.flow_stage(f.numpy(), b.numpy(), div_mode=1)
+    ops.set_div_mode("rcp")
+    try:
+        got = ops.flow_stage(f.to(DEV), b.to(DEV))
+    finally:
+        ops.set_div_mode("ieee")
+    for name, g, w_ in zip(["flow_fwd", "flow_bwd", "mask_fwd", "mask_bwd"], got, want):
+        assert_bits_equal(npy(g), w_, name)
+    ieee = orc.flow_stage(f.numpy(), b.numpy(), div_mode=0)
+    assert (ieee[0] != want[0]).any()   # the two modes are genuinely different arithmetic
