@@ -74,48 +74,72 @@ def algorithmic_bytes(kernel, B, n):
 # ------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    """SM clock and throttle reasons DURING the timed region, polled through NVML every few ms
+    in a thread (nvidia-smi's own loop is too slow for a 20 ms region); falls back to one
+    `nvidia-smi` query per 50 ms if NVML is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows = []
-        self.proc = None
         self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+
+    def _loop_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.samples.append((time.perf_counter(), mhz, mask))
+            time.sleep(0.002)
+
+    def _loop_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [0x8, 0x40, 0x20, 0x4]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                mask = sum(b for b, v in zip(bits, out[2:6]) if v.strip().lower().startswith("active"))
+                self.max_mhz = float(out[1])
+                self.samples.append((time.perf_counter(), float(out[0]), mask))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def _loop(self):
+        try:
+            self._loop_nvml()
+        except Exception:
+            self._loop_smi()
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        time.sleep(0.02)  # let the first sample land before the timed region opens
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(self.NAMES, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        t1 = time.perf_counter()
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        inside = [(m, k) for (t, m, k) in self.samples if self.t0 <= t <= t1] or [(m, k) for (_, m, k) in self.samples[-3:]]
+        mask = 0
+        for _, k in inside:
+            mask |= k
+        return {"sm_mhz": statistics.median([m for m, _ in inside]) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit), "samples": len(inside)}
 
 
 # ------------------------------------------------------------------------------ multi-rank bookkeeping
@@ -232,24 +256,19 @@ def run_b200(a):
     frames_per_s = aggregate_frames_per_s(a.batch, world, a.n_frames, ms_per_step)
 
     # -------- end to end from pinned host buffers ("e2e") --------
-    out_host = {"loss": torch.empty((), dtype=torch.float32).pin_memory(),
-                "pn": torch.empty((2, a.batch), dtype=torch.float32).pin_memory(),
-                "g": torch.empty((2, a.batch, C_FEAT, a.grid, a.grid), dtype=torch.float32).pin_memory()}
+    # through the package's host-buffer entry (pixpro_b200.host_step.HostPixelStep): every step copies
+    # links, crop descriptors, features and keys from pinned host memory and returns loss, positive
+    # counts and the feature gradients to pinned host memory, synchronising before it returns.
+    from pixpro_b200.host_step import HostPixelStep
     e2e_keys = ["feat1", "feat2", "k1", "k2", "c1", "c2"] + (["lo_f", "lo_b"] if use_flow else [])
-    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in e2e_keys)
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    host_in = {k: pinned[k] for k in e2e_keys}
+    hstep = HostPixelStep(dev, a.batch, C_FEAT, a.grid, size=size, gamma=GAMMA, clamp=CLAMP, pos_ratio=POS_RATIO,
+                          alpha1=ALPHA1, alpha2=ALPHA2)
+    h2d = hstep.h2d_bytes(host_in)
+    d2h = hstep.d2h_bytes()
 
     def e2e_step():
-        t = dict(d)
-        for k in e2e_keys:
-            t[k] = pinned[k].to(dev, non_blocking=True)
-        loss, pn1, pn2, g1, g2 = hot_path(t)
-        out_host["loss"].copy_(loss, non_blocking=True)
-        out_host["pn"][0].copy_(pn1, non_blocking=True)
-        out_host["pn"][1].copy_(pn2, non_blocking=True)
-        out_host["g"][0].copy_(g1, non_blocking=True)
-        out_host["g"][1].copy_(g2, non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the caller reads the loss every step
+        hstep(host_in, d["w"], d["bias"])
 
     for _ in range(max(3, a.warmup // 2)):
         e2e_step()
