@@ -129,11 +129,12 @@ def forward_backward_consistency(flow_fwd, flow_bwd, alpha_1=0.01, alpha_2=0.5, 
     return c1, mask.view(torch.bool), cyc
 
 
-def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=False):
+def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=False, use_workspace=True):
     """Flow stage of contrast/util.py:175-248 (use_flow_file, not use_flow_frames), fused.
 
     lo_fwd/lo_bwd: loader layout [B,n,2,h,w].  Returns (flow_fwd, flow_bwd [B,2,H,W],
-    mask_fwd, mask_bwd bool [B,H,W] or None when alpha_1/alpha_2 is None)."""
+    mask_fwd, mask_bwd bool [B,H,W] or None when alpha_1/alpha_2 is None).
+    use_workspace=False forces the scratch-free chain kernel (same bits, slower for n > 1)."""
     f = _f32(lo_fwd, "lo_fwd")
     b = _f32(lo_bwd, "lo_bwd")
     assert f.ndim == 5 and f.shape == b.shape and f.shape[2] == 2, "flow_stage expects [B,n,2,h,w]"
@@ -144,10 +145,13 @@ def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=
     fb = torch.empty((B, 2, H, W), device=f.device, dtype=torch.float32)
     mf = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
     mb = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
+    L = _cabi.lib()
+    wsz = L.pp_flow_stage_workspace(B, n, h, w, int(flow_up)) if use_workspace else 0
+    ws = torch.empty((wsz,), device=f.device, dtype=torch.uint8) if wsz else None
     with torch.cuda.device(f.device):
-        _cabi.check(_cabi.lib().pp_flow_stage(_ptr(f), _ptr(b), B, n, h, w, int(flow_up), int(use_mask),
-                                              float(alpha_1 or 0.0), float(alpha_2 or 0.0), int(is_norm), _div_mode,
-                                              _ptr(ff), _ptr(fb), _ptr(mf), _ptr(mb), _stream()), "pp_flow_stage")
+        _cabi.check(L.pp_flow_stage(_ptr(f), _ptr(b), B, n, h, w, int(flow_up), int(use_mask),
+                                    float(alpha_1 or 0.0), float(alpha_2 or 0.0), int(is_norm), _div_mode,
+                                    _ptr(ff), _ptr(fb), _ptr(mf), _ptr(mb), _ptr(ws), wsz, _stream()), "pp_flow_stage")
     return ff, fb, (mf.view(torch.bool) if use_mask else None), (mb.view(torch.bool) if use_mask else None)
 
 

@@ -63,7 +63,7 @@ def test_argument_validation_needs_no_gpu():
     assert L.pp_upflow8(None, 1, 4, 4, None, None) == 1  # PP_ERR_INVALID
     assert b"null pointer" in L.pp_last_error()
     with pytest.raises(_cabi.PixProB200Error):
-        _cabi.check(L.pp_flow_stage(None, None, 1, 1, 4, 4, 1, 1, 0.01, 0.5, 0, 0, None, None, None, None, None), "pp_flow_stage")
+        _cabi.check(L.pp_flow_stage(None, None, 1, 1, 4, 4, 1, 1, 0.01, 0.5, 0, 0, None, None, None, None, None, 0, None), "pp_flow_stage")
 
 
 def test_wrappers_refuse_cpu_tensors():

@@ -376,3 +376,14 @@ def test_rcp_mode_matches_oracle_rcp_mode(ops, orc, synth):
         assert_bits_equal(npy(g), w_, name)
     ieee = orc.flow_stage(f.numpy(), b.numpy(), div_mode=0)
     assert (ieee[0] != want[0]).any()   # the two modes are genuinely different arithmetic
+
+
+def test_chunked_chain_equals_scratch_free_chain(ops, synth):
+    """n > 1: the L2-chunked path (up-sample a chunk of links once, chain from the dense scratch)
+    and the scratch-free kernel (x8 up-sampling evaluated inside every tap) give the same bits."""
+    f, b = synth.flow_fields(5, 5, seed=91)
+    f, b = f.to(DEV), b.to(DEV)
+    a_ = ops.flow_stage(f, b, use_workspace=True)
+    b_ = ops.flow_stage(f, b, use_workspace=False)
+    for x, y in zip(a_, b_):
+        assert torch.equal(x, y)
