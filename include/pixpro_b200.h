@@ -139,6 +139,12 @@ PP_API int pp_ppm_bwd(const float* feat, const float* val, const float* out, con
                int P, double gamma, double clamp_value, int final_norm, float* d_feat_sim, float* d_val, void* workspace,
                void* stream);
 
+/* ---- tensor-core building block (tcgen05, 3xTF32: fp32-accurate) ----------------------------
+ * C[b] = A[b] * B[b]^T;  A [batch,M,K], B [batch,N,K], C [batch,M,N], all row-major fp32.
+ * The PPM / loss contractions at large grids run on the same kernel with fused loaders; this
+ * entry exposes the bare GEMM for numerics tests and microbenchmarks.                        */
+PP_API int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

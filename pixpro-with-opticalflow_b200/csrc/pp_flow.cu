@@ -207,6 +207,76 @@ __global__ void __launch_bounds__(256) chain_kernel(ChainArgs<DM> a) {
     o[HW] = oy;
 }
 
+// Dense-link chain, 4 pixels per thread (X0 + lane + 32*j: every gather of a warp covers 32
+// consecutive pixels), not normalised, W % 128 == 0.  Interior samples (all four taps inside
+// the frame) take a branch-free path: clamped coordinates, 8 loads off one pointer (immediate
+// offsets when the frame size is a compile-time constant), the four chains of a thread
+// interleaved by the scheduler.  Samples touching the border are recomputed by the fully
+// predicated sample_link (rare, divergent).  Same arithmetic as chain_kernel<false,false,DM>.
+template <int DM, int WC, int HC>
+__global__ void __launch_bounds__(256) chain_dense4_kernel(ChainArgs<DM> a) {
+    const int X0 = blockIdx.x * 128 + threadIdx.x;
+    const int Y = blockIdx.y * 8 + threadIdx.y;
+    const int W = WC ? WC : a.W, H = HC ? HC : a.H, HW = H * W;
+    if (WC) {
+        a.half_w = (float)(WC - 1) / 2.0f; a.half_h = (float)(HC - 1) / 2.0f;
+        a.dw.s = (float)(WC - 1); a.dw.inv = 1.0f / (float)(WC - 1);
+        a.dh.s = (float)(HC - 1); a.dh.inv = 1.0f / (float)(HC - 1);
+    }
+    if (Y >= H) return;
+    const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    const int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const float* links = (dir ? a.links[1] : a.links[0]) + b * a.stride_b;
+    const unsigned xlim = W - 2, ylim = H - 2;
+    float cx[4], cy[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { cx[j] = (float)(X0 + 32 * j); cy[j] = (float)Y; }
+    for (int i = 0; i < a.n; i++) {  // util.py:315-323
+        const float* lp = links + i * a.stride_n;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float gx = norm_coord(cx[j], a.dw), gy = norm_coord(cy[j], a.dh);
+            const float ix = mul(add(gx, 1.0f), a.half_w), iy = mul(add(gy, 1.0f), a.half_h);
+            const float xw = floorf(ix), yn = floorf(iy);
+            const float wgt = sub(ix, xw), e = sub(add(xw, 1.0f), ix), n_ = sub(iy, yn), s_ = sub(add(yn, 1.0f), iy);
+            const float nw = mul(s_, e), ne = mul(s_, wgt), sw = mul(n_, e), se = mul(n_, wgt);
+            const int x0 = (int)xw, y0 = (int)yn;
+            // interior <=> 0 <= x0 <= W-2 and 0 <= y0 <= H-2 (float compares first: huge / NaN coordinates are not interior)
+            const bool interior = (xw >= 0.0f) && (yn >= 0.0f) && ((unsigned)x0 <= xlim) && ((unsigned)y0 <= ylim);
+            const unsigned xc = min((unsigned)x0, xlim), yc = min((unsigned)y0, ylim);
+            const float* p0 = ptr_at(lp, (int)(yc * W + xc));
+            float x00, x01, x10, x11, y00, y01, y10, y11;
+            if (WC) {
+                x00 = __ldg(p0); x01 = __ldg(p0 + 1); x10 = __ldg(p0 + WC); x11 = __ldg(p0 + WC + 1);
+                y00 = __ldg(p0 + WC * HC); y01 = __ldg(p0 + WC * HC + 1); y10 = __ldg(p0 + WC * HC + WC); y11 = __ldg(p0 + WC * HC + WC + 1);
+            } else {
+                const float* p1 = ptr_at(p0, W);
+                const float* q0 = ptr_at(p0, HW);
+                const float* q1 = ptr_at(q0, W);
+                x00 = __ldg(p0); x01 = __ldg(p0 + 1); x10 = __ldg(p1); x11 = __ldg(p1 + 1);
+                y00 = __ldg(q0); y01 = __ldg(q0 + 1); y10 = __ldg(q1); y11 = __ldg(q1 + 1);
+            }
+            float sx = combine4(x00, x01, x10, x11, nw, ne, sw, se);
+            float sy = combine4(y00, y01, y10, y11, nw, ne, sw, se);
+            if (!interior) {
+                DenseLink L{lp, HW, W};
+                float2 sl = sample_link<false>(L, gx, gy, W, H, a.half_w, a.half_h, a.dw, a.dh);
+                sx = sl.x;
+                sy = sl.y;
+            }
+            cx[j] = add(cx[j], sx);
+            cy[j] = add(cy[j], sy);
+        }
+    }
+    float* o = ptr_at((dir ? a.out[1] : a.out[0]) + b * 2 * (int64_t)HW, Y * W + X0);
+    float* oy = ptr_at(o, HW);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        o[32 * j] = sub(cx[j], (float)(X0 + 32 * j));  // util.py:328
+        oy[32 * j] = sub(cy[j], (float)Y);
+    }
+}
+
 // n == 1 with flow_up (the published n_frames=2 setting): the composite IS the up-sampled
 // link.  ATen's bilinear kernel interpolates horizontally first:
 //     val = fma(l0y, T(i0y,X), l1y * T(i1y,X)),   T(r,X) = fma(l0x, L[r][i0x], l1x * L[r][i1x])
@@ -462,6 +532,12 @@ static int launch_chain_dm(const float* l0, const float* l1, float* o0, float* o
         dim3 grid((W / 4 + 31) / 32, (H / 8 + 7) / 8, (unsigned)(B * ndir));
         PP_LAUNCH("chain_up", st, upchain1_kernel<DM><<<grid, block, 0, st>>>(a));
         return check_launch("upchain1_kernel");
+    }
+    if (!up && n > 1 && !is_norm && (W % 128 == 0) && H >= 2) {
+        dim3 grid4(W / 128, (H + 7) / 8, (unsigned)(B * ndir));
+        if (W == 1280 && H == 720) PP_LAUNCH("chain_dense", st, (chain_dense4_kernel<DM, 1280, 720><<<grid4, block, 0, st>>>(a)));
+        else PP_LAUNCH("chain_dense", st, (chain_dense4_kernel<DM, 0, 0><<<grid4, block, 0, st>>>(a)));
+        return check_launch("chain_dense4_kernel");
     }
     dim3 grid((W + 31) / 32, (H + 7) / 8, (unsigned)(B * ndir));
     if (up) {

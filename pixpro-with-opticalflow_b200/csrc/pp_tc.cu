@@ -1,0 +1,56 @@
+// pp_tc.cu — tcgen05 batched GEMM entry used by tests / microbenchmarks:
+// C[b] = A[b] * B[b]^T in fp32 accuracy (3xTF32), A [batch,M,K], B [batch,N,K], C [batch,M,N].
+#include "pp_common.cuh"
+#include "pp_tc.cuh"
+
+namespace pp {
+namespace tc {
+
+struct LoadRowK {  // row-major [rows, K], k contiguous
+    static constexpr bool kRowMajorK = true;
+    const float* p;
+    int rows, K;
+    __device__ __forceinline__ float4 load4(int64_t b, int row, int k) const {
+        if (row >= rows || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* q = p + (b * rows + row) * (int64_t)K + k;
+        if (k + 3 < K && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(q));
+        float4 v;
+        v.x = __ldg(q);
+        v.y = k + 1 < K ? __ldg(q + 1) : 0.f;
+        v.z = k + 2 < K ? __ldg(q + 2) : 0.f;
+        v.w = k + 3 < K ? __ldg(q + 3) : 0.f;
+        return v;
+    }
+};
+
+struct StoreC {
+    float* c;
+    int M, N;
+    __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
+        float* q = c + (b * M + m) * (int64_t)N + n;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (n + i < N) q[i] = v[i];
+    }
+};
+
+}  // namespace tc
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* stream) {
+    PP_REQUIRE(A && B && C, "pp_tc_gemm_nt: null pointer");
+    PP_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "pp_tc_gemm_nt: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    auto kern = tc::tc_gemm_kernel<tc::LoadRowK, tc::LoadRowK, tc::StoreC>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TC_SMEM_BYTES);
+        attr = true;
+    }
+    dim3 grid((N + tc::TN - 1) / tc::TN, (M + tc::TM - 1) / tc::TM, (unsigned)batch);
+    PP_LAUNCH("tc_gemm_nt", st,
+              kern<<<grid, 128, tc::TC_SMEM_BYTES, st>>>(M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N}));
+    return check_launch("tc_gemm_kernel");
+}

@@ -1,0 +1,203 @@
+// pp_tc.cuh — tcgen05 (5th-gen tensor core) building blocks for the dense contractions of the
+// pixel path at large grids (P = G*G >= 128: the 14x14 and 28x28 feature grids).
+//
+// Precision: the path is specified in fp32 with a 1e-5 relative bar, which single-pass TF32
+// (10-bit mantissa) cannot meet.  Every fp32 operand is therefore split into hi = the 19 bits a
+// TF32 tensor core keeps and lo = x - hi (exact), and each logical product is issued as three
+// tcgen05.mma kind::tf32 instructions accumulating into the same TMEM tile:
+//        a*b  ~=  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi        (dropped term ~2^-22 relative)
+// with fp32 accumulation in TMEM — "3xTF32".
+//
+// Data path: operands are staged by the CTA's threads (not TMA: tiles need an elementwise
+// prologue — normalisation, relu^γ, hi/lo split — that TMA cannot apply) into shared memory in
+// the UMMA canonical K-major, no-swizzle layout: 8-row x 16-byte core matrices, core matrices of
+// consecutive 8-row groups SBO bytes apart, the two 16-byte K halves of one instruction LBO bytes
+// apart.  One elected thread issues the MMAs and commits them to an mbarrier; the accumulator
+// tile lives in TMEM (128 lanes x N columns) and is read back with tcgen05.ld for the epilogue.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pp {
+namespace tc {
+
+constexpr int TM = 128;  // accumulator rows  (UMMA M, cta_group::1)
+constexpr int TN = 128;  // accumulator columns (UMMA N)
+constexpr int TK = 32;   // K extent of one staged chunk (fp32 elements) = 4 MMA k-steps of 8
+constexpr uint32_t SBO = 128;             // bytes between 8-row core matrices
+constexpr uint32_t LBO = (TM / 8) * 128 + 16;  // bytes between 16-byte K columns of core matrices (+16: bank spread for row-wise staging)
+constexpr uint32_t TILE_BYTES = (TK / 4) * LBO;  // one staged operand tile (TM == TN)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_NONE
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)(LBO >> 4) << 16;                // leading byte offset, bits [16,30)
+    d |= (uint64_t)(SBO >> 4) << 32;                // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+    return d;                                       // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// tcgen05.commit: the mbarrier is arrived on when all previously issued MMAs of this thread completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a broken pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// hi/lo split of 4 values and store as one 16-byte core-matrix row in each of the two tiles
+__device__ __forceinline__ void split_store(uint8_t* tile_hi, uint8_t* tile_lo, int row, int kchunk, float4 v) {
+    const uint32_t off = (uint32_t)kchunk * LBO + (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16;
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(tile_hi + off) = h;
+    *reinterpret_cast<float4*>(tile_lo + off) = l;
+}
+
+// ---- batched C[b] = A[b] * B[b]^T  (A: M x K, B: N x K, both presented K-major by their loaders)
+// LA/LB::load4(b, row, k) -> 4 consecutive-k values of operand row `row` (zeros out of range);
+// LA/LB::kRowMajorK: true if k is the contiguous index in memory (stage row-wise for coalescing).
+// EP::store16(b, m, n, v): 16 consecutive columns n..n+15 of row m.
+// grid (ceil(N/TN), ceil(M/TM), batch); block 128 threads; dynamic smem 2 stages x 4 tiles.
+constexpr int STAGES = 2;
+constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;
+constexpr uint32_t TC_SMEM_BYTES = STAGES * STAGE_BYTES + 64;
+
+template <class L>
+__device__ __forceinline__ void stage_operand(const L& ld, int64_t b, int row0, int k0, uint8_t* hi, uint8_t* lo) {
+#pragma unroll
+    for (int it = 0; it < (TM * (TK / 4)) / 128; it++) {
+        const int item = it * 128 + threadIdx.x;
+        const int row = L::kRowMajorK ? (item >> 3) : (item & (TM - 1));
+        const int kc = L::kRowMajorK ? (item & 7) : (item >> 7);
+        split_store(hi, lo, row, kc, ld.load4(b, row0 + row, k0 + 4 * kc));
+    }
+}
+
+template <class LA, class LB, class EP>
+__global__ void __launch_bounds__(128) tc_gemm_kernel(int M, int N, int K, LA la, LB lb, EP ep) {
+    extern __shared__ __align__(128) uint8_t tc_smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + STAGES * STAGE_BYTES);  // one per stage
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES);
+    const int64_t b = blockIdx.z;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 2 * TN);  // columns [0,TN): hi*hi sums; [TN,2TN): the small correction terms
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t idesc = make_idesc(TM, TN);
+    const int nchunk = (K + TK - 1) / TK;
+    for (int c = 0; c < nchunk; c++) {
+        const int s = c & 1;
+        uint8_t* st = tc_smem + s * STAGE_BYTES;
+        if (c >= STAGES) mbar_wait(&bars[s], ((c >> 1) - 1) & 1);  // the MMAs that read this stage have completed
+        stage_operand(la, b, m0, c * TK, st, st + TILE_BYTES);
+        stage_operand(lb, b, n0, c * TK, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
+        fence_smem_to_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after_sync();
+            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < TK / 8; kk++) {  // one MMA consumes K = 8 fp32 = two 16-byte columns
+                const uint32_t ko = kk * 2 * LBO;
+                const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+                // The tensor core aligns and truncates addends to the accumulator's exponent, so the
+                // 2^-11-times-smaller correction products are summed in their own accumulator tile
+                // and added to the main one once, in fp32, in the epilogue (measured: 2x lower error).
+                mma_tf32(tmem_d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, acc);
+                mma_tf32(tmem_d + TN, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, acc);
+                mma_tf32(tmem_d + TN, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1u);
+            }
+            mma_commit(&bars[s]);
+        }
+    }
+    {
+        const int cl = nchunk - 1;
+        mbar_wait(&bars[cl & 1], (cl >> 1) & 1);  // commit of the last chunk: every MMA has completed
+        fence_after_sync();
+    }
+    // epilogue: thread t of warp w owns accumulator row 32w + t (TMEM lane), 128 fp32 columns
+    const int m = m0 + warp * 32 + (threadIdx.x & 31);
+    const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int j = 0; j < TN; j += 16) {
+        float v[16], w[16];
+        tmem_ld16(lane_addr + j, v);
+        tmem_ld16(lane_addr + TN + j, w);
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] += w[i];
+        if (m < M && n0 + j < N) ep.store16(b, m, n0 + j, v);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 2 * TN);
+}
+
+}  // namespace tc
+}  // namespace pp

@@ -40,6 +40,7 @@ SIGNATURES = {
     "pp_ppm_fwd": (_i, [_vp, _vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _vp]),
     "pp_ppm_bwd_workspace": (_l, [_l, _i, _i]),
     "pp_ppm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
+    "pp_tc_gemm_nt": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -360,3 +360,19 @@ def ppm(feat, val, gamma=2.0, clamp_value=0.0, final_norm=True):
     """PixPro.featprop after value_transform (contrast/models/PixPro.py:343-363) fused with the
     caller's F.normalize (:380) when final_norm.  feat, val [B,C,H,W] -> [B,C,H,W]."""
     return _PPM.apply(feat, val, gamma, clamp_value, final_norm)
+
+
+# ---------------------------------------------------------------------------- tensor cores --
+
+def tc_gemm_nt(A, B):
+    """C[b] = A[b] @ B[b].T on the tcgen05 tensor cores with 3xTF32 (fp32-accurate).
+    A [batch,M,K], B [batch,N,K] -> [batch,M,N]."""
+    A = _f32(A, "A")
+    B = _f32(B, "B")
+    assert A.ndim == 3 and B.ndim == 3 and A.shape[0] == B.shape[0] and A.shape[2] == B.shape[2]
+    batch, M, K = A.shape
+    N = B.shape[1]
+    C = torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        _cabi.check(_cabi.lib().pp_tc_gemm_nt(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, _stream()), "pp_tc_gemm_nt")
+    return C
