@@ -15,9 +15,11 @@
 // normalised copy of x or v is ever written.  Column norms use one warp-shuffle reduction
 // kernel.  saved = [nx | nv | ny | S] per batch (3·B·P + B·P·P floats).
 #include <math.h>
+#include <stdlib.h>
 
 #include "pp_common.cuh"
 #include "pp_ppm.cuh"
+#include "pp_tc.cuh"
 
 namespace pp {
 
@@ -218,6 +220,125 @@ struct EpGradS {  // gS[b,i,j] = v * A'(S[b,i,j])
     }
 };
 
+// ---- tensor-core route for large grids (tcgen05 3xTF32, pp_tc.cuh) --------------------------------
+// Specialised operand loaders for the tensor-core route (operands are pre-normalised once by
+// coldiv_kernel, so loads are plain vector / coalesced accesses without divisions).
+struct TcLdT {  // transposed: operand row = spatial index i, k = channel c; memory [C][P] (i contiguous)
+    static constexpr bool kRowMajorK = false;
+    const float* p;
+    int C, P;
+    __device__ __forceinline__ float4 load4(int64_t b, int i, int c) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < P) {
+            const float* q = p + (b * C + c) * (int64_t)P + i;
+            if (c < C) v.x = __ldg(q);
+            if (c + 1 < C) v.y = __ldg(q + P);
+            if (c + 2 < C) v.z = __ldg(q + 2 * (int64_t)P);
+            if (c + 3 < C) v.w = __ldg(q + 3 * (int64_t)P);
+        }
+        return v;
+    }
+};
+__device__ __forceinline__ float4 ldg4_guard(const float* q, int k, int K) {  // 4 consecutive values, zero beyond K
+    if (k + 3 < K && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(q));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K) v.x = __ldg(q);
+    if (k + 1 < K) v.y = __ldg(q + 1);
+    if (k + 2 < K) v.z = __ldg(q + 2);
+    if (k + 3 < K) v.w = __ldg(q + 3);
+    return v;
+}
+struct TcLdN {  // natural: memory [rows][K], k contiguous
+    static constexpr bool kRowMajorK = true;
+    const float* p;
+    int rows, K;
+    __device__ __forceinline__ float4 load4(int64_t b, int row, int k) const {
+        if (row >= rows || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return ldg4_guard(p + (b * rows + row) * (int64_t)K + k, k, K);
+    }
+};
+struct TcLdActN {  // relu^γ(S[row][k..k+3])  (S symmetric: also serves A[k][row])
+    static constexpr bool kRowMajorK = true;
+    const float* S;
+    int P;
+    Act act;
+    __device__ __forceinline__ float4 load4(int64_t b, int row, int k) const {
+        if (row >= P || k >= P) return make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = ldg4_guard(S + (b * P + row) * (int64_t)P + k, k, P);
+        v.x = act.f(v.x);
+        v.y = k + 1 < P ? act.f(v.y) : 0.f;
+        v.z = k + 2 < P ? act.f(v.z) : 0.f;
+        v.w = k + 3 < P ? act.f(v.w) : 0.f;
+        return v;
+    }
+};
+struct TcLdSymN {  // gS[row][k..k+3] + gS[k..k+3][row]
+    static constexpr bool kRowMajorK = true;
+    const float* gS;
+    int P;
+    __device__ __forceinline__ float4 load4(int64_t b, int row, int k) const {
+        if (row >= P || k >= P) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* base = gS + b * (int64_t)P * P;
+        float4 v = ldg4_guard(base + row * (int64_t)P + k, k, P);
+        v.x += __ldg(base + k * (int64_t)P + row);
+        if (k + 1 < P) v.y += __ldg(base + (k + 1) * (int64_t)P + row);
+        if (k + 2 < P) v.z += __ldg(base + (k + 2) * (int64_t)P + row);
+        if (k + 3 < P) v.w += __ldg(base + (k + 3) * (int64_t)P + row);
+        return v;
+    }
+};
+struct TcStN {  // out[b][m][n..n+15]
+    float* out;
+    int M, N;
+    __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
+        float* q = out + (b * M + m) * (int64_t)N + n;
+        if (n + 15 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (n + i < N) q[i] = v[i];
+        }
+    }
+};
+struct TcStGradS {  // gS[b][i][j] = v * A'(S[b][i][j])
+    float* gS;
+    const float* S;
+    int P;
+    Act act;
+    __device__ __forceinline__ void store16(int64_t b, int i, int j, const float v[16]) const {
+        const int64_t o = (b * P + i) * (int64_t)P + j;
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+            if (j + u < P) gS[o + u] = v[u] * act.df(__ldg(S + o + u));
+    }
+};
+
+template <class LA, class LB, class EP>
+static int launch_tc(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
+    auto kern = tc::tc_gemm_kernel<LA, LB, EP>;
+    static bool attr = false;  // one flag per template instantiation
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TC_SMEM_BYTES);
+        attr = true;
+    }
+    dim3 grid((N + tc::TN - 1) / tc::TN, (M + tc::TM - 1) / tc::TM, (unsigned)B);
+    PP_LAUNCH(what, st, kern<<<grid, tc::TC_THREADS, tc::TC_SMEM_BYTES, st>>>(M, N, K, la, lb, ep));
+    return check_launch(what);
+}
+
+// Grids of 14x14 and up (P >= 128) are large enough to fill 128-row tensor-core tiles
+// (BASELINE.json north_star); PIXPRO_B200_NO_TC=1 forces the CUDA-core path for A/B runs.
+static bool use_tensor_cores(int P) {
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char* e = getenv("PIXPRO_B200_NO_TC");
+        disabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    return !disabled && P >= 128;
+}
+
 template <class LA, class LB, class EP>
 static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (unsigned)B);
@@ -226,15 +347,17 @@ static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la,
 }
 
 struct Saved {
-    float *nx, *nv, *ny, *S;
+    float *nx, *nv, *ny, *S, *xh, *vh;  // xh, vh: normalised operands (generic path only)
 };
-static Saved carve_saved(void* p, int64_t B, int P) {
+static Saved carve_saved(void* p, int64_t B, int C, int P) {
     Saved s;
     float* f = (float*)p;
     s.nx = f; f += B * P;
     s.nv = f; f += B * P;
     s.ny = f; f += B * P;
-    s.S = f;
+    s.S = f; f += B * (int64_t)P * P;
+    s.xh = f; f += B * (int64_t)C * P;
+    s.vh = f;
     return s;
 }
 
@@ -245,8 +368,9 @@ using namespace pp;
 extern "C" {
 
 int64_t pp_ppm_saved_bytes(int64_t B, int C, int P) {
-    (void)C;
-    return (3 * B * P + B * (int64_t)P * P) * (int64_t)sizeof(float);
+    int64_t f = 3 * B * P + B * (int64_t)P * P;
+    if (!ppm_small_supported(C, P)) f += 2 * B * (int64_t)C * P;  // normalised operands kept for the backward contractions
+    return f * (int64_t)sizeof(float);
 }
 
 int64_t pp_ppm_bwd_workspace(int64_t B, int C, int P) {
@@ -259,7 +383,7 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
     PP_REQUIRE(feat && val && out && saved, "pp_ppm_fwd: null pointer");
     PP_REQUIRE(B > 0 && B <= 65535 && C > 0 && P > 0, "pp_ppm_fwd: bad shape B=%lld C=%d P=%d", (long long)B, C, P);
     cudaStream_t st = (cudaStream_t)stream;
-    Saved sv = carve_saved(saved, B, P);
+    Saved sv = carve_saved(saved, B, C, P);
     Act act = make_act(gamma, clamp_value);
     if (ppm_small_supported(C, P))  // e.g. the 7x7 grid: one block per sample, one launch
         return ppm_fwd_small(feat, val, B, C, P, act, final_norm, out, sv.nx, sv.nv, sv.ny, sv.S, st);
@@ -269,15 +393,26 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
     int rc = check_launch("colnorm_kernel");
     if (rc) return rc;
     // S[i][j] = Σ_c x̂[c][i] x̂[c][j]
-    rc = launch_bgemm("ppm S", B, P, P, C, LoadColScaled{feat, sv.nx, C, P}, LoadColScaled{feat, sv.nx, C, P},
-                      EpStore{sv.S, P, P}, st);
-    if (rc) return rc;
-    // Y[c][i] = Σ_j v̂[c][j] A[i][j]
-    rc = launch_bgemm("ppm Y", B, C, P, P, LoadRowScaled{val, sv.nv, C, P}, LoadActS{sv.S, P, act}, EpStore{out, C, P}, st);
-    if (rc) return rc;
+    const int64_t total = B * (int64_t)C * P;
+    if (use_tensor_cores(P)) {
+        // normalise once (x̂, v̂ kept for backward), then the two contractions on the tensor cores
+        PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, sv.nx, C, P, total, sv.xh));
+        PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(val, sv.nv, C, P, total, sv.vh));
+        rc = check_launch("ppm coldiv");
+        if (rc) return rc;
+        rc = launch_tc("ppm S (tcgen05)", B, P, P, C, TcLdT{sv.xh, C, P}, TcLdT{sv.xh, C, P}, TcStN{sv.S, P, P}, st);
+        if (rc) return rc;
+        rc = launch_tc("ppm Y (tcgen05)", B, C, P, P, TcLdN{sv.vh, C, P}, TcLdActN{sv.S, P, act}, TcStN{out, C, P}, st);
+        if (rc) return rc;
+    } else {
+        rc = launch_bgemm("ppm S", B, P, P, C, LoadColScaled{feat, sv.nx, C, P}, LoadColScaled{feat, sv.nx, C, P},
+                          EpStore{sv.S, P, P}, st);
+        if (rc) return rc;
+        rc = launch_bgemm("ppm Y", B, C, P, P, LoadRowScaled{val, sv.nv, C, P}, LoadActS{sv.S, P, act}, EpStore{out, C, P}, st);
+        if (rc) return rc;
+    }
     if (final_norm) {
         PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(out, C, P, sv.ny));
-        int64_t total = B * (int64_t)C * P;
         PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, sv.ny, C, P, total, out));
         rc = check_launch("ppm final normalize");
     }
@@ -290,7 +425,7 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
     PP_REQUIRE(feat && val && out && g && saved && d_feat_sim && d_val && workspace, "pp_ppm_bwd: null pointer");
     PP_REQUIRE(B > 0 && B <= 65535 && C > 0 && P > 0, "pp_ppm_bwd: bad shape B=%lld C=%d P=%d", (long long)B, C, P);
     cudaStream_t st = (cudaStream_t)stream;
-    Saved sv = carve_saved(const_cast<void*>(saved), B, P);
+    Saved sv = carve_saved(const_cast<void*>(saved), B, C, P);
     Act act = make_act(gamma, clamp_value);
     if (ppm_small_supported(C, P))
         return ppm_bwd_small(feat, val, out, g, B, C, P, act, final_norm, sv.nx, sv.nv, sv.ny, sv.S, d_feat_sim, d_val, st);
@@ -308,13 +443,24 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
         gyp = gy;
     }
     // gS[i][j] = (Σ_c gy[c][i] v̂[c][j]) A'(S[i][j])
+    if (use_tensor_cores(P)) {
+        rc = launch_tc("ppm gS (tcgen05)", B, P, P, C, TcLdT{gyp, C, P}, TcLdT{sv.vh, C, P}, TcStGradS{gS, sv.S, P, act}, st);
+        if (rc) return rc;
+        // gv̂[c][j] = Σ_i gy[c][i] A[i][j]; A is symmetric, so the B operand row j reads S[j][:] contiguously
+        rc = launch_tc("ppm gvh (tcgen05)", B, C, P, P, TcLdN{gyp, C, P}, TcLdActN{sv.S, P, act}, TcStN{gvh, C, P}, st);
+        if (rc) return rc;
+        rc = launch_tc("ppm gxh (tcgen05)", B, C, P, P, TcLdN{sv.xh, C, P}, TcLdSymN{gS, P}, TcStN{gxh, C, P}, st);
+        if (rc) return rc;
+        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gxh, sv.xh, nullptr, sv.nx, C, P, d_feat_sim));
+        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gvh, sv.vh, nullptr, sv.nv, C, P, d_val));
+        return check_launch("ppm normbwd(in)");
+    }
+    // gS[i][j] = (Σ_c gy[c][i] v̂[c][j]) A'(S[i][j])
     rc = launch_bgemm("ppm gS", B, P, P, C, LoadColScaled{gyp, nullptr, C, P}, LoadColScaled{val, sv.nv, C, P},
                       EpGradS{gS, sv.S, P, act}, st);
     if (rc) return rc;
-    // gv̂[c][j] = Σ_i gy[c][i] A[i][j]
     rc = launch_bgemm("ppm gvh", B, C, P, P, LoadRowScaled{gyp, nullptr, C, P}, LoadActS_T{sv.S, P, act}, EpStore{gvh, C, P}, st);
     if (rc) return rc;
-    // gx̂[c][i] = Σ_j x̂[c][j] (gS[i][j] + gS[j][i])
     rc = launch_bgemm("ppm gxh", B, C, P, P, LoadRowScaled{feat, sv.nx, C, P}, LoadSym{gS, P}, EpStore{gxh, C, P}, st);
     if (rc) return rc;
     PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gxh, feat, sv.nx, sv.nx, C, P, d_feat_sim));

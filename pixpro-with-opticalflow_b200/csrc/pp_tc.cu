@@ -51,6 +51,6 @@ extern "C" int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t b
     }
     dim3 grid((N + tc::TN - 1) / tc::TN, (M + tc::TM - 1) / tc::TM, (unsigned)batch);
     PP_LAUNCH("tc_gemm_nt", st,
-              kern<<<grid, 128, tc::TC_SMEM_BYTES, st>>>(M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N}));
+              kern<<<grid, tc::TC_THREADS, tc::TC_SMEM_BYTES, st>>>(M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N}));
     return check_launch("tc_gemm_kernel");
 }

@@ -117,24 +117,43 @@ __device__ __forceinline__ void split_store(uint8_t* tile_hi, uint8_t* tile_lo, 
 // LA/LB::load4(b, row, k) -> 4 consecutive-k values of operand row `row` (zeros out of range);
 // LA/LB::kRowMajorK: true if k is the contiguous index in memory (stage row-wise for coalescing).
 // EP::store16(b, m, n, v): 16 consecutive columns n..n+15 of row m.
-// grid (ceil(N/TN), ceil(M/TM), batch); block 128 threads; dynamic smem 2 stages x 4 tiles.
+// grid (ceil(N/TN), ceil(M/TM), batch); block 256 threads (8 warps stage operands, warps 0-3 run
+// the epilogue, thread 0 issues the MMAs); dynamic smem = 2 stages x 4 tiles.
+// Pipeline: the global loads of chunk c+1 are issued into registers before chunk c is split and
+// stored, so their latency hides behind the store phase, the barrier and the tensor-core work.
 constexpr int STAGES = 2;
+constexpr int TC_THREADS = 256;
+constexpr int ITEMS = (TM * (TK / 4)) / TC_THREADS;  // float4 items per thread per operand per chunk (= 4)
 constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;
 constexpr uint32_t TC_SMEM_BYTES = STAGES * STAGE_BYTES + 64;
 
 template <class L>
-__device__ __forceinline__ void stage_operand(const L& ld, int64_t b, int row0, int k0, uint8_t* hi, uint8_t* lo) {
+__device__ __forceinline__ void item_coords(int it, int& row, int& kc) {
+    const int item = it * TC_THREADS + threadIdx.x;
+    row = L::kRowMajorK ? (item >> 3) : (item & (TM - 1));
+    kc = L::kRowMajorK ? (item & 7) : (item >> 7);
+}
+template <class L>
+__device__ __forceinline__ void load_operand(const L& ld, int64_t b, int row0, int k0, float4 r[ITEMS]) {
 #pragma unroll
-    for (int it = 0; it < (TM * (TK / 4)) / 128; it++) {
-        const int item = it * 128 + threadIdx.x;
-        const int row = L::kRowMajorK ? (item >> 3) : (item & (TM - 1));
-        const int kc = L::kRowMajorK ? (item & 7) : (item >> 7);
-        split_store(hi, lo, row, kc, ld.load4(b, row0 + row, k0 + 4 * kc));
+    for (int it = 0; it < ITEMS; it++) {
+        int row, kc;
+        item_coords<L>(it, row, kc);
+        r[it] = ld.load4(b, row0 + row, k0 + 4 * kc);
+    }
+}
+template <class L>
+__device__ __forceinline__ void store_operand(const float4 r[ITEMS], uint8_t* hi, uint8_t* lo) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        int row, kc;
+        item_coords<L>(it, row, kc);
+        split_store(hi, lo, row, kc, r[it]);
     }
 }
 
 template <class LA, class LB, class EP>
-__global__ void __launch_bounds__(128) tc_gemm_kernel(int M, int N, int K, LA la, LB lb, EP ep) {
+__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(int M, int N, int K, LA la, LB lb, EP ep) {
     extern __shared__ __align__(128) uint8_t tc_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + STAGES * STAGE_BYTES);  // one per stage
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES);
@@ -152,12 +171,20 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(int M, int N, int K, LA la
     const uint32_t tmem_d = *tmem_slot;
     const uint32_t idesc = make_idesc(TM, TN);
     const int nchunk = (K + TK - 1) / TK;
+    float4 ra[ITEMS], rb[ITEMS];
+    load_operand(la, b, m0, 0, ra);
+    load_operand(lb, b, n0, 0, rb);
     for (int c = 0; c < nchunk; c++) {
         const int s = c & 1;
         uint8_t* st = tc_smem + s * STAGE_BYTES;
+        float4 na[ITEMS], nb[ITEMS];
+        if (c + 1 < nchunk) {  // prefetch the next chunk into registers
+            load_operand(la, b, m0, (c + 1) * TK, na);
+            load_operand(lb, b, n0, (c + 1) * TK, nb);
+        }
         if (c >= STAGES) mbar_wait(&bars[s], ((c >> 1) - 1) & 1);  // the MMAs that read this stage have completed
-        stage_operand(la, b, m0, c * TK, st, st + TILE_BYTES);
-        stage_operand(lb, b, n0, c * TK, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
+        store_operand<LA>(ra, st, st + TILE_BYTES);
+        store_operand<LB>(rb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
         fence_smem_to_async();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -176,23 +203,29 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(int M, int N, int K, LA la
             }
             mma_commit(&bars[s]);
         }
+        if (c + 1 < nchunk) {
+#pragma unroll
+            for (int it = 0; it < ITEMS; it++) { ra[it] = na[it]; rb[it] = nb[it]; }
+        }
     }
     {
         const int cl = nchunk - 1;
         mbar_wait(&bars[cl & 1], (cl >> 1) & 1);  // commit of the last chunk: every MMA has completed
         fence_after_sync();
     }
-    // epilogue: thread t of warp w owns accumulator row 32w + t (TMEM lane), 128 fp32 columns
-    const int m = m0 + warp * 32 + (threadIdx.x & 31);
-    const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    // epilogue (warps 0-3): thread t of warp w owns accumulator row 32w + t (TMEM lane)
+    if (warp < 4) {
+        const int m = m0 + warp * 32 + (threadIdx.x & 31);
+        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (int j = 0; j < TN; j += 16) {
-        float v[16], w[16];
-        tmem_ld16(lane_addr + j, v);
-        tmem_ld16(lane_addr + TN + j, w);
+        for (int j = 0; j < TN; j += 16) {
+            float v[16], w[16];
+            tmem_ld16(lane_addr + j, v);
+            tmem_ld16(lane_addr + TN + j, w);
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] += w[i];
-        if (m < M && n0 + j < N) ep.store16(b, m, n0 + j, v);
+            for (int i = 0; i < 16; i++) v[i] += w[i];
+            if (m < M && n0 + j < N) ep.store16(b, m, n0 + j, v);
+        }
     }
     fence_before_sync();
     __syncthreads();
