@@ -15,6 +15,7 @@
 
 #include "pp_common.cuh"
 #include "pp_small.cuh"
+#include "pp_tc.cuh"
 
 namespace pp {
 
@@ -93,6 +94,8 @@ __global__ void __launch_bounds__(128) add_flow_kernel(const float* __restrict__
 // partial[B,ntile].
 struct LossWs {
     float *cqx, *cqy, *ckx, *cky, *mg, *md, *den, *partial;
+    int* rowcnt;     // [B,P] positives per query cell        (large-grid path)
+    uint8_t* posb;   // [B,P,P] positive matrix as bytes       (large-grid path)
 };
 static int loss_ntile(int P) { return (P + 6) / 7; }
 static LossWs carve_ws(void* ws, int64_t B, int P) {
@@ -105,7 +108,9 @@ static LossWs carve_ws(void* ws, int64_t B, int P) {
     w.mg = f; f += B * P;
     w.md = f; f += B;
     w.den = f; f += B;
-    w.partial = f;
+    w.partial = f; f += B * loss_ntile(P);
+    w.rowcnt = reinterpret_cast<int*>(f); f += B * P;
+    w.posb = reinterpret_cast<uint8_t*>(f);
     return w;
 }
 
@@ -303,6 +308,134 @@ __global__ void __launch_bounds__(256) loss_final_kernel(FinalArgs fa, int64_t B
     if (threadIdx.x == 0) loss[0] = (float)(-2.0 * red[0] / (double)B);  // :247
 }
 
+// ---- a8 for large grids (P > 64: 14x14, 28x28): tensor-core contraction ------------------------
+// centres/warp per sample -> positive matrix as bytes + exact row counts (parallel over rows) ->
+// denominators -> M = K posᵀ on the tcgen05 kernel (0/1 operand: exact in TF32) scaled to dq in
+// the epilogue -> per-sample Σ q∘dq.  Same arithmetic for every boolean as the small path.
+__global__ void __launch_bounds__(256) loss_centres_kernel(PrepArgs a) {
+    const int P = a.P, G = a.G;
+    const int64_t b = blockIdx.x;
+    const float* cq = a.coord_q + b * 10;
+    const float* ck = a.coord_k + b * 10;
+    float qbw = a.dG(sub(cq[2], cq[0])), qbh = a.dG(sub(cq[3], cq[1]));
+    float kbw = a.dG(sub(ck[2], ck[0])), kbh = a.dG(sub(ck[3], ck[1]));
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        int x = p % G, y = p / G;
+        float fx = add((float)x, 0.5f), fy = add((float)y, 0.5f);
+        float vqx = mul(add(mul(fx, qbw), cq[0]), a.wo), vqy = mul(add(mul(fy, qbh), cq[1]), a.ho);
+        float vkx = mul(add(mul(fx, kbw), ck[0]), a.wo), vky = mul(add(mul(fy, kbh), ck[1]), a.ho);
+        bool mg = true;
+        if (a.flow) {
+            int64_t HW = (int64_t)a.warp.Hin * a.warp.Win;
+            float ox, oy;
+            warp_point(a.flow + b * 2 * HW, a.mask ? a.mask + b * HW : nullptr, a.warp, vqx, vqy, ox, oy, mg);
+            vqx = ox;
+            vqy = oy;
+        }
+        a.ws.cqx[b * P + p] = vqx; a.ws.cqy[b * P + p] = vqy;
+        a.ws.ckx[b * P + p] = vkx; a.ws.cky[b * P + p] = vky;
+        a.ws.mg[b * P + p] = mg ? 1.0f : 0.0f;
+        if (a.centres) {
+            int64_t BP = a.B * P;
+            a.centres[0 * BP + b * P + p] = vqx; a.centres[1 * BP + b * P + p] = vqy;
+            a.centres[2 * BP + b * P + p] = vkx; a.centres[3 * BP + b * P + p] = vky;
+        }
+    }
+    if (threadIdx.x == 0) {
+        float qdw = mul(qbw, a.wo), qdh = mul(qbh, a.ho), kdw = mul(kbw, a.wo), kdh = mul(kbh, a.ho);
+        float qd = __fsqrt_rn(add(mul(qdw, qdw), mul(qdh, qdh)));
+        float kd = __fsqrt_rn(add(mul(kdw, kdw), mul(kdh, kdh)));
+        a.ws.md[b] = fmaxf(qd, kd);
+    }
+}
+
+// grid (ceil(P/8), B); warp w of the block owns query cell i = 8*blockIdx.x + w
+__global__ void __launch_bounds__(256) loss_pos_kernel(LossWs ws, int P, float pr, uint8_t* posb) {
+    const int64_t b = blockIdx.y;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= P) return;
+    const float qx = ws.cqx[b * P + i], qy = ws.cqy[b * P + i], md = ws.md[b];
+    const bool mg = ws.mg[b * P + i] != 0.0f;
+    const float* kx = ws.ckx + b * P;
+    const float* ky = ws.cky + b * P;
+    uint8_t* row = posb + (b * P + i) * (int64_t)P;
+    int cnt = 0;
+    for (int j = lane; j < P; j += 32) {
+        bool pos = mg && pair_pos(qx, qy, kx[j], ky[j], md, pr);
+        row[j] = pos ? 1 : 0;
+        cnt += pos;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) ws.rowcnt[b * P + i] = cnt;
+}
+
+__global__ void __launch_bounds__(256) loss_cnt_kernel(LossWs ws, int P, float* pos_num, float* pos_mean) {
+    __shared__ int red[256];
+    const int64_t b = blockIdx.x;
+    int c = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) c += ws.rowcnt[b * P + i];
+    red[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float fc = (float)red[0];
+        ws.den[b] = add(fc, 1e-6f);  // PixPro.py:241 fp32 denominator
+        if (pos_num) pos_num[b] = fc;
+        if (pos_mean) pos_mean[b] = __fdiv_rn(fc, (float)(P * P));
+    }
+}
+
+struct TcLdPos {  // B operand: row = query cell i, k = key cell j; bytes -> 0/1 floats (exact in TF32)
+    static constexpr bool kRowMajorK = true;
+    const uint8_t* posb;
+    int P;
+    __device__ __forceinline__ float4 load4(int64_t b, int i, int j) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < P && j < P) {
+            const uint8_t* q = posb + (b * P + i) * (int64_t)P + j;
+            v.x = (float)q[0];
+            if (j + 1 < P) v.y = (float)q[1];
+            if (j + 2 < P) v.z = (float)q[2];
+            if (j + 3 < P) v.w = (float)q[3];
+        }
+        return v;
+    }
+};
+struct TcStDq {  // dq[b][c][i..i+15] = M * (-2 / (B den_b))
+    float* dq;
+    const float* den;
+    float scale;
+    int C, P;
+    __device__ __forceinline__ void store16(int64_t b, int c, int i, const float v[16]) const {
+        const float s = scale / __ldg(den + b);
+        float* q = dq + (b * C + c) * (int64_t)P + i;
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+            if (i + u < P) q[u] = v[u] * s;
+    }
+};
+
+// partial[b] = Σ q∘M = (Σ q∘dq) * den_b / scale   (deterministic block reduction per sample)
+__global__ void __launch_bounds__(256) loss_dot_kernel(const float* __restrict__ q, const float* __restrict__ dq, LossWs ws,
+                                                        int64_t CP, float scale) {
+    __shared__ float red[256];
+    const int64_t b = blockIdx.x;
+    const float* qb = q + b * CP;
+    const float* db = dq + b * CP;
+    float s = 0.0f;
+    for (int64_t e = threadIdx.x; e < CP; e += blockDim.x) s = fmaf(__ldg(qb + e), __ldg(db + e), s);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ws.partial[b] = red[0] * (ws.den[b] / scale);
+}
+
 // ---- a8 for small grids (P <= 64): ONE block per sample does stages 1 and 2 ------------------
 // centres + flow warp + positive matrix (as 0/1 floats, transposed) in shared memory, then
 // M = K·posᵀ with the thread-per-channel contraction of pp_small.cuh, the loss partial Σ q∘M and
@@ -444,7 +577,9 @@ int pp_add_optical_flow(const float* flow, int64_t B, int Hin, int Win, const fl
 
 int64_t pp_regression_loss_workspace(int64_t B, int G) {
     int64_t P = (int64_t)G * G;
-    return (5 * B * P + 2 * B + B * loss_ntile((int)P)) * (int64_t)sizeof(float);
+    int64_t bytes = (5 * B * P + 2 * B + B * loss_ntile((int)P)) * (int64_t)sizeof(float);
+    if (P > PMAX) bytes += B * P * (int64_t)sizeof(int) + B * P * P;  // row counts + byte matrix of positives
+    return bytes;
 }
 
 struct LossCall {
@@ -500,6 +635,22 @@ static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int
                   loss_small_kernel<<<(unsigned)(B * ncall), SM_THREADS, small_loss_smem_bytes(C, P), st>>>(sa2));
         rc = check_launch("loss_small_kernel");
         if (rc) return rc;
+    } else if (use_tensor_cores(P) && P > PMAX && calls[0].dq && (ncall == 1 || calls[1].dq)) {
+        ntile = 1;
+        for (int c = 0; c < ncall; c++) {
+            uint8_t* posb = calls[c].pos_mask ? calls[c].pos_mask : pa[c].ws.posb;
+            PP_LAUNCH("loss_centres", st, loss_centres_kernel<<<(unsigned)B, 256, 0, st>>>(pa[c]));
+            PP_LAUNCH("loss_pos", st, loss_pos_kernel<<<dim3((P + 7) / 8, (unsigned)B), 256, 0, st>>>(pa[c].ws, P, pa[c].pr, posb));
+            PP_LAUNCH("loss_cnt", st, loss_cnt_kernel<<<(unsigned)B, 256, 0, st>>>(pa[c].ws, P, pa[c].pos_num, pa[c].pos_mean));
+            rc = check_launch("loss prep (large grid)");
+            if (rc) return rc;
+            rc = launch_tc("loss M=K*pos^T (tcgen05)", B, C, P, P, TcLdN{calls[c].k, C, P}, TcLdPos{posb, P},
+                           TcStDq{calls[c].dq, pa[c].ws.den, scale, C, P}, st);
+            if (rc) return rc;
+            PP_LAUNCH("loss_dot", st, loss_dot_kernel<<<(unsigned)B, 256, 0, st>>>(calls[c].q, calls[c].dq, pa[c].ws, (int64_t)C * P, scale));
+            rc = check_launch("loss_dot_kernel");
+            if (rc) return rc;
+        }
     } else {
         for (int c = 0; c < ncall; c++) {
             PP_LAUNCH("loss_prep", st, loss_prep_kernel<<<(unsigned)B, 256, 5 * P * sizeof(float), st>>>(pa[c]));

@@ -239,24 +239,6 @@ struct TcLdT {  // transposed: operand row = spatial index i, k = channel c; mem
         return v;
     }
 };
-__device__ __forceinline__ float4 ldg4_guard(const float* q, int k, int K) {  // 4 consecutive values, zero beyond K
-    if (k + 3 < K && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(q));
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k < K) v.x = __ldg(q);
-    if (k + 1 < K) v.y = __ldg(q + 1);
-    if (k + 2 < K) v.z = __ldg(q + 2);
-    if (k + 3 < K) v.w = __ldg(q + 3);
-    return v;
-}
-struct TcLdN {  // natural: memory [rows][K], k contiguous
-    static constexpr bool kRowMajorK = true;
-    const float* p;
-    int rows, K;
-    __device__ __forceinline__ float4 load4(int64_t b, int row, int k) const {
-        if (row >= rows || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
-        return ldg4_guard(p + (b * rows + row) * (int64_t)K + k, k, K);
-    }
-};
 struct TcLdActN {  // relu^γ(S[row][k..k+3])  (S symmetric: also serves A[k][row])
     static constexpr bool kRowMajorK = true;
     const float* S;
@@ -287,21 +269,6 @@ struct TcLdSymN {  // gS[row][k..k+3] + gS[k..k+3][row]
         return v;
     }
 };
-struct TcStN {  // out[b][m][n..n+15]
-    float* out;
-    int M, N;
-    __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
-        float* q = out + (b * M + m) * (int64_t)N + n;
-        if (n + 15 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (n + i < N) q[i] = v[i];
-        }
-    }
-};
 struct TcStGradS {  // gS[b][i][j] = v * A'(S[b][i][j])
     float* gS;
     const float* S;
@@ -314,30 +281,6 @@ struct TcStGradS {  // gS[b][i][j] = v * A'(S[b][i][j])
             if (j + u < P) gS[o + u] = v[u] * act.df(__ldg(S + o + u));
     }
 };
-
-template <class LA, class LB, class EP>
-static int launch_tc(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
-    auto kern = tc::tc_gemm_kernel<LA, LB, EP>;
-    static bool attr = false;  // one flag per template instantiation
-    if (!attr) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TC_SMEM_BYTES);
-        attr = true;
-    }
-    dim3 grid((N + tc::TN - 1) / tc::TN, (M + tc::TM - 1) / tc::TM, (unsigned)B);
-    PP_LAUNCH(what, st, kern<<<grid, tc::TC_THREADS, tc::TC_SMEM_BYTES, st>>>(M, N, K, la, lb, ep));
-    return check_launch(what);
-}
-
-// Grids of 14x14 and up (P >= 128) are large enough to fill 128-row tensor-core tiles
-// (BASELINE.json north_star); PIXPRO_B200_NO_TC=1 forces the CUDA-core path for A/B runs.
-static bool use_tensor_cores(int P) {
-    static int disabled = -1;
-    if (disabled < 0) {
-        const char* e = getenv("PIXPRO_B200_NO_TC");
-        disabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    return !disabled && P >= 128;
-}
 
 template <class LA, class LB, class EP>
 static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
