@@ -26,7 +26,7 @@ namespace tc {
 
 constexpr int TM = 128;  // accumulator rows  (UMMA M, cta_group::1)
 constexpr int TN = 128;  // accumulator columns (UMMA N)
-constexpr int TK = 32;   // K extent of one staged chunk (fp32 elements) = 4 MMA k-steps of 8
+constexpr int TK = 16;   // K extent of one staged chunk (fp32 elements) = 2 MMA k-steps of 8; 66 KB per CTA -> 2 CTAs per SM
 constexpr uint32_t SBO = 128;             // bytes between 8-row core matrices
 constexpr uint32_t LBO = (TM / 8) * 128 + 16;  // bytes between 16-byte K columns of core matrices (+16: bank spread for row-wise staging)
 constexpr uint32_t TILE_BYTES = (TK / 4) * LBO;  // one staged operand tile (TM == TN)
@@ -121,7 +121,9 @@ __device__ __forceinline__ void split_store(uint8_t* tile_hi, uint8_t* tile_lo, 
 // LA/LB::kRowMajorK: true if k is the contiguous index in memory (stage row-wise for coalescing).
 // EP::store16(b, m, n, v): 16 consecutive columns n..n+15 of row m.
 // grid (ceil(N/TN), ceil(M/TM), batch); block 256 threads (8 warps stage operands, warps 0-3 run
-// the epilogue, thread 0 issues the MMAs); dynamic smem = 2 stages x 4 tiles.
+// the epilogue, thread 0 issues the MMAs); dynamic smem = 2 stages x 4 tiles = 66 KB, 256 TMEM
+// columns: two CTAs per SM, so one CTA's staging overlaps the other's tensor-core work
+// (ncu, profiles/r01_m_*: with one 132 KB CTA per SM the tensor pipe sat idle 84 % of the time).
 // Pipeline: the global loads of chunk c+1 are issued into registers before chunk c is split and
 // stored, so their latency hides behind the store phase, the barrier and the tensor-core work.
 constexpr int STAGES = 2;
@@ -133,8 +135,9 @@ constexpr uint32_t TC_SMEM_BYTES = STAGES * STAGE_BYTES + 64;
 template <class L>
 __device__ __forceinline__ void item_coords(int it, int& row, int& kc) {
     const int item = it * TC_THREADS + threadIdx.x;
-    row = L::kRowMajorK ? (item >> 3) : (item & (TM - 1));
-    kc = L::kRowMajorK ? (item & 7) : (item >> 7);
+    constexpr int KC = TK / 4;  // 16-byte K columns per chunk
+    row = L::kRowMajorK ? (item / KC) : (item & (TM - 1));
+    kc = L::kRowMajorK ? (item % KC) : (item >> 7);
 }
 template <class L>
 __device__ __forceinline__ void load_operand(const L& ld, int64_t b, int row0, int k0, float4 r[ITEMS]) {
@@ -156,7 +159,7 @@ __device__ __forceinline__ void store_operand(const float4 r[ITEMS], uint8_t* hi
 }
 
 template <class LA, class LB, class EP>
-__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(int M, int N, int K, LA la, LB lb, EP ep) {
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(int M, int N, int K, LA la, LB lb, EP ep) {
     extern __shared__ __align__(128) uint8_t tc_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + STAGES * STAGE_BYTES);  // one per stage
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES);
