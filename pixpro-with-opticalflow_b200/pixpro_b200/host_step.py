@@ -5,10 +5,18 @@ the loader's flow links / crop descriptors and the feature maps live in pinned h
 `HostPixelStep` stages them to the device, runs flow stage -> PPM -> paired loss -> backward, and
 returns loss / positive counts / feature gradients in pinned host memory.
 
-Copies and kernels are overlapped with two CUDA streams instead of being serialised: the flow
-links go first on the compute stream (the flow kernels need only them), while features, keys and
-crop descriptors are copied on a side stream underneath the flow kernels; the compute stream waits
-on an event before the PPM.  Nothing here computes: all arithmetic is in libpixpro_b200.so.
+Copies and kernels are overlapped with two CUDA streams instead of being serialised: all host->
+device copies are queued on a side stream, flow links first and in `flow_chunks` batch chunks,
+then features, keys and crop descriptors.  The compute stream starts the flow kernels of chunk i
+as soon as its event fires, so only the first chunk's copy (1/flow_chunks of the links) is exposed;
+everything else streams underneath the flow kernels.
+
+With `use_graph=True` (default) the whole step — copies on both streams, every kernel of the path,
+the autograd backward, the device->host copies — is captured ONCE into a CUDA graph and replayed:
+per-step host work drops from ~50 Python-level launches to one cudaGraphLaunch, which is what the
+end-to-end number is bound by once the kernels are fast.  The pinned input / output tensors are
+the graph's fixed endpoints: the caller refills the same input tensors every step.
+Nothing here computes: all arithmetic is in libpixpro_b200.so.
 """
 import torch
 import torch.nn.functional as F
@@ -18,12 +26,19 @@ from . import ops
 
 class HostPixelStep:
     def __init__(self, device, batch, channels=256, grid=7, size=(720, 1280), gamma=2.0, clamp=0.0, pos_ratio=0.7,
-                 alpha1=0.01, alpha2=0.5, flow_up=True):
+                 alpha1=0.01, alpha2=0.5, flow_up=True, flow_chunks=4, use_graph=True):
         self.dev = torch.device(device)
         self.size, self.gamma, self.clamp, self.pos_ratio = size, gamma, clamp, pos_ratio
         self.alpha1, self.alpha2, self.flow_up = alpha1, alpha2, flow_up
         self.side = torch.cuda.Stream(device=self.dev)
         self.ready = torch.cuda.Event()
+        self.use_graph = use_graph
+        self.graph = None
+        self.calls = 0
+        self.key = None
+        self.param_grads = None
+        self.flow_chunks = max(1, min(flow_chunks, batch))
+        self.chunk_ready = [torch.cuda.Event() for _ in range(self.flow_chunks)]
         self.out = {"loss": torch.empty((), dtype=torch.float32).pin_memory(),
                     "pos_num": torch.empty((2, batch), dtype=torch.float32).pin_memory(),
                     "d_feat": torch.empty((2, batch, channels, grid, grid), dtype=torch.float32).pin_memory()}
@@ -36,23 +51,69 @@ class HostPixelStep:
 
     def __call__(self, host, w, bias):
         """host: dict of pinned tensors lo_f, lo_b (optional), feat1, feat2, k1, k2, c1, c2.
-        w, bias: value_transform parameters (device-resident, they are model state)."""
+        w, bias: value_transform parameters (device-resident, they are model state).
+        Returns (pinned outputs dict, (d_w, d_bias))."""
+        if not self.use_graph:
+            out = self._step(host, w, bias)
+            torch.cuda.current_stream(self.dev).synchronize()  # the caller reads the loss every step
+            return out
+        key = tuple(sorted((k, v.data_ptr()) for k, v in host.items())) + (w.data_ptr(), bias.data_ptr())
+        if self.graph is not None and key != self.key:
+            raise ValueError("HostPixelStep(use_graph=True): pass the same pinned input tensors every step "
+                             "(refill them in place); the captured graph copies from fixed addresses")
+        self.calls += 1
+        if self.graph is None:
+            if self.calls <= 2:  # eager warm-up: lazy one-time setup (smem opt-ins, divisor certification, cuDNN plans)
+                out = self._step(host, w, bias)
+                torch.cuda.current_stream(self.dev).synchronize()
+                return out
+            self.key = key
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                _, self.param_grads = self._step(host, w, bias)
+        self.graph.replay()
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.out, self.param_grads
+
+    def _step(self, host, w, bias):
         dev = self.dev
         main = torch.cuda.current_stream(dev)
         use_flow = "lo_f" in host
-        if use_flow:  # first in the queue: the flow kernels depend on nothing else
-            lo_f = host["lo_f"].to(dev, non_blocking=True)
-            lo_b = host["lo_b"].to(dev, non_blocking=True)
+        capturing = torch.cuda.is_current_stream_capturing()  # graph-private memory needs no record_stream
         self.side.wait_stream(main)
+        chunks = []
         with torch.cuda.stream(self.side):
+            if use_flow:  # first in the copy queue, chunk by chunk: the flow kernels depend on nothing else
+                B = host["lo_f"].shape[0]
+                step = (B + self.flow_chunks - 1) // self.flow_chunks
+                for i, b0 in enumerate(range(0, B, step)):
+                    lf = host["lo_f"][b0:b0 + step].to(dev, non_blocking=True)
+                    lb = host["lo_b"][b0:b0 + step].to(dev, non_blocking=True)
+                    self.chunk_ready[i].record(self.side)
+                    chunks.append((b0, lf, lb, self.chunk_ready[i]))
             t = {k: host[k].to(dev, non_blocking=True) for k in ("feat1", "feat2", "k1", "k2", "c1", "c2")}
             self.ready.record(self.side)
         ff = fb = mf = mb = None
         if use_flow:
-            ff, fb, mf, mb = ops.flow_stage(lo_f, lo_b, flow_up=self.flow_up, alpha_1=self.alpha1, alpha_2=self.alpha2)
+            lo_h, lo_w = host["lo_f"].shape[-2:]
+            H, W = (8 * lo_h, 8 * lo_w) if self.flow_up else (lo_h, lo_w)
+            ff = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+            fb = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+            mf = torch.empty((B, H, W), device=dev, dtype=torch.uint8)
+            mb = torch.empty((B, H, W), device=dev, dtype=torch.uint8)
+            for b0, lf, lb, ev in chunks:
+                main.wait_event(ev)
+                if not capturing:
+                    lf.record_stream(main)
+                    lb.record_stream(main)
+                e = b0 + lf.shape[0]
+                ops.flow_stage(lf, lb, flow_up=self.flow_up, alpha_1=self.alpha1, alpha_2=self.alpha2,
+                               out=(ff[b0:e], fb[b0:e], mf[b0:e], mb[b0:e]))
+            mf, mb = mf.view(torch.bool), mb.view(torch.bool)
         main.wait_event(self.ready)
-        for v in t.values():
-            v.record_stream(main)
+        if not capturing:
+            for v in t.values():
+                v.record_stream(main)
         f12 = torch.cat([t["feat1"], t["feat2"]], dim=0).requires_grad_(True)
         wg = w.detach().requires_grad_(True)
         bg = bias.detach().requires_grad_(True)
@@ -65,5 +126,4 @@ class HostPixelStep:
         self.out["loss"].copy_(loss.detach(), non_blocking=True)
         self.out["pos_num"].copy_(pn, non_blocking=True)
         self.out["d_feat"].copy_(f12.grad.view(2, B, *f12.shape[1:]), non_blocking=True)
-        main.synchronize()  # the caller reads the loss every step
         return self.out, (wg.grad, bg.grad)

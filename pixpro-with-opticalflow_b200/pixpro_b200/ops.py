@@ -129,22 +129,31 @@ def forward_backward_consistency(flow_fwd, flow_bwd, alpha_1=0.01, alpha_2=0.5, 
     return c1, mask.view(torch.bool), cyc
 
 
-def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=False, use_workspace=True):
+def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=False, use_workspace=True, out=None):
     """Flow stage of contrast/util.py:175-248 (use_flow_file, not use_flow_frames), fused.
 
     lo_fwd/lo_bwd: loader layout [B,n,2,h,w].  Returns (flow_fwd, flow_bwd [B,2,H,W],
     mask_fwd, mask_bwd bool [B,H,W] or None when alpha_1/alpha_2 is None).
-    use_workspace=False forces the scratch-free chain kernel (same bits, slower for n > 1)."""
+    use_workspace=False forces the scratch-free chain kernel (same bits, slower for n > 1).
+    out=(flow_fwd, flow_bwd, mask_fwd u8, mask_bwd u8): write into preallocated contiguous tensors
+    (e.g. batch slices of larger buffers) instead of allocating."""
     f = _f32(lo_fwd, "lo_fwd")
     b = _f32(lo_bwd, "lo_bwd")
     assert f.ndim == 5 and f.shape == b.shape and f.shape[2] == 2, "flow_stage expects [B,n,2,h,w]"
     B, n, _, h, w = f.shape
     H, W = (8 * h, 8 * w) if flow_up else (h, w)
     use_mask = alpha_1 is not None and alpha_2 is not None
-    ff = torch.empty((B, 2, H, W), device=f.device, dtype=torch.float32)
-    fb = torch.empty((B, 2, H, W), device=f.device, dtype=torch.float32)
-    mf = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
-    mb = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
+    if out is not None:
+        ff, fb, mf, mb = out
+        for t_, shp, dt in ((ff, (B, 2, H, W), torch.float32), (fb, (B, 2, H, W), torch.float32)) + \
+                (((mf, (B, H, W), torch.uint8), (mb, (B, H, W), torch.uint8)) if use_mask else ()):
+            if tuple(t_.shape) != shp or t_.dtype != dt or not t_.is_contiguous() or not t_.is_cuda:
+                raise ValueError(f"flow_stage: out tensor must be contiguous CUDA {dt} of shape {shp}")
+    else:
+        ff = torch.empty((B, 2, H, W), device=f.device, dtype=torch.float32)
+        fb = torch.empty((B, 2, H, W), device=f.device, dtype=torch.float32)
+        mf = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
+        mb = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
     L = _cabi.lib()
     wsz = L.pp_flow_stage_workspace(B, n, h, w, int(flow_up)) if use_workspace else 0
     ws = torch.empty((wsz,), device=f.device, dtype=torch.uint8) if wsz else None

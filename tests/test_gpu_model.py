@@ -255,3 +255,39 @@ def test_momentum_update_and_state_dict_roundtrip(group):
     mom = 1. - (1. - 0.99) * (math.cos(math.pi * k0 / model.K) + 1) / 2.
     want = model2.projector_k.linear2.bias * mom + model.projector.linear2.bias * (1 - mom)
     assert torch.allclose(model.projector_k.linear2.bias, want, atol=1e-6)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_host_pixel_step_matches_device_path(use_graph):
+    """The host-buffer entry (pinned in, pinned out; chunked copies on a side stream; optionally the
+    whole step replayed from one CUDA graph) returns exactly what the device-resident ops return."""
+    from pixpro_b200 import ops, synth
+    from pixpro_b200.host_step import HostPixelStep
+    B, C, G = 8, 256, 7
+    lf, lb = synth.flow_fields(B, 1, seed=5)
+    f1, f2, k1, k2 = synth.features(B, C, G, seed=6)
+    c1, c2 = synth.crop_coords(B, seed=7), synth.crop_coords(B, seed=8)
+    gen = torch.Generator().manual_seed(9)
+    w = (torch.randn(C, C, 1, 1, generator=gen) / 16).to(DEV)
+    bias = torch.zeros(C, device=DEV)
+    host = {k: v.pin_memory() for k, v in dict(lo_f=lf, lo_b=lb, feat1=f1, feat2=f2, k1=k1, k2=k2, c1=c1, c2=c2).items()}
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        step = HostPixelStep(DEV, B, C, G, use_graph=use_graph)
+        for _ in range(4):  # eager warm-up, capture, then replays
+            out, (dw, db) = step(host, w, bias)
+        ff, fb, mf, mb = ops.flow_stage(lf.to(DEV), lb.to(DEV))
+        x = torch.cat([f1, f2]).to(DEV).requires_grad_(True)
+        wg = w.clone().requires_grad_(True)
+        p1, p2 = ops.ppm(x, F.conv2d(x, wg, bias), 2.0, 0.0, True).chunk(2)
+        l12, pn, _ = ops.regression_loss_pair(p1, k2.to(DEV), c1.to(DEV), c2.to(DEV), p2, k1.to(DEV), c2.to(DEV), c1.to(DEV), 0.7,
+                                              flow1=ff, flow2=fb, size=(720, 1280), mask1=mf, mask2=mb)
+        (l12[0] + l12[1]).backward()
+        assert torch.equal(out["pos_num"].to(DEV), pn)
+        assert abs(out["loss"].item() - (l12[0] + l12[1]).item()) <= 1e-6 * max(1e-3, abs(out["loss"].item()))
+        ref = x.grad.view(2, B, C, G, G).cpu()
+        assert (out["d_feat"] - ref).abs().max().item() <= 1e-6 * ref.abs().max().item() + 1e-12
+        assert (dw - wg.grad).abs().max().item() <= 1e-5 * wg.grad.abs().max().item()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
