@@ -213,7 +213,7 @@ def run_b200(a):
             ff = fb = mf = mb = None
         # as PixPro.forward does: both views through the PPM as one batch, both loss directions in one launch
         f12 = torch.cat([f1, f2], dim=0)
-        pred1, pred2 = ops.ppm(f12, F.conv2d(f12, w, bias), GAMMA, CLAMP, final_norm=True).chunk(2, dim=0)
+        pred1, pred2 = ops.ppm(f12, ops.conv1x1(f12, w, bias), GAMMA, CLAMP, final_norm=True).chunk(2, dim=0)
         l12, pn, _ = ops.regression_loss_pair(pred1, t["k2"], t["c1"], t["c2"], pred2, t["k1"], t["c2"], t["c1"], POS_RATIO,
                                               flow1=ff, flow2=fb, size=size, mask1=mf, mask2=mb)
         loss = l12[0] + l12[1]

@@ -139,6 +139,16 @@ PP_API int pp_ppm_bwd(const float* feat, const float* val, const float* out, con
                int P, double gamma, double clamp_value, int final_norm, float* d_feat_sim, float* d_val, void* workspace,
                void* stream);
 
+/* ---- value transform of the PPM: 1x1 convolution (contrast/models/PixPro.py:21-23,300,343) ---
+ * x [B,Cin,P], w [Cout,Cin], bias [Cout] or NULL -> y [B,Cout,P]; backward: dy -> dx (NULL to
+ * skip), dw, db (NULL to skip).  One tcgen05 3xTF32 GEMM each over the joint (sample,pixel) index;
+ * workspace: pp_conv1x1_bwd_workspace() bytes (split-K partials of dw).                       */
+PP_API int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B, int Cin, int Cout, int P, float* y,
+                          void* stream);
+PP_API int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P);
+PP_API int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
+                          float* dw, float* db, void* workspace, void* stream);
+
 /* ---- tensor-core building block (tcgen05, 3xTF32: fp32-accurate) ----------------------------
  * C[b] = A[b] * B[b]^T;  A [batch,M,K], B [batch,N,K], C [batch,M,N], all row-major fp32.
  * The PPM / loss contractions at large grids run on the same kernel with fused loaders; this

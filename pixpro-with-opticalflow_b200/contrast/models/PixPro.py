@@ -160,14 +160,23 @@ class PixPro(BaseModel):
             for p_q, p_k in zip(online.parameters(), momentum.parameters()):
                 p_k.data = p_k.data * m + p_q.data * (1. - m)
 
+    def _value(self, feat):
+        """value_transform(feat) (PixPro.py:343).  The published setting (transform_layer=1, a 1x1
+        conv) runs on the tcgen05 3xTF32 kernel — same parameters, fp32-accurate; Identity and the
+        MLP2d variant (BatchNorm inside) stay on PyTorch/cuDNN."""
+        vt = self.value_transform
+        if isinstance(vt, nn.Conv2d) and vt.kernel_size == (1, 1) and feat.is_cuda:
+            return _ops.conv1x1(feat, vt.weight, vt.bias)
+        return vt(feat)
+
     def featprop(self, feat):
-        """Pixel Propagation Module (PixPro.py:339-363): value transform on cuDNN, then the fused
+        """Pixel Propagation Module (PixPro.py:339-363): value transform, then the fused
         normalise / self-similarity / relu^p / propagation kernels."""
-        return _ops.ppm(feat, self.value_transform(feat), self.pixpro_p, self.pixpro_clamp_value, final_norm=False)
+        return _ops.ppm(feat, self._value(feat), self.pixpro_p, self.pixpro_clamp_value, final_norm=False)
 
     def _featprop_normalized(self, feat):
         # featprop followed by F.normalize(dim=1) (PixPro.py:379-380) in one fused op
-        return _ops.ppm(feat, self.value_transform(feat), self.pixpro_p, self.pixpro_clamp_value, final_norm=True)
+        return _ops.ppm(feat, self._value(feat), self.pixpro_p, self.pixpro_clamp_value, final_norm=True)
 
     def regression_loss(self, x, y):
         return -2. * torch.einsum('nc, nc->n', [x, y]).mean()

@@ -1,0 +1,201 @@
+// pp_conv.cu — the PPM's value transform (1x1 convolution, contrast/models/PixPro.py:21-23,
+// :300, applied at :343) forward and backward on the tcgen05 3xTF32 kernel of pp_tc.cuh.
+//
+// SURVEY.md §8(f) rank 3 ("value_transform fused into the PPM prologue"): at the benchmark size
+// (2B = 128 samples, 256 -> 256 channels, 7x7 grid) cuDNN's fp32 conv + its weight/bias gradient
+// kernels cost ~190 us per step — more than every PPM/loss kernel together — while the three
+// contractions are only 2.5 GFLOP.  Here each is ONE tensor-core GEMM over the joint (sample,
+// pixel) index n = b*P + p, read straight from the [B,C,P] layout (no im2col, no transposes):
+//     y [o][n] = Σ_c W[o][c] x[c][n] + bias[o]            M=Cout N=B*P K=Cin
+//     dx[c][n] = Σ_o W[o][c] dy[o][n]                      M=Cin  N=B*P K=Cout
+//     dW[o][c] = Σ_n dy[o][n] x[c][n]                      M=Cout N=Cin K=B*P  (split-K, deterministic reduce)
+//     db[o]    = Σ_n dy[o][n]
+// fp32-accurate (3xTF32, ~1e-6 relative), checked against torch in tests/test_gpu_tc.py.
+#include "pp_common.cuh"
+#include "pp_tc.cuh"
+
+namespace pp {
+
+// joint index n -> (b, p) without an integer division per element: P is small, use float reciprocal
+// with an exact fix-up (n < 2^24).
+struct DivP {
+    int P;
+    float inv;
+    __device__ __forceinline__ void operator()(int n, int& b, int& p) const {
+        b = (int)((float)n * inv);
+        p = n - b * P;
+        if (p < 0) { b -= 1; p += P; }
+        if (p >= P) { b += 1; p -= P; }
+    }
+};
+static DivP make_divp(int P) { return DivP{P, 1.0f / (float)P}; }
+
+// operand row = joint index n, k = channel: t[b][k][p]  (x or dy viewed as [N][C], "transposed")
+struct LdNC {
+    static constexpr bool kRowMajorK = false;
+    const float* t;
+    int C, NP;  // channels, B*P
+    DivP dp;
+    __device__ __forceinline__ float4 load4(int64_t, int n, int k) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < NP) {
+            int b, p;
+            dp(n, b, p);
+            const float* q = t + ((int64_t)b * C + k) * dp.P + p;
+            if (k < C) v.x = __ldg(q);
+            if (k + 1 < C) v.y = __ldg(q + dp.P);
+            if (k + 2 < C) v.z = __ldg(q + 2 * dp.P);
+            if (k + 3 < C) v.w = __ldg(q + 3 * dp.P);
+        }
+        return v;
+    }
+};
+// operand row = channel, k = joint index n of split `s`: t[b][row][p], n = s*KS + k
+struct LdCN {
+    static constexpr bool kRowMajorK = true;
+    const float* t;
+    int C, NP, KS;
+    DivP dp;
+    __device__ __forceinline__ float4 load4(int64_t s, int row, int k) const {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row < C && k < KS) {
+            const int n0 = (int)s * KS + k;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int n = n0 + u;
+                if (k + u < KS && n < NP) {
+                    int b, p;
+                    dp(n, b, p);
+                    v[u] = __ldg(t + ((int64_t)b * C + row) * dp.P + p);
+                }
+            }
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+// W [Cout][Cin]: rows o, k = c (natural)  /  rows c, k = o (transposed)
+struct LdW {
+    static constexpr bool kRowMajorK = true;
+    const float* w;
+    int rows, K;
+    __device__ __forceinline__ float4 load4(int64_t, int row, int k) const {
+        if (row >= rows || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return ldg4_guard(w + (int64_t)row * K + k, k, K);
+    }
+};
+struct LdWT {
+    static constexpr bool kRowMajorK = false;
+    const float* w;
+    int Cout, Cin;  // operand rows = c (Cin), k = o (Cout)
+    __device__ __forceinline__ float4 load4(int64_t, int c, int o) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < Cin) {
+            const float* q = w + (int64_t)o * Cin + c;
+            if (o < Cout) v.x = __ldg(q);
+            if (o + 1 < Cout) v.y = __ldg(q + Cin);
+            if (o + 2 < Cout) v.z = __ldg(q + 2 * Cin);
+            if (o + 3 < Cout) v.w = __ldg(q + 3 * Cin);
+        }
+        return v;
+    }
+};
+// out[b][m][p] (+ bias[m]) for the 16 joint indices n..n+15
+struct StCN {
+    float* out;
+    const float* bias;  // may be null
+    int C, NP;
+    DivP dp;
+    __device__ __forceinline__ void store16(int64_t, int m, int n, const float v[16]) const {
+        const float bv = bias ? __ldg(bias + m) : 0.0f;
+        int b, p;
+        dp(n, b, p);
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (n + u < NP) out[((int64_t)b * C + m) * dp.P + p] = v[u] + bv;
+            if (++p == dp.P) { p = 0; b++; }
+        }
+    }
+};
+
+// dW[o][c] = Σ_s part[s][o][c];  db[o] = Σ_n dy[o][n]   (fixed summation order)
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int total,
+                                                                 float* __restrict__ dw) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    float s = 0.0f;
+    for (int k = 0; k < splits; k++) s += __ldg(part + (int64_t)k * total + e);
+    dw[e] = s;
+}
+__global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __restrict__ dy, int B, int C, int P,
+                                                              float* __restrict__ db) {
+    __shared__ float red[256];
+    const int o = blockIdx.x;
+    float s = 0.0f;
+    for (int e = threadIdx.x; e < B * P; e += blockDim.x) {
+        int b = e / P, p = e - b * P;
+        s += __ldg(dy + ((int64_t)b * C + o) * P + p);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) db[o] = red[0];
+}
+
+constexpr int kWgradSplitK = 128;  // joint indices per split
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B, int Cin, int Cout, int P, float* y,
+                   void* stream) {
+    PP_REQUIRE(x && w && y, "pp_conv1x1_fwd: null pointer");
+    PP_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && P > 0 && B * P < (1 << 24), "pp_conv1x1_fwd: bad shape");
+    const int NP = (int)(B * P);
+    return launch_tc("conv1x1 fwd (tcgen05)", 1, Cout, NP, Cin, LdW{w, Cout, Cin}, LdNC{x, Cin, NP, make_divp(P)},
+                     StCN{y, bias, Cout, NP, make_divp(P)}, (cudaStream_t)stream);
+}
+
+int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P) {
+    const int64_t splits = (B * P + kWgradSplitK - 1) / kWgradSplitK;
+    return splits * Cin * Cout * (int64_t)sizeof(float);
+}
+
+int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
+                   float* dw, float* db, void* workspace, void* stream) {
+    PP_REQUIRE(x && w && dy && workspace, "pp_conv1x1_bwd: null pointer");
+    PP_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && P > 0 && B * P < (1 << 24), "pp_conv1x1_bwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NP = (int)(B * P);
+    int rc;
+    if (dx) {
+        rc = launch_tc("conv1x1 dgrad (tcgen05)", 1, Cin, NP, Cout, LdWT{w, Cout, Cin}, LdNC{dy, Cout, NP, make_divp(P)},
+                       StCN{dx, nullptr, Cin, NP, make_divp(P)}, st);
+        if (rc) return rc;
+    }
+    if (dw) {
+        const int splits = (NP + kWgradSplitK - 1) / kWgradSplitK;
+        PP_REQUIRE(splits <= 65535, "pp_conv1x1_bwd: too many split-K slices");
+        float* part = (float*)workspace;
+        rc = launch_tc("conv1x1 wgrad (tcgen05)", splits, Cout, Cin, kWgradSplitK, LdCN{dy, Cout, NP, kWgradSplitK, make_divp(P)},
+                       LdCN{x, Cin, NP, kWgradSplitK, make_divp(P)}, TcStN{part, Cout, Cin}, st);
+        if (rc) return rc;
+        const int total = Cout * Cin;
+        PP_LAUNCH("conv1x1 wgrad reduce", st, conv_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, splits, total, dw));
+        rc = check_launch("conv_wgrad_reduce_kernel");
+        if (rc) return rc;
+    }
+    if (db) {
+        PP_LAUNCH("conv1x1 bias grad", st, conv_bias_grad_kernel<<<Cout, 256, 0, st>>>(dy, (int)B, Cout, P, db));
+        rc = check_launch("conv_bias_grad_kernel");
+        if (rc) return rc;
+    }
+    return PP_OK;
+}
+
+}  // extern "C"

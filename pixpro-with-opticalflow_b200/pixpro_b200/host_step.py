@@ -117,7 +117,7 @@ class HostPixelStep:
         f12 = torch.cat([t["feat1"], t["feat2"]], dim=0).requires_grad_(True)
         wg = w.detach().requires_grad_(True)
         bg = bias.detach().requires_grad_(True)
-        pred1, pred2 = ops.ppm(f12, F.conv2d(f12, wg, bg), self.gamma, self.clamp, final_norm=True).chunk(2, dim=0)
+        pred1, pred2 = ops.ppm(f12, ops.conv1x1(f12, wg, bg), self.gamma, self.clamp, final_norm=True).chunk(2, dim=0)
         l12, pn, _ = ops.regression_loss_pair(pred1, t["k2"], t["c1"], t["c2"], pred2, t["k1"], t["c2"], t["c1"],
                                               self.pos_ratio, flow1=ff, flow2=fb, size=self.size, mask1=mf, mask2=mb)
         loss = l12[0] + l12[1]

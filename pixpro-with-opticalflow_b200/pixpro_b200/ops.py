@@ -371,6 +371,54 @@ def ppm(feat, val, gamma=2.0, clamp_value=0.0, final_norm=True):
     return _PPM.apply(feat, val, gamma, clamp_value, final_norm)
 
 
+# -------------------------------------------------------------------------- value transform --
+
+class _Conv1x1(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, w, bias):
+        x = _f32(x, "x")
+        w2 = _f32(w, "weight").reshape(w.shape[0], w.shape[1])
+        b = _f32(bias, "bias") if bias is not None else None
+        B, Cin = x.shape[:2]
+        P = x[0, 0].numel()
+        Cout = w2.shape[0]
+        assert w2.shape[1] == Cin
+        y = torch.empty((B, Cout) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _cabi.check(_cabi.lib().pp_conv1x1_fwd(_ptr(x), _ptr(w2), _ptr(b), B, Cin, Cout, P, _ptr(y), _stream()),
+                        "pp_conv1x1_fwd")
+        ctx.save_for_backward(x, w2)
+        ctx.has_bias = bias is not None
+        ctx.w_shape = tuple(w.shape)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, w2 = ctx.saved_tensors
+        dy = _f32(dy, "grad_out")
+        B, Cin = x.shape[:2]
+        P = x[0, 0].numel()
+        Cout = w2.shape[0]
+        L = _cabi.lib()
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.empty_like(w2) if need_w else None
+        db = torch.empty((Cout,), device=x.device, dtype=torch.float32) if need_b else None
+        ws = torch.empty((L.pp_conv1x1_bwd_workspace(B, Cin, Cout, P),), device=x.device, dtype=torch.uint8)
+        with torch.cuda.device(x.device):
+            _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
+                                         _stream()), "pp_conv1x1_bwd")
+        return dx, (dw.view(ctx.w_shape) if dw is not None else None), db
+
+
+def conv1x1(x, weight, bias=None):
+    """1x1 convolution (the PPM value transform, contrast/models/PixPro.py:21-23) on the tcgen05
+    tensor cores with 3xTF32 (fp32-accurate).  x [B,Cin,H,W], weight [Cout,Cin,1,1] or [Cout,Cin]."""
+    return _Conv1x1.apply(x, weight, bias)
+
+
 # ---------------------------------------------------------------------------- tensor cores --
 
 def tc_gemm_nt(A, B):

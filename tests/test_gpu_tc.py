@@ -32,3 +32,27 @@ def test_tc_gemm_exact_on_small_integers():
     C = ops.tc_gemm_nt(A, B)
     ref = torch.bmm(A.double(), B.double().transpose(1, 2)).float()
     assert torch.equal(C, ref)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,G", [(128, 256, 256, 7), (5, 256, 256, 14), (3, 64, 96, 5)])
+def test_conv1x1_matches_torch(B, Cin, Cout, G):
+    """value transform (1x1 conv) forward/backward on the tensor cores vs cuDNN in true fp32."""
+    import torch.nn.functional as F
+    from pixpro_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + G)
+    x = torch.randn(B, Cin, G, G, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / 16).to(DEV).requires_grad_(True)
+    b = torch.randn(Cout, generator=g).to(DEV).requires_grad_(True)
+    dy = torch.randn(B, Cout, G, G, generator=g).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(x.double(), w.double(), b.double())
+        gx, gw, gb = torch.autograd.grad(ref, (x, w, b), dy.double())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    y = ops.conv1x1(x, w, b)
+    y.backward(dy)
+    for got, want in ((y, ref), (x.grad, gx), (w.grad, gw), (b.grad, gb)):
+        err = (got.double() - want).abs().max().item() / want.abs().max().item()
+        assert err < 1e-5, err
