@@ -53,14 +53,15 @@ bool div_certified(float s) {
     }
     const volatile float inv_v = 1.0f / s;
     const float inv = inv_v;
-    bool ok = true;
+    const volatile float lo_v = recip_lo(s);
+    const float inv_lo = lo_v;
+    bool ok = (inv_lo == 0.0f) || (fabsf(inv_lo) >= 1.3552527156068805e-20f);  // 2^-66
     for (uint32_t m = 0; m < (1u << 23) && ok; m++) {
         uint32_t bits = 0x3f800000u | m;
         float x;
         memcpy(&x, &bits, 4);
-        volatile float q0 = x * inv;
-        float r = fmaf(-q0, s, x);
-        float q = fmaf(r, inv, q0);
+        volatile float t0 = x * inv_lo;
+        float q = fmaf(x, inv, t0);
         volatile float t = x / s;
         ok = (q == t);
     }

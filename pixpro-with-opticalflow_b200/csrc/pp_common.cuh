@@ -99,41 +99,114 @@ static inline ScalarDiv make_div(float s, int div_mode) {
 }
 
 // Compile-time division flavours for the flow kernels (where divisions dominate the issue
-// slots).  Exact constant division (Markstein):  q0 = RN(x*inv); r = fma(-q0, s, x) (exact
-// residual); q = RN(q0 + r*inv)  equals RN(x/s) for every x in [2^-100, 2^100] ∪ {+0} when the
-// divisor passes div_certified(): the host checks the identity for all 2^23 mantissas of one
-// binade against true division (every step scales exactly by powers of two, so one binade
-// covers the range).  Outside that range (non-finite, denormal-tiny, -0) the unguarded form
-// may differ from IEEE division, so DM_FAST is used only where such inputs provably cannot
-// reach an output bit; DM_FASTG adds the range guard and is exact everywhere.
+// slots).  Exact constant division in TWO instructions: with inv = fl32(1/s) and
+// inv_lo = fl32(1/s - inv) (so inv + inv_lo = 1/s to ~2^-48),
+//     q = fma(x, inv, RN(x * inv_lo))
+// is within 2^-47 (relative) of x/s before its single final rounding, hence equals RN(x/s) unless
+// x/s lies that close to a rounding boundary.  For the divisors used here (s = d or d/2 with d a
+// small integer) the quotient of a 24-bit x can be no closer than 2^-25/d to a boundary, and the
+// host does not rely on that argument: div_certified() checks the identity for all 2^23 mantissas
+// of one binade against true division.  Every step scales exactly by powers of two as long as no
+// intermediate is subnormal, so one binade covers every x in [2^-60, 2^100] ∪ {+0} (the host also
+// requires inv_lo == 0 or |inv_lo| >= 2^-66, which keeps RN(x*inv_lo) normal on that range).
+// Outside that range (non-finite, tiny, -0) the unguarded form may differ from IEEE division, so
+// DM_FAST is used only where such inputs provably cannot reach an output bit;
+// DM_FASTG adds the range guard and is exact everywhere.
 enum { DM_IEEE = 0, DM_RCP = 1, DM_FAST = 2, DM_FASTG = 3 };
 
 bool div_certified(float s);  // host, cached (pp_api.cu)
 
+// fl32(1/s - fl32(1/s)); usable in constant expressions (device code folds it for literal s).
+__host__ __device__ constexpr float recip_lo(float s) { return (float)(1.0 / (double)s - (double)(1.0f / s)); }
+
 template <int DM>
 struct Div {
-    float s;    // divisor
-    float inv;  // fl32(1/s)
+    float s;       // divisor
+    float inv;     // fl32(1/s)
+    float inv_lo;  // fl32(1/s - inv)
     __device__ __forceinline__ float operator()(float x) const {
         if (DM == DM_RCP) return __fmul_rn(x, inv);
         if (DM == DM_IEEE) return __fdiv_rn(x, s);
-        float q0 = __fmul_rn(x, inv);
-        float r = __fmaf_rn(-q0, s, x);
-        float q = __fmaf_rn(r, inv, q0);
+        float q = __fmaf_rn(x, inv, __fmul_rn(x, inv_lo));
         if (DM == DM_FASTG) {
             float ax = fabsf(x);
-            bool plain = (ax >= 7.888609052210118e-31f && ax <= 1.2676506002282294e30f) || (__float_as_uint(x) == 0u);
+            bool plain = (ax >= 8.673617379884035e-19f && ax <= 1.2676506002282294e30f) || (__float_as_uint(x) == 0u);
             if (!plain) q = __fdiv_rn(x, s);
         }
         return q;
     }
 };
+// Div over a compile-time divisor (every field folds to an instruction immediate).
+template <int DM>
+__device__ __forceinline__ Div<DM> const_div(float s) {
+    Div<DM> d;
+    d.s = s;
+    d.inv = 1.0f / s;
+    d.inv_lo = recip_lo(s);
+    return d;
+}
 template <int DM>
 static inline Div<DM> make_div(float s) {
     Div<DM> d;
     d.s = s;
     d.inv = 1.0f / s;
+    d.inv_lo = recip_lo(s);
     return d;
+}
+
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) ---------------------------------------
+// One issue slot performs the same individually rounded operation on two floats.  The flow kernels
+// are issue-bound on exactly-rounded scalar arithmetic, so they process two pixels per packed op.
+// CAUTION (ptxas 12.9): a packed mul whose result feeds a packed add/sub IS contracted into one
+// FFMA2 despite the .rn modifiers (verified in SASS; the scalar forms are never contracted).
+// Wherever the reference rounds a product before adding it, the add must therefore be done with
+// the scalar add()/sub() on the unpacked halves.  Other shapes (product as multiplicand or as
+// fma addend, sum feeding a product) have no fused form and are safe.
+struct F2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ F2 pk(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ F2 pk1(float x) { return pk(x, x); }
+__device__ __forceinline__ void unpk(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 sub2(F2 a, F2 b) {
+    F2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+// certified exact division of both halves by one constant (Div<DM_FAST> on pairs)
+struct Div2 {
+    F2 inv, inv_lo;
+    __device__ __forceinline__ F2 operator()(F2 x) const { return fma2(x, inv, mul2(x, inv_lo)); }
+};
+template <int DM>
+__device__ __forceinline__ Div2 make_div2(const Div<DM>& d) {
+    Div2 r;
+    r.inv = pk1(d.inv);
+    r.inv_lo = pk1(d.inv_lo);
+    return r;
+}
+// out = fma(v_se,se, fma(v_sw,sw, fma(v_ne,ne, v_nw*nw))) on pairs (see combine4 below)
+__device__ __forceinline__ F2 combine4_2(F2 vnw, F2 vne, F2 vsw, F2 vse, F2 nw, F2 ne, F2 sw, F2 se) {
+    return fma2(vse, se, fma2(vsw, sw, fma2(vne, ne, mul2(vnw, nw))));
 }
 
 // util.py:334-339  2*c/(size-1) - 1

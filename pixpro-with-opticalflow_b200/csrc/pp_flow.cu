@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(256) chain_dense4_kernel(ChainArgs<DM> a) {
     const int W = WC ? WC : a.W, H = HC ? HC : a.H, HW = H * W;
     if (WC) {
         a.half_w = (float)(WC - 1) / 2.0f; a.half_h = (float)(HC - 1) / 2.0f;
-        a.dw.s = (float)(WC - 1); a.dw.inv = 1.0f / (float)(WC - 1);
-        a.dh.s = (float)(HC - 1); a.dh.inv = 1.0f / (float)(HC - 1);
+        a.dw = const_div<DM>((float)(WC - 1));
+        a.dh = const_div<DM>((float)(HC - 1));
     }
     if (Y >= H) return;
     const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
@@ -435,10 +435,10 @@ __global__ void __launch_bounds__(256) fbmask4_kernel(FbArgs<DM> a) {
     const int W = WC ? WC : a.W, H = HC ? HC : a.H, HW = H * W;
     if (WC) {  // fold every derived constant
         a.half_w = (float)(WC - 1) / 2.0f; a.half_h = (float)(HC - 1) / 2.0f;
-        a.dw2.s = (float)(WC - 1) / 2.0f; a.dw2.inv = 1.0f / ((float)(WC - 1) / 2.0f);
-        a.dh2.s = (float)(HC - 1) / 2.0f; a.dh2.inv = 1.0f / ((float)(HC - 1) / 2.0f);
-        a.dw.s = (float)(WC - 1); a.dw.inv = 1.0f / (float)(WC - 1);
-        a.dh.s = (float)(HC - 1); a.dh.inv = 1.0f / (float)(HC - 1);
+        a.dw2 = const_div<DM>((float)(WC - 1) / 2.0f);
+        a.dh2 = const_div<DM>((float)(HC - 1) / 2.0f);
+        a.dw = const_div<DM>((float)(WC - 1));
+        a.dh = const_div<DM>((float)(HC - 1));
     }
     if (Y >= H) return;
     const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
@@ -492,6 +492,120 @@ __global__ void __launch_bounds__(256) fbmask4_kernel(FbArgs<DM> a) {
         bool ok = inb && (sub(cyc2, eps) <= 0.0f);                        // :296
         if (edge) ok = fb_pixel_edge<DM>(g, W, H, HW, c1x, c1y, fnx, fny, a.half_w, a.half_h, a.a1, a.a2, a.dw, a.dh);
         mp[32 * j] = ok ? 1 : 0;
+    }
+}
+
+// One whole pixel of the mask from scratch, generic predicated taps (rare fix-up path of the packed
+// kernels: pixels that land exactly on the last row / column).  Same arithmetic as fb_kernel.
+template <int DM>
+__device__ __noinline__ void fb_pixel_redo(const float* f, const float* g, uint8_t* m, int X, int Y, int W, int H, float half_w,
+                                           float half_h, float a1, float a2, Div<DM> dw, Div<DM> dh) {
+    const int HW = H * W, i = Y * W + X;
+    const float fnx = norm_flow(__ldg(f + i), dw), fny = norm_flow(__ldg(f + HW + i), dh);
+    const float c1x = add(norm_coord((float)X, dw), fnx), c1y = add(norm_coord((float)Y, dh), fny);
+    const bool inb = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);
+    m[i] = (inb && fb_pixel_edge<DM>(g, W, H, HW, c1x, c1y, fnx, fny, half_w, half_h, a1, a2, dw, dh)) ? 1 : 0;
+}
+
+// fbmask4_kernel on packed fp32 pairs (certified-division mode only).  Same pixel layout (one
+// thread -> pixels X0 + lane + 32*j of its row); pixels (j, j+1) form the two halves of every FFMA2 /
+// FMUL2 / FADD2, which halves the issue slots of the ~60 exactly-rounded operations per pixel
+// (profiles/r01_final_flow_ncu_summary.txt: the scalar kernel is issue-bound, 119 instructions per
+// pixel).  Three more instruction savings, all value-preserving:
+//  * the 2-instruction certified division (pp_common.cuh);
+//  * floor as F2I.FLOOR + I2FP (one conversion-unit op instead of FRND + F2I);
+//  * east/south weights as 1 - w instead of (floor+1) - i: for an in-frame pixel i >= 0, so
+//    w = i - floor(i) is exact and both forms round the same real number 1 - w (a pixel outside the
+//    frame is masked off whatever its weights are).
+// Products that the reference rounds before adding (squares, alpha_1 * sum) are added with scalar
+// adds: see the contraction caveat at F2 in pp_common.cuh.
+template <int WC, int HC>
+__global__ void __launch_bounds__(256) fbmask4p_kernel(FbArgs<DM_FAST> a) {
+    constexpr int DM = DM_FAST;
+    const int X0 = blockIdx.x * 128 + threadIdx.x;
+    const int Y = blockIdx.y * 8 + threadIdx.y;
+    const int W = WC ? WC : a.W, H = HC ? HC : a.H, HW = H * W;
+    if (WC) {  // fold every derived constant
+        a.half_w = (float)(WC - 1) / 2.0f; a.half_h = (float)(HC - 1) / 2.0f;
+        a.dw2 = const_div<DM>((float)(WC - 1) / 2.0f);
+        a.dh2 = const_div<DM>((float)(HC - 1) / 2.0f);
+        a.dw = const_div<DM>((float)(WC - 1));
+        a.dh = const_div<DM>((float)(HC - 1));
+    }
+    if (Y >= H) return;
+    const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    const int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const float* f = (dir ? a.flow[1] : a.flow[0]) + b * 2 * (int64_t)HW;
+    const float* g = (dir ? a.flow[0] : a.flow[1]) + b * 2 * (int64_t)HW;
+    const int i = Y * W + X0;
+    const float* fpx = ptr_at(f, i);
+    const float* fpy = ptr_at(fpx, HW);
+    float fxs[4], fys[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { fxs[j] = __ldg(fpx + 32 * j); fys[j] = __ldg(fpy + 32 * j); }
+    const Div2 dW = make_div2(a.dw2), dH = make_div2(a.dh2);
+    const F2 one2 = pk1(1.0f), hw2 = pk1(a.half_w), hh2 = pk1(a.half_h);
+    const F2 yn2 = pk1(norm_coord_h((float)Y, a.dh2));
+    const unsigned xlim = W - 2, ylim = H - 2;
+    uint8_t* mp = (dir ? a.mask[1] : a.mask[0]) + b * HW + i;
+    unsigned edges = 0;
+#pragma unroll
+    for (int jp = 0; jp < 4; jp += 2) {
+        const F2 fnx = dW(pk(fxs[jp], fxs[jp + 1])), fny = dH(pk(fys[jp], fys[jp + 1]));          // :264
+        const F2 xn = sub2(dW(pk((float)(X0 + 32 * jp), (float)(X0 + 32 * jp + 32))), one2);      // :271
+        const F2 c1x = add2(xn, fnx), c1y = add2(yn2, fny);                                       // :275
+        const F2 ix = mul2(add2(c1x, one2), hw2), iy = mul2(add2(c1y, one2), hh2);
+        float c1xs[2], c1ys[2], ixs[2], iys[2], wxs[2], wys[2];
+        unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
+        unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
+        bool inb[2];
+        float t[2][8];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);                          // :276
+            const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
+            wxs[p] = sub(ixs[p], __int2float_rn(x0));
+            wys[p] = sub(iys[p], __int2float_rn(y0));
+            if (inb[p] && ((unsigned)x0 > xlim || (unsigned)y0 > ylim)) edges |= 1u << (jp + p);
+            // clamp: garbage coordinates of out-of-frame pixels still address valid memory
+            const unsigned xc = min((unsigned)x0, xlim), yc = min((unsigned)y0, ylim);
+            const float* p0 = ptr_at(g, (int)(yc * W + xc));  // row y0, x channel
+            if (WC) {  // immediate offsets off one pointer
+                t[p][0] = __ldg(p0); t[p][1] = __ldg(p0 + 1); t[p][2] = __ldg(p0 + WC); t[p][3] = __ldg(p0 + WC + 1);
+                t[p][4] = __ldg(p0 + WC * HC); t[p][5] = __ldg(p0 + WC * HC + 1);
+                t[p][6] = __ldg(p0 + WC * HC + WC); t[p][7] = __ldg(p0 + WC * HC + WC + 1);
+            } else {
+                const float* p1 = ptr_at(p0, W);   // row y0+1
+                const float* q0 = ptr_at(p0, HW);  // y channel
+                const float* q1 = ptr_at(q0, W);
+                t[p][0] = __ldg(p0); t[p][1] = __ldg(p0 + 1); t[p][2] = __ldg(p1); t[p][3] = __ldg(p1 + 1);
+                t[p][4] = __ldg(q0); t[p][5] = __ldg(q0 + 1); t[p][6] = __ldg(q1); t[p][7] = __ldg(q1 + 1);
+            }
+        }
+        const F2 wx = pk(wxs[0], wxs[1]), wy = pk(wys[0], wys[1]);
+        const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
+        const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
+        const F2 bx = combine4_2(dW(pk(t[0][0], t[1][0])), dW(pk(t[0][1], t[1][1])), dW(pk(t[0][2], t[1][2])),
+                                 dW(pk(t[0][3], t[1][3])), nw, ne, sw, se);
+        const F2 by = combine4_2(dH(pk(t[0][4], t[1][4])), dH(pk(t[0][5], t[1][5])), dH(pk(t[0][6], t[1][6])),
+                                 dH(pk(t[0][7], t[1][7])), nw, ne, sw, se);
+        const F2 cyx = add2(fnx, bx), cyy = add2(fny, by);                                        // :279
+        float cx2[2], cy2[2], fx2[2], fy2[2], bx2[2], by2[2];
+        unpk(mul2(cyx, cyx), cx2[0], cx2[1]); unpk(mul2(cyy, cyy), cy2[0], cy2[1]);
+        unpk(mul2(fnx, fnx), fx2[0], fx2[1]); unpk(mul2(fny, fny), fy2[0], fy2[1]);
+        unpk(mul2(bx, bx), bx2[0], bx2[1]); unpk(mul2(by, by), by2[0], by2[1]);
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const float cyc2 = add(cx2[p], cy2[p]);                                               // :293
+            const float eps = add(mul(a.a1, add(add(fx2[p], fy2[p]), add(bx2[p], by2[p]))), a.a2);  // :294
+            mp[32 * (jp + p)] = (inb[p] && (sub(cyc2, eps) <= 0.0f)) ? 1 : 0;                     // :296
+        }
+    }
+    if (edges) {  // pixels warped exactly onto the last row / column: redo with predicated taps
+#pragma unroll 1
+        for (int j = 0; j < 4; j++)
+            if (edges >> j & 1)
+                fb_pixel_redo<DM>(f, g, (dir ? a.mask[1] : a.mask[0]) + b * HW, X0 + 32 * j, Y, W, H, a.half_w, a.half_h, a.a1, a.a2, a.dw, a.dh);
     }
 }
 
@@ -577,6 +691,11 @@ static int launch_fb_dm(const float* f0, const float* f1, uint8_t* m0, uint8_t* 
     dim3 block(32, 8);
     if (mask_only4) {
         dim3 grid(W / 128, (H + 7) / 8, (unsigned)(B * ndir));
+        if constexpr (DM == DM_FAST) {
+            if (W == 1280 && H == 720) PP_LAUNCH("fb", st, (fbmask4p_kernel<1280, 720><<<grid, block, 0, st>>>(a)));
+            else PP_LAUNCH("fb", st, (fbmask4p_kernel<0, 0><<<grid, block, 0, st>>>(a)));
+            return check_launch("fbmask4p_kernel");
+        }
         if (W == 1280 && H == 720) PP_LAUNCH("fb", st, (fbmask4_kernel<DM, 1280, 720><<<grid, block, 0, st>>>(a)));
         else PP_LAUNCH("fb", st, (fbmask4_kernel<DM, 0, 0><<<grid, block, 0, st>>>(a)));
         return check_launch("fbmask4_kernel");
