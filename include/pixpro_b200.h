@@ -49,6 +49,10 @@ PP_API int pp_abi_version(void);
 PP_API const char* pp_last_error(void);
 /* number of kernels launched by this library in the calling process since load */
 PP_API int64_t pp_launch_count(void);
+/* Diagnostics of the TMA-staged FB-mask kernel: number of pixels (since load / last reset) whose
+ * gather footprint fell outside the staged box and were recomputed from global memory.
+ * Synchronises the device.  -1 on error. */
+PP_API int64_t pp_fb_redo_count(int reset);
 /* Per-kernel device timing (tracing aid).  pp_profile_enable(1) clears the records and makes
  * every launch bracket its kernel with a cudaEvent pair on the launch stream;
  * pp_profile_num_kernels() synchronises those events and aggregates by kernel name;

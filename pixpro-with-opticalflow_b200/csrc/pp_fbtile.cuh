@@ -1,0 +1,328 @@
+// pp_fbtile.cuh — forward-backward consistency mask (contrast/util.py:253-297) with the gathered
+// field staged in shared memory by TMA.  Included by pp_flow.cu (needs its FB helpers).
+//
+// Why: the gather-from-global kernels (fbmask4*_kernel) are bound by L1 data-pipe wavefronts, not
+// by DRAM or issue slots (profiles/r01_final_flow_ncu_summary.txt: 30 wavefronts per warp-pixel
+// for 11 memory instructions — every one of the 8 tap loads of a warp touches ~3.3 cache lines,
+// and the 8 loads touch the same lines again and again).  Here each TW x TH tile's gather
+// footprint is brought into shared memory ONCE by a single TMA box copy and the 8 taps per pixel
+// become LDS with immediate offsets.  BW is a multiple of 32 floats so that the lanes of a warp
+// (consecutive columns, a few rows apart) fall into distinct banks.
+//
+// Structure: one CTA = one tile, 8 warps, 4 CTAs per SM (their different phases hide the
+// load -> TMA -> compute dependency; a persistent producer/consumer ring was measured slower: its
+// iterator / stage bookkeeping cost more issue slots than the gather it replaced).
+//  * warp 0 first evaluates the warped position (same arithmetic as below) on an 8x4 lattice of
+//    the tile, warp-reduces the bounding box, centres the BW x BH box on it (x origin rounded down
+//    to 4 floats: TMA needs a 16-byte aligned start, measured with profiles/mb/tma_probe.cu) and
+//    issues one cp.async.bulk.tensor.3d for both channels.  Rows / columns outside the frame are
+//    zero-filled by TMA — exactly the value grid_sample's zero padding gives a missing tap, so
+//    frame-edge pixels need no special case.
+//  * every thread then handles TW/32 columns x TH/8 rows of pixels as packed fp32 pairs of two
+//    rows (see fbmask4p_kernel).  A pixel whose 2x2 footprint is not inside the staged box (flow
+//    rougher than the lattice predicts) reads its taps from global memory instead, in line, so the
+//    result never depends on the prediction and rough fields degrade gracefully towards the
+//    gather kernel's speed.
+#pragma once
+#include <cuda.h>
+#include <stdio.h>
+
+#include "pp_common.cuh"
+#include "pp_tc.cuh"
+
+namespace pp {
+namespace fbt {
+
+struct Args {
+    const float* flow[2];  // [B,2,H,W] each
+    uint8_t* mask[2];      // [B,H,W]
+    int H, W, ndir;
+    int B, pf_samples;  // samples; L2 prefetch distance in samples (0 = off)
+    float half_w, half_h, a1, a2;
+    Div<DM_FAST> dw, dh;    // / (W-1), / (H-1)
+    Div<DM_FAST> dw2, dh2;  // / ((W-1)/2), / ((H-1)/2)
+};
+
+__device__ unsigned long long g_redo_pixels;  // pixels that took their taps from global memory
+__device__ unsigned int g_wait_timeouts;      // mbarrier waits that gave up (pipeline bug: results invalid)
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a broken pipeline is counted and the kernel runs on (the host reports it as an
+// error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 22); spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(tc::smem_u32(bar)), "r"(parity), "r"(2000u)  // suspend-time hint (ns): sleep, do not poll
+            : "memory");
+        if (done) return;
+    }
+    atomicAdd(&g_wait_timeouts, 1u);
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(tc::smem_u32(bar))
+        : "memory");
+}
+
+// L2 prefetch of one box (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+// grid = (W / TW, H / TH, planes); block = 256.  Requires W % TW == 0 and H % TH == 0.
+template <int TW, int TH, int BW, int BH, int MINB>
+__global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant__ CUtensorMap tm0,
+                                                          const __grid_constant__ CUtensorMap tm1,
+                                                          const __grid_constant__ CUtensorMap tp0,
+                                                          const __grid_constant__ CUtensorMap tp1, Args a) {
+    constexpr int DM = DM_FAST;
+    constexpr int NX = TW / 32;  // columns per thread
+    constexpr int NR = TH / 8;   // rows per thread (row k -> Y0 + 8 k)
+    static_assert(TW % 32 == 0 && TH % 16 == 0, "tile shape");
+    constexpr uint32_t BOX_BYTES = 2 * BW * BH * 4;
+    extern __shared__ __align__(1024) uint8_t fbt_smem[];
+    __shared__ uint64_t full;
+    __shared__ int2 origin;
+    __shared__ int nglobal_cta;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = a.W, H = a.H, HW = H * W;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    const int b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const float* f = (dir ? a.flow[1] : a.flow[0]) + (int64_t)b * 2 * HW;
+    if (threadIdx.x == 0) {
+        nglobal_cta = 0;
+        tc::mbar_init(&full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 32 && dir == 0 && b + a.pf_samples < a.B) {
+        // Pull the same tile of both fields of a LATER sample into L2 (exact TW x TH tiles, maps tp*):
+        // the CTAs that will work there ~one wave from now then find their lattice samples, their own
+        // flow and most of their box in L2, which shortens the exposed load -> TMA -> compute chain.
+        tma_prefetch_3d(&tp0, tx0, ty0, (b + a.pf_samples) * 2);
+        tma_prefetch_3d(&tp1, tx0, ty0, (b + a.pf_samples) * 2);
+    }
+    if (warp == 0) {  // place the box and start the copy
+        const int X = tx0 + ((lane & 7) * (TW - 1)) / 7, Y = ty0 + ((lane >> 3) * (TH - 1)) / 3;
+        const float* p = ptr_at(f, Y * W + X);
+        const float fnx = norm_flow_h(__ldg(p), a.dw2), fny = norm_flow_h(__ldg(ptr_at(p, HW)), a.dh2);
+        const float c1x = add(norm_coord_h((float)X, a.dw2), fnx), c1y = add(norm_coord_h((float)Y, a.dh2), fny);
+        const bool inb = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);
+        const int x0 = __float2int_rd(mul(add(c1x, 1.0f), a.half_w)), y0 = __float2int_rd(mul(add(c1y, 1.0f), a.half_h));
+        const int mnx = __reduce_min_sync(0xffffffffu, inb ? x0 : INT_MAX);
+        const int mxx = __reduce_max_sync(0xffffffffu, inb ? x0 : INT_MIN);
+        const int mny = __reduce_min_sync(0xffffffffu, inb ? y0 : INT_MAX);
+        const int mxy = __reduce_max_sync(0xffffffffu, inb ? y0 : INT_MIN);
+        if (lane == 0) {
+            int ox, oy;
+            if (mnx == INT_MAX) {  // no sample lands in the frame: any box will do
+                ox = tx0 - (BW - TW) / 2;
+                oy = ty0 - (BH - TH) / 2;
+            } else {  // centre the box on the footprint [mn, mx + 1]
+                ox = mnx - (BW - (mxx + 2 - mnx)) / 2;
+                oy = mny - (BH - (mxy + 2 - mny)) / 2;
+            }
+            ox &= ~3;  // TMA: the box must start on a 16-byte boundary of the innermost dimension
+            origin = make_int2(ox, oy);
+            mbar_arrive_expect_tx(&full, BOX_BYTES);
+            tma_load_3d(fbt_smem, dir ? &tm0 : &tm1, ox, oy, b * 2, &full);
+        }
+        __syncwarp();
+    }
+    const Div2 dW = make_div2(a.dw2), dH = make_div2(a.dh2);
+    const F2 one2 = pk1(1.0f), hw2 = pk1(a.half_w), hh2 = pk1(a.half_h);
+    const int X0 = tx0 + lane, Y0 = ty0 + warp;
+    const float* fp = ptr_at(f, Y0 * W + X0);                  // own flow, x channel, row Y0
+    uint8_t* mp = (dir ? a.mask[1] : a.mask[0]) + (int64_t)b * HW + Y0 * W + X0;
+    const int rstep = 8 * W;                                    // one thread-row (8 image rows)
+    F2 xn2[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) xn2[c] = pk1(norm_coord_h((float)(X0 + 32 * c), a.dw2));
+    float nfx[NX][2], nfy[NX][2];  // own flow of the next row pair (register prefetch)
+    auto prefetch = [&](int kp) {
+#pragma unroll
+        for (int c = 0; c < NX; c++)
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const float* q = ptr_at(fp, (kp + p) * rstep + 32 * c);
+                nfx[c][p] = __ldg(q);
+                nfy[c][p] = __ldg(ptr_at(q, HW));
+            }
+    };
+    prefetch(0);
+    mbar_wait_bounded(&full, 0);
+    const int2 o = origin;
+    const float* sp = reinterpret_cast<const float*>(fbt_smem);
+    int nglobal = 0;  // pixels of this thread whose footprint was outside the staged box
+    const float* g = (dir ? a.flow[0] : a.flow[1]) + (int64_t)b * 2 * HW;
+#pragma unroll
+    for (int kp = 0; kp < NR; kp += 2) {
+        float fxs[NX][2], fys[NX][2];
+#pragma unroll
+        for (int c = 0; c < NX; c++)
+#pragma unroll
+            for (int p = 0; p < 2; p++) { fxs[c][p] = nfx[c][p]; fys[c][p] = nfy[c][p]; }
+        if (kp + 2 < NR) prefetch(kp + 2);
+        const F2 yn = sub2(dH(pk((float)(Y0 + 8 * kp), (float)(Y0 + 8 * kp + 8))), one2);          // :271
+#pragma unroll
+        for (int c = 0; c < NX; c++) {
+            const F2 fnx = dW(pk(fxs[c][0], fxs[c][1])), fny = dH(pk(fys[c][0], fys[c][1]));       // :264
+            const F2 c1x = add2(xn2[c], fnx), c1y = add2(yn, fny);                                 // :275
+            const F2 ix = mul2(add2(c1x, one2), hw2), iy = mul2(add2(c1y, one2), hh2);
+            float c1xs[2], c1ys[2], ixs[2], iys[2], wxs[2], wys[2];
+            unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
+            unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
+            bool inb[2];
+            float t[2][8];
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);                       // :276
+                const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
+                wxs[p] = sub(ixs[p], __int2float_rn(x0));
+                wys[p] = sub(iys[p], __int2float_rn(y0));
+                const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
+                if (inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2))) {
+                    // footprint outside the staged box (rare): the same taps straight from global memory,
+                    // zero where grid_sample pads (an in-frame pixel can only miss column W or row H)
+                    const float* q = ptr_at(g, y0 * W + x0);
+                    const bool xin = x0 < W - 1, yin = y0 < H - 1;
+                    t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
+                    t[p][1] = xin ? __ldg(q + 1) : 0.0f; t[p][5] = xin ? __ldg(ptr_at(q, HW) + 1) : 0.0f;
+                    t[p][2] = yin ? __ldg(ptr_at(q, W)) : 0.0f; t[p][6] = yin ? __ldg(ptr_at(q, HW + W)) : 0.0f;
+                    t[p][3] = (xin && yin) ? __ldg(ptr_at(q, W) + 1) : 0.0f; t[p][7] = (xin && yin) ? __ldg(ptr_at(q, HW + W) + 1) : 0.0f;
+                    nglobal++;
+                } else {
+                    // clamp: a pixel outside the frame (masked off below) still addresses the staged box
+                    const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
+                    t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
+                    t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
+                }
+            }
+            const F2 wx = pk(wxs[0], wxs[1]), wy = pk(wys[0], wys[1]);
+            const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
+            const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
+            const F2 bx = combine4_2(dW(pk(t[0][0], t[1][0])), dW(pk(t[0][1], t[1][1])), dW(pk(t[0][2], t[1][2])),
+                                     dW(pk(t[0][3], t[1][3])), nw, ne, sw, se);
+            const F2 by = combine4_2(dH(pk(t[0][4], t[1][4])), dH(pk(t[0][5], t[1][5])), dH(pk(t[0][6], t[1][6])),
+                                     dH(pk(t[0][7], t[1][7])), nw, ne, sw, se);
+            const F2 cyx = add2(fnx, bx), cyy = add2(fny, by);                                     // :279
+            float cx2[2], cy2[2], fx2[2], fy2[2], bx2[2], by2[2];
+            unpk(mul2(cyx, cyx), cx2[0], cx2[1]); unpk(mul2(cyy, cyy), cy2[0], cy2[1]);
+            unpk(mul2(fnx, fnx), fx2[0], fx2[1]); unpk(mul2(fny, fny), fy2[0], fy2[1]);
+            unpk(mul2(bx, bx), bx2[0], bx2[1]); unpk(mul2(by, by), by2[0], by2[1]);
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const float cyc2 = add(cx2[p], cy2[p]);                                             // :293
+                const float eps = add(mul(a.a1, add(add(fx2[p], fy2[p]), add(bx2[p], by2[p]))), a.a2);  // :294
+                mp[(kp + p) * rstep + 32 * c] = (inb[p] && (sub(cyc2, eps) <= 0.0f)) ? 1 : 0;       // :296
+            }
+        }
+    }
+    // diagnostics counter: one global atomic per CTA at most (per-thread atomics on one address
+    // serialise in L2 and cost milliseconds on rough fields)
+    const int wsum = __reduce_add_sync(0xffffffffu, nglobal);
+    if (lane == 0 && wsum) atomicAdd(&nglobal_cta, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0 && nglobal_cta) atomicAdd(&g_redo_pixels, (unsigned long long)nglobal_cta);
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// [planes, H, W] fp32 planes viewed as a 3-D tensor (W fastest); box = BW x BH x 2 planes.
+static bool make_map(CUtensorMap* tm, const float* base, int64_t planes, int H, int W, int BW, int BH) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BW, (cuuint32_t)BH, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int TW, int TH, int BW, int BH, int MINB>
+static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
+    auto kern = fbbox_kernel<TW, TH, BW, BH, MINB>;
+    constexpr int smem = 2 * BW * BH * 4;
+    static bool ready = false;
+    static const bool dbg = getenv("PIXPRO_B200_FBDBG") != nullptr;
+    if (a.W % TW != 0 || a.H % TH != 0) return -1;
+    if (!ready) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            if (dbg) fprintf(stderr, "fbbox: cudaFuncSetAttribute(%d) failed: %s\n", smem, cudaGetErrorString(e));
+            cudaGetLastError();
+            return -1;
+        }
+        if (dbg) {
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+            fprintf(stderr, "fbbox<%d,%d,%d,%d>: %d blocks/SM, %d B smem\n", TW, TH, BW, BH, occ, smem);
+        }
+        ready = true;
+    }
+    CUtensorMap tm0, tm1, tp0, tp1;
+    if (!make_map(&tm0, a.flow[0], B * 2, a.H, a.W, BW, BH) || !make_map(&tm1, a.flow[1], B * 2, a.H, a.W, BW, BH) ||
+        !make_map(&tp0, a.flow[0], B * 2, a.H, a.W, TW, TH) || !make_map(&tp1, a.flow[1], B * 2, a.H, a.W, TW, TH)) {
+        if (dbg) fprintf(stderr, "fbbox: tensor map encode failed\n");
+        return -1;
+    }
+    dim3 grid(a.W / TW, a.H / TH, (unsigned)(B * a.ndir));
+    PP_LAUNCH("fb", st, (kern<<<grid, 256, smem, st>>>(tm0, tm1, tp0, tp1, a)));
+    return check_launch("fbbox_kernel");
+}
+
+// returns -1 when the TMA path is not applicable (caller falls back to the gather kernels)
+static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, int ndir, int64_t B, int H, int W, float a1, float a2,
+                  cudaStream_t st) {
+    if (H < 2 || W < 64 || B * ndir > 65535) return -1;
+    if (((uintptr_t)f0 | (uintptr_t)f1) & 15) return -1;
+    Args a;
+    a.flow[0] = f0; a.flow[1] = f1; a.mask[0] = m0; a.mask[1] = m1;
+    a.H = H; a.W = W; a.ndir = ndir;
+    a.B = (int)B;
+    static const int pf = [] { const char* e = getenv("PIXPRO_B200_FBPF"); return e ? atoi(e) : 1; }();
+    a.pf_samples = pf > 0 ? pf : (int)B;  // >= B disables the prefetch
+    a.half_w = (float)(W - 1) / 2.0f; a.half_h = (float)(H - 1) / 2.0f;
+    a.a1 = a1; a.a2 = a2;
+    a.dw = make_div<DM_FAST>((float)(W - 1)); a.dh = make_div<DM_FAST>((float)(H - 1));
+    a.dw2 = make_div<DM_FAST>((float)(W - 1) / 2.0f); a.dh2 = make_div<DM_FAST>((float)(H - 1) / 2.0f);
+    static const int variant = [] { const char* e = getenv("PIXPRO_B200_FBTILE"); return e ? atoi(e) : 1; }();
+    switch (variant) {
+        case 0: return -1;  // disabled: gather kernels
+        case 2: return launch_cfg<64, 48, 96, 72, 3>(a, B, st);
+        case 3: return launch_cfg<64, 32, 96, 56, 4>(a, B, st);
+        case 4: return launch_cfg<64, 32, 96, 48, 4>(a, B, st);
+        case 5: return launch_cfg<32, 48, 64, 72, 4>(a, B, st);
+        default: return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
+    }
+}
+
+}  // namespace fbt
+}  // namespace pp

@@ -15,7 +15,10 @@
 // terms amortised), (b) address with 32-bit offsets from per-thread base pointers, and (c) use
 // the certified 3-instruction exact division of pp_common.cuh instead of the IEEE sequence.
 // The chain state lives in registers; no intermediate tensor is materialised.
+#include <limits.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "pp_common.cuh"
 
@@ -609,6 +612,10 @@ __global__ void __launch_bounds__(256) fbmask4p_kernel(FbArgs<DM_FAST> a) {
     }
 }
 
+}  // namespace pp
+#include "pp_fbtile.cuh"
+namespace pp {
+
 // a11 calc_mask_ratio: one block per sample, integer count of zeros (exact), one division.
 __global__ void __launch_bounds__(256) mask_ratio_kernel(const uint8_t* __restrict__ mask, int64_t HW, float* __restrict__ ratio) {
     const uint8_t* m = mask + blockIdx.x * HW;
@@ -713,6 +720,11 @@ static int launch_fb(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1,
         return launch_fb_dm<DM_RCP>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, mask_only4, st);
     const bool cert = div_certified((float)(W - 1)) && div_certified((float)(H - 1));
     const bool cert_half = div_certified((float)(W - 1) / 2.0f) && div_certified((float)(H - 1) / 2.0f);
+    if (cert && cert_half && mask_only4 && fb_alpha2_eff(alpha_2, H, W) >= 1e-12f) {
+        // TMA-staged tile kernel (pp_fbtile.cuh); -1 = not applicable to this shape / alignment
+        const int rc = fbt::launch(f0, f1, m0, m1, ndir, B, H, W, (float)alpha_1, fb_alpha2_eff(alpha_2, H, W), st);
+        if (rc != -1) return rc;
+    }
     if (cert && cert_half && mask_only4)
         return launch_fb_dm<DM_FAST>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, true, st);
     if (cert)  // values leave the kernel (cycle / coords1): guarded variant, exact for every input
@@ -847,6 +859,22 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
         if (rc) return rc;
     }
     return PP_OK;
+}
+
+int64_t pp_fb_redo_count(int reset) {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, fbt::g_redo_pixels, sizeof(v)) != cudaSuccess) return -1;
+    unsigned int to = 0;
+    if (cudaMemcpyFromSymbol(&to, fbt::g_wait_timeouts, sizeof(to)) != cudaSuccess) return -1;
+    if (to) {
+        set_error("pp_fb_redo_count: %u mbarrier waits of the tile kernel timed out (results invalid)", to);
+        return -2;
+    }
+    if (reset) {
+        const unsigned long long z = 0;
+        cudaMemcpyToSymbol(fbt::g_redo_pixels, &z, sizeof(z));
+    }
+    return (int64_t)v;
 }
 
 int pp_calc_mask_ratio(const uint8_t* mask, int64_t B, int H, int W, float* ratio, void* stream) {

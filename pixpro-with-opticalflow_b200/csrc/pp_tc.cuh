@@ -66,6 +66,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // bounded wait: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 26); spin++) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
