@@ -192,6 +192,14 @@ __device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
     return r;
 }
+// a*b as an FFMA2 with a +0 addend: bit-identical to the rounded product whenever the product is
+// not -0 (squares, products of non-negative factors) — and, being an fma result, it can feed a
+// packed add/sub without being contracted into it (see the caveat above).
+__device__ __forceinline__ F2 mul2_nc(F2 a, F2 b) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(0ull));
+    return r;
+}
 // certified exact division of both halves by one constant (Div<DM_FAST> on pairs)
 struct Div2 {
     F2 inv, inv_lo;

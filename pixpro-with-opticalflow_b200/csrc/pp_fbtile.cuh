@@ -73,6 +73,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+__device__ __forceinline__ uint8_t* byte_ptr_at(uint8_t* base, int off) {  // base + off as one IMAD.WIDE
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"((unsigned long long)base));
+    return reinterpret_cast<uint8_t*>(r);
+}
 // L2 prefetch of one box (no shared-memory destination, no completion to wait for)
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
         __syncwarp();
     }
     const Div2 dW = make_div2(a.dw2), dH = make_div2(a.dh2);
-    const F2 one2 = pk1(1.0f), hw2 = pk1(a.half_w), hh2 = pk1(a.half_h);
+    const F2 one2 = pk1(1.0f), hw2 = pk1(a.half_w), hh2 = pk1(a.half_h), a1_2 = pk1(a.a1), a2_2 = pk1(a.a2);
     const int X0 = tx0 + lane, Y0 = ty0 + warp;
     const float* fp = ptr_at(f, Y0 * W + X0);                  // own flow, x channel, row Y0
     uint8_t* mp = (dir ? a.mask[1] : a.mask[0]) + (int64_t)b * HW + Y0 * W + X0;
@@ -180,18 +185,19 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
         for (int c = 0; c < NX; c++) {
             const F2 fnx = dW(pk(fxs[c][0], fxs[c][1])), fny = dH(pk(fys[c][0], fys[c][1]));       // :264
             const F2 c1x = add2(xn2[c], fnx), c1y = add2(yn, fny);                                 // :275
-            const F2 ix = mul2(add2(c1x, one2), hw2), iy = mul2(add2(c1y, one2), hh2);
-            float c1xs[2], c1ys[2], ixs[2], iys[2], wxs[2], wys[2];
+            // (c1 + 1) * half: >= 0 for every in-frame pixel, so the non-contractable product form is exact
+            const F2 ix = mul2_nc(add2(c1x, one2), hw2), iy = mul2_nc(add2(c1y, one2), hh2);
+            float c1xs[2], c1ys[2], ixs[2], iys[2];
             unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
             unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
             bool inb[2];
-            float t[2][8];
+            float t[2][8], xws[2], yws[2];
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);                       // :276
                 const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
-                wxs[p] = sub(ixs[p], __int2float_rn(x0));
-                wys[p] = sub(iys[p], __int2float_rn(y0));
+                xws[p] = __int2float_rn(x0);
+                yws[p] = __int2float_rn(y0);
                 const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
                 if (inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2))) {
                     // footprint outside the staged box (rare): the same taps straight from global memory,
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
                     t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
                 }
             }
-            const F2 wx = pk(wxs[0], wxs[1]), wy = pk(wys[0], wys[1]);
+            const F2 wx = sub2(ix, pk(xws[0], xws[1])), wy = sub2(iy, pk(yws[0], yws[1]));
             const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
             const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
             const F2 bx = combine4_2(dW(pk(t[0][0], t[1][0])), dW(pk(t[0][1], t[1][1])), dW(pk(t[0][2], t[1][2])),
@@ -218,16 +224,15 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
             const F2 by = combine4_2(dH(pk(t[0][4], t[1][4])), dH(pk(t[0][5], t[1][5])), dH(pk(t[0][6], t[1][6])),
                                      dH(pk(t[0][7], t[1][7])), nw, ne, sw, se);
             const F2 cyx = add2(fnx, bx), cyy = add2(fny, by);                                     // :279
-            float cx2[2], cy2[2], fx2[2], fy2[2], bx2[2], by2[2];
-            unpk(mul2(cyx, cyx), cx2[0], cx2[1]); unpk(mul2(cyy, cyy), cy2[0], cy2[1]);
-            unpk(mul2(fnx, fnx), fx2[0], fx2[1]); unpk(mul2(fny, fny), fy2[0], fy2[1]);
-            unpk(mul2(bx, bx), bx2[0], bx2[1]); unpk(mul2(by, by), by2[0], by2[1]);
+            // squares and alpha_1 * sum are never -0 (alpha_1 >= 0 is checked by the launcher)
+            const F2 cyc2 = add2(mul2_nc(cyx, cyx), mul2_nc(cyy, cyy));                            // :293
+            const F2 f2 = add2(mul2_nc(fnx, fnx), mul2_nc(fny, fny)), b2 = add2(mul2_nc(bx, bx), mul2_nc(by, by));
+            const F2 eps = add2(mul2_nc(a1_2, add2(f2, b2)), a2_2);                                // :294
+            float ds[2];
+            unpk(sub2(cyc2, eps), ds[0], ds[1]);
 #pragma unroll
-            for (int p = 0; p < 2; p++) {
-                const float cyc2 = add(cx2[p], cy2[p]);                                             // :293
-                const float eps = add(mul(a.a1, add(add(fx2[p], fy2[p]), add(bx2[p], by2[p]))), a.a2);  // :294
-                mp[(kp + p) * rstep + 32 * c] = (inb[p] && (sub(cyc2, eps) <= 0.0f)) ? 1 : 0;       // :296
-            }
+            for (int p = 0; p < 2; p++)
+                *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = (inb[p] && (ds[p] <= 0.0f)) ? 1 : 0;   // :296
         }
     }
     // diagnostics counter: one global atomic per CTA at most (per-thread atomics on one address
@@ -301,7 +306,7 @@ static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
 // returns -1 when the TMA path is not applicable (caller falls back to the gather kernels)
 static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, int ndir, int64_t B, int H, int W, float a1, float a2,
                   cudaStream_t st) {
-    if (H < 2 || W < 64 || B * ndir > 65535) return -1;
+    if (H < 2 || W < 64 || B * ndir > 65535 || !(a1 >= 0.0f)) return -1;
     if (((uintptr_t)f0 | (uintptr_t)f1) & 15) return -1;
     Args a;
     a.flow[0] = f0; a.flow[1] = f1; a.mask[0] = m0; a.mask[1] = m1;
