@@ -6,6 +6,7 @@
   (3) size-independent properties at BASELINE.json's full sizes (B=64, 720x1280).
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -179,6 +180,9 @@ def test_featprop_golden(ops, tag):
     (2, 2, 100, 180, False, False, 8.0),    # dense links, no up-sampling
     (1, 4, 33, 47, True, True, 1.0),        # flow_cat_norm
     (1, 2, 16, 16, True, False, 40.0),      # flows that leave the frame
+    (2, 1, 12, 16, True, False, 6.0),       # 96x128: TMA-staged FB kernel, flows crossing the frame border
+    (1, 2, 18, 24, True, False, 1.0),       # 144x192: TMA-staged FB kernel, smooth chained field
+    (2, 1, 96, 128, False, False, 30.0),    # dense 96x128 links: footprints far outside the staged box
 ])
 def test_flow_stage_vs_oracle(ops, orc, synth, B, n, h, w, flow_up, is_norm, mag):
     f, b = synth.flow_fields(B, n, h=h, w=w, seed=7 * n + h, magnitude=mag)
@@ -188,6 +192,26 @@ def test_flow_stage_vs_oracle(ops, orc, synth, B, n, h, w, flow_up, is_norm, mag
         assert_bits_equal(npy(gt), wt, name)
     valid = want[2].mean()
     assert 0.0 <= valid <= 1.0
+
+
+def test_fb_tile_kernel_rough_field_and_no_timeouts(ops, orc):
+    """White-noise flows (no spatial coherence): every footprint prediction of the TMA-staged FB
+    kernel fails, all taps come from its in-line global path; results must still be the oracle's,
+    and no mbarrier wait of the kernel may have timed out in this process."""
+    from pixpro_b200 import _cabi
+    g = torch.Generator().manual_seed(5)
+    f = (torch.randn(2, 1, 2, 96, 128, generator=g) * 20.0).contiguous()
+    b = (torch.randn(2, 1, 2, 96, 128, generator=g) * 20.0).contiguous()
+    before = _cabi.fb_redo_count()
+    assert before >= 0
+    want = orc.flow_stage(f.numpy(), b.numpy(), flow_up=False, is_norm=False)
+    got = ops.flow_stage(f.to(DEV), b.to(DEV), flow_up=False)
+    for name, gt, wt in zip(["flow_fwd", "flow_bwd", "mask_fwd", "mask_bwd"], got, want):
+        assert_bits_equal(npy(gt), wt, name)
+    after = _cabi.fb_redo_count()
+    assert after >= 0, "mbarrier wait timed out in the FB tile kernel"
+    if os.environ.get("PIXPRO_B200_FBTILE", "1") != "0":
+        assert after > before, "the tile kernel should have taken taps from global memory on white noise"
 
 
 def test_flow_stage_empty_batch(ops):
