@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
             float c1xs[2], c1ys[2], ixs[2], iys[2];
             unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
             unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
-            bool inb[2];
+            bool inb[2], outside[2];
+            int gofs[2];
             float t[2][8], xws[2], yws[2];
 #pragma unroll
             for (int p = 0; p < 2; p++) {
@@ -199,22 +200,28 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
                 xws[p] = __int2float_rn(x0);
                 yws[p] = __int2float_rn(y0);
                 const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
-                if (inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2))) {
-                    // footprint outside the staged box (rare): the same taps straight from global memory,
-                    // zero where grid_sample pads (an in-frame pixel can only miss column W or row H)
-                    const float* q = ptr_at(g, y0 * W + x0);
-                    const bool xin = x0 < W - 1, yin = y0 < H - 1;
-                    t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
-                    t[p][1] = xin ? __ldg(q + 1) : 0.0f; t[p][5] = xin ? __ldg(ptr_at(q, HW) + 1) : 0.0f;
-                    t[p][2] = yin ? __ldg(ptr_at(q, W)) : 0.0f; t[p][6] = yin ? __ldg(ptr_at(q, HW + W)) : 0.0f;
-                    t[p][3] = (xin && yin) ? __ldg(ptr_at(q, W) + 1) : 0.0f; t[p][7] = (xin && yin) ? __ldg(ptr_at(q, HW + W) + 1) : 0.0f;
-                    nglobal++;
-                } else {
-                    // clamp: a pixel outside the frame (masked off below) still addresses the staged box
-                    const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
-                    t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
-                    t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
-                }
+                outside[p] = inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
+                gofs[p] = (y0 << 16) | (x0 & 0xffff);  // only read for in-frame pixels (launcher: W, H < 32768)
+                // clamp: a pixel outside the box or the frame still addresses the staged box
+                const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
+                t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
+                t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
+            }
+            if (outside[0] || outside[1]) {
+                // footprint outside the staged box (rare): the same taps straight from global memory,
+                // zero where grid_sample pads (an in-frame pixel can only miss column W or row H)
+#pragma unroll
+                for (int p = 0; p < 2; p++)
+                    if (outside[p]) {
+                        const int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
+                        const float* q = ptr_at(g, y0 * W + x0);
+                        const bool xin = x0 < W - 1, yin = y0 < H - 1;
+                        t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
+                        t[p][1] = xin ? __ldg(q + 1) : 0.0f; t[p][5] = xin ? __ldg(ptr_at(q, HW) + 1) : 0.0f;
+                        t[p][2] = yin ? __ldg(ptr_at(q, W)) : 0.0f; t[p][6] = yin ? __ldg(ptr_at(q, HW + W)) : 0.0f;
+                        t[p][3] = (xin && yin) ? __ldg(ptr_at(q, W) + 1) : 0.0f; t[p][7] = (xin && yin) ? __ldg(ptr_at(q, HW + W) + 1) : 0.0f;
+                        nglobal++;
+                    }
             }
             const F2 wx = sub2(ix, pk(xws[0], xws[1])), wy = sub2(iy, pk(yws[0], yws[1]));
             const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
@@ -306,7 +313,7 @@ static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
 // returns -1 when the TMA path is not applicable (caller falls back to the gather kernels)
 static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, int ndir, int64_t B, int H, int W, float a1, float a2,
                   cudaStream_t st) {
-    if (H < 2 || W < 64 || B * ndir > 65535 || !(a1 >= 0.0f)) return -1;
+    if (H < 2 || W < 64 || H >= 32768 || W >= 32768 || B * ndir > 65535 || !(a1 >= 0.0f)) return -1;
     if (((uintptr_t)f0 | (uintptr_t)f1) & 15) return -1;
     Args a;
     a.flow[0] = f0; a.flow[1] = f1; a.mask[0] = m0; a.mask[1] = m1;
