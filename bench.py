@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--grid", type=int, default=7)
     ap.add_argument("--cpu-sample", type=int, default=0, help="samples per CPU-arm step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="PPM forward on the same stream as the flow stage (A/B switch)")
     return ap.parse_args()
 
 
@@ -200,6 +201,7 @@ def run_b200(a):
     d = {k: v.to(dev) for k, v in host.items()}
     size = (H_FULL, W_FULL)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    side = torch.cuda.Stream(device=dev, priority=-1)
 
     def hot_path(t):
         """One pass of the path on device-resident tensors t; returns (loss, pos stats, grads)."""
@@ -207,13 +209,24 @@ def run_b200(a):
         f2 = t["feat2"].detach().requires_grad_(True)
         w = t["w"].detach().requires_grad_(True)
         bias = t["bias"].detach().requires_grad_(True)
+        cur = torch.cuda.current_stream(dev)
+        # The PPM forward depends on nothing the flow stage produces.  It is a handful of latency-bound
+        # one-block-per-sample launches, so it goes to a HIGH-PRIORITY side stream (its few blocks get the
+        # first free SM slots) and runs underneath the HBM-bound flow kernels of the current stream.
+        ppm_stream = cur if a.no_overlap else side
+        ppm_stream.wait_stream(cur)
+        with torch.cuda.stream(ppm_stream):
+            # as PixPro.forward does: both views through the PPM as one batch
+            f12 = torch.cat([f1, f2], dim=0)
+            pred12 = ops.ppm(f12, ops.conv1x1(f12, w, bias), GAMMA, CLAMP, final_norm=True)
         if use_flow:
             ff, fb, mf, mb = ops.flow_stage(t["lo_f"], t["lo_b"], flow_up=True, alpha_1=ALPHA1, alpha_2=ALPHA2)
         else:
             ff = fb = mf = mb = None
-        # as PixPro.forward does: both views through the PPM as one batch, both loss directions in one launch
-        f12 = torch.cat([f1, f2], dim=0)
-        pred1, pred2 = ops.ppm(f12, ops.conv1x1(f12, w, bias), GAMMA, CLAMP, final_norm=True).chunk(2, dim=0)
+        cur.wait_stream(ppm_stream)
+        pred12.record_stream(cur)
+        pred1, pred2 = pred12.chunk(2, dim=0)
+        # both loss directions in one launch
         l12, pn, _ = ops.regression_loss_pair(pred1, t["k2"], t["c1"], t["c2"], pred2, t["k1"], t["c2"], t["c1"], POS_RATIO,
                                               flow1=ff, flow2=fb, size=size, mask1=mf, mask2=mb)
         loss = l12[0] + l12[1]

@@ -31,6 +31,7 @@ class HostPixelStep:
         self.size, self.gamma, self.clamp, self.pos_ratio = size, gamma, clamp, pos_ratio
         self.alpha1, self.alpha2, self.flow_up = alpha1, alpha2, flow_up
         self.side = torch.cuda.Stream(device=self.dev)
+        self.aux = torch.cuda.Stream(device=self.dev, priority=-1)  # few latency-bound blocks: first free SM slots
         self.ready = torch.cuda.Event()
         self.use_graph = use_graph
         self.graph = None
@@ -110,14 +111,23 @@ class HostPixelStep:
                 ops.flow_stage(lf, lb, flow_up=self.flow_up, alpha_1=self.alpha1, alpha_2=self.alpha2,
                                out=(ff[b0:e], fb[b0:e], mf[b0:e], mb[b0:e]))
             mf, mb = mf.view(torch.bool), mb.view(torch.bool)
+        # PPM forward on a third stream: it needs only the features, so it runs underneath the tail of
+        # the flow kernels instead of after them; the loss (which needs both) joins the two.
+        with torch.cuda.stream(self.aux):
+            self.aux.wait_event(self.ready)  # also forks aux from the (possibly capturing) main stream
+            if not capturing:
+                for v in t.values():
+                    v.record_stream(self.aux)
+            f12 = torch.cat([t["feat1"], t["feat2"]], dim=0).requires_grad_(True)
+            wg = w.detach().requires_grad_(True)
+            bg = bias.detach().requires_grad_(True)
+            pred12 = ops.ppm(f12, ops.conv1x1(f12, wg, bg), self.gamma, self.clamp, final_norm=True)
         main.wait_event(self.ready)
+        main.wait_stream(self.aux)
         if not capturing:
-            for v in t.values():
+            for v in list(t.values()) + [pred12, f12]:
                 v.record_stream(main)
-        f12 = torch.cat([t["feat1"], t["feat2"]], dim=0).requires_grad_(True)
-        wg = w.detach().requires_grad_(True)
-        bg = bias.detach().requires_grad_(True)
-        pred1, pred2 = ops.ppm(f12, ops.conv1x1(f12, wg, bg), self.gamma, self.clamp, final_norm=True).chunk(2, dim=0)
+        pred1, pred2 = pred12.chunk(2, dim=0)
         l12, pn, _ = ops.regression_loss_pair(pred1, t["k2"], t["c1"], t["c2"], pred2, t["k1"], t["c2"], t["c1"],
                                               self.pos_ratio, flow1=ff, flow2=fb, size=self.size, mask1=mf, mask2=mb)
         loss = l12[0] + l12[1]
