@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "pp_common.cuh"
 #include "pp_tc.cuh"
@@ -250,6 +251,256 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
     if (threadIdx.x == 0 && nglobal_cta) atomicAdd(&g_redo_pixels, (unsigned long long)nglobal_cta);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense-link chain (contrast/util.py:301-330, num > 1) with each link's gather footprint staged by
+// TMA.  Same idea as fbbox_kernel, but the gather position of step i depends on steps < i, so per
+// step: every thread evaluates the tap origin of its 12 pixels, the CTA reduces the exact bounding
+// box (warp redux + 4 shared atomics + one __syncthreads), thread 0 centres the BW x BH box on it
+// and issues the TMA copy of link i, and the taps are read from shared memory.  Positions are
+// recomputed after the wait instead of being kept in registers (12 pixels x 4 values would not
+// fit).  Taps outside the frame are TMA zero fill (= grid_sample's zero padding); a pixel whose
+// footprint misses the box reads global memory in line.  Arithmetic = chain_kernel<false,false>.
+// grid = (W / TW, H / TH, B * ndir); block = 256.
+// PIXPRO_B200_CHAINBOX: 0 = gather kernels only, 1 (default) = TMA-staged dense chain where it pays,
+// 2 = also the fused x8-up-sampling chain in pp_flow_stage
+static int chainbox_mode() {
+    static const int m = [] { const char* e = getenv("PIXPRO_B200_CHAINBOX"); return e ? atoi(e) : 1; }();
+    return m;
+}
+
+// order-preserving float <-> int (for integer warp / shared-memory min and max of floats)
+__device__ __forceinline__ int fkey(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// floor of the un-normalised sampling coordinate of pixel coordinate c (util.py:334-339 + GridSampler.cuh:22-31)
+__device__ __forceinline__ int tap_origin(float c, const Div<DM_FAST>& d, float half) {
+    return __float2int_rd(mul(add(norm_coord(c, d), 1.0f), half));
+}
+
+struct ChainBoxArgs {
+    const float* links[2];  // per direction: link i of sample b at links + b * stride_b + i * stride_n, each [2,H,W]
+    float* out[2];          // per direction, [B,2,H,W]
+    int plane_n, plane_b;   // stride_n / (H*W), stride_b / (H*W)
+    int n, H, W, ndir;
+    float half_w, half_h;
+    Div<DM_FAST> dw, dh;
+    // UP variant: links are LOW-RES [2,h,w] fields (strides in floats), up-sampled x8 into the box on the fly
+    int64_t lo_stride_n, lo_stride_b;
+    int h, w;
+    float rh, rw;
+};
+
+template <bool UP, int TW, int TH, int BW, int BH, int MINB>
+__global__ void __launch_bounds__(256, MINB) chainbox_kernel(const __grid_constant__ CUtensorMap tm0,
+                                                             const __grid_constant__ CUtensorMap tm1, ChainBoxArgs a) {
+    constexpr int NX = TW / 32, NR = TH / 8;
+    constexpr uint32_t BOX_BYTES = 2 * BW * BH * 4;
+    extern __shared__ __align__(1024) uint8_t fbt_smem[];
+    __shared__ uint64_t full;
+    __shared__ int bb[4];  // min x0, max x0, min y0, max y0 of the taps that touch the frame
+    __shared__ int2 origin;
+    constexpr int TR = BH / 8 + 3;  // low-res rows a BH-row box can touch (scale < 1/8), +1 slack
+    float* Tb = reinterpret_cast<float*>(fbt_smem + 2 * BW * BH * 4);  // UP: [2][TR][BW] horizontally interpolated rows
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = a.W, H = a.H, HW = H * W;
+    const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    const int b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const int X0 = blockIdx.x * TW + lane, Y0 = blockIdx.y * TH + warp;
+    if (threadIdx.x == 0) {
+        bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN;  // fkey space
+        tc::mbar_init(&full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const Div2 dW = make_div2(a.dw), dH = make_div2(a.dh);
+    const F2 one2 = pk1(1.0f), two2 = pk1(2.0f), hw2 = pk1(a.half_w), hh2 = pk1(a.half_h);
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    // chain state: pixel (c, k) -> (X0 + 32 c, Y0 + 8 k); pairs (k, k+1) share a packed register
+    F2 cx[NX][NR / 2], cy[NX][NR / 2];
+#pragma unroll
+    for (int c = 0; c < NX; c++)
+#pragma unroll
+        for (int k = 0; k < NR / 2; k++) {
+            cx[c][k] = pk1((float)(X0 + 32 * c));
+            cy[c][k] = pk((float)(Y0 + 16 * k), (float)(Y0 + 16 * k + 8));
+        }
+    const float* sp = reinterpret_cast<const float*>(fbt_smem);
+    for (int i = 0; i < a.n; i++) {
+        // ---- bounding box of the tap origins ---------------------------------------------------------
+        // x0 = floor(unnormalise(normalise(cx))) is a monotone function of cx (every step is), so the box of
+        // the origins is that function of the box of the coordinates: 4 min/max per pixel here, the exact
+        // arithmetic once per thread below.  Coordinates are clamped to where a 2x2 footprint still
+        // touches the frame (pixels further out sample zeros whatever the box holds); NaNs drop out.
+        float fmnx = 3.0e38f, fmxx = -3.0e38f, fmny = 3.0e38f, fmxy = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < NX; c++)
+#pragma unroll
+            for (int k = 0; k < NR / 2; k++) {
+                float xs[2], ys[2];
+                unpk(cx[c][k], xs[0], xs[1]);
+                unpk(cy[c][k], ys[0], ys[1]);
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const float x = fminf(fmaxf(xs[p], -1.0f), wm1 + 0.5f), y = fminf(fmaxf(ys[p], -1.0f), hm1 + 0.5f);
+                    fmnx = fminf(fmnx, x); fmxx = fmaxf(fmxx, x); fmny = fminf(fmny, y); fmxy = fmaxf(fmxy, y);
+                }
+            }
+        {
+            const int k0 = __reduce_min_sync(0xffffffffu, fkey(fmnx)), k1 = __reduce_max_sync(0xffffffffu, fkey(fmxx));
+            const int k2 = __reduce_min_sync(0xffffffffu, fkey(fmny)), k3 = __reduce_max_sync(0xffffffffu, fkey(fmxy));
+            if (lane == 0) { atomicMin(&bb[0], k0); atomicMax(&bb[1], k1); atomicMin(&bb[2], k2); atomicMax(&bb[3], k3); }
+        }
+        __syncthreads();  // also: every thread is done reading the previous link's box
+        const float* lp = nullptr;
+        int2 o;
+        if (UP) {
+            // ---- box <- 8 * bilinear x8 of the low-res link, ATen's arithmetic (UpSample.cuh), separable:
+            // T(r, X) = fma(l0x, L[r][i0x], l1x * L[r][i1x]) once per low-res row and column, then
+            // value(Y, X) = 8 * fma(l0y, T(i0y, X), l1y * T(i1y, X)).  Cells outside the frame are 0.
+            const int bx0 = tap_origin(funkey(bb[0]), a.dw, a.half_w), bx1 = tap_origin(funkey(bb[1]), a.dw, a.half_w);
+            const int by0 = tap_origin(funkey(bb[2]), a.dh, a.half_h), by1 = tap_origin(funkey(bb[3]), a.dh, a.half_h);
+            const int ox = bx0 - (BW - (bx1 + 2 - bx0)) / 2, oy = by0 - (BH - (by1 + 2 - by0)) / 2;
+            o = make_int2(ox, oy);
+            __syncthreads();  // everyone has read bb
+            if (threadIdx.x == 0) { bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN; }
+            const float* lo = (dir ? a.links[1] : a.links[0]) + b * a.lo_stride_b + i * a.lo_stride_n;
+            const int hw = a.h * a.w;
+            const int ya = max(oy, 0), yb = min(oy + BH - 1, H - 1);
+            const int r_lo = axis_tap(ya, a.rh, a.h).i0;
+            const int nrow = ya <= yb ? axis_tap(yb, a.rh, a.h).i1 - r_lo + 1 : 0;
+            F2* Tp = reinterpret_cast<F2*>(Tb);  // [TR][BW] of (x, y) channel pairs
+            constexpr int RG = (256 + BW - 1) / BW;  // row groups: one column per thread
+            for (int e = threadIdx.x; e < BW * RG; e += 256) {
+                const int c = e % BW, rg = e / BW, X = ox + c;
+                const bool xin = X >= 0 && X < W;
+                const AxisTap tx = axis_tap(xin ? X : 0, a.rw, a.w);
+                const F2 l0 = pk1(tx.l0), l1 = pk1(tx.l1);
+                for (int r = rg; r < nrow; r += RG) {
+                    const float* row = lo + (r_lo + r) * a.w;
+                    F2 v;
+                    v.v = 0ull;  // columns outside the frame hold zeros: the vertical pass needs no column test
+                    if (xin) v = fma2(l0, pk(__ldg(row + tx.i0), __ldg(row + hw + tx.i0)), mul2(l1, pk(__ldg(row + tx.i1), __ldg(row + hw + tx.i1))));
+                    Tp[r * BW + c] = v;
+                }
+            }
+            __syncthreads();
+            float* box = reinterpret_cast<float*>(fbt_smem);
+            const F2 eight2 = pk1(8.0f);
+            for (int y = warp; y < BH; y += 8) {
+                const int Y = oy + y;
+                float* bxr = box + y * BW + lane;
+                if (Y >= 0 && Y < H) {  // warp-uniform
+                    const AxisTap ty = axis_tap(Y, a.rh, a.h);
+                    const F2* t0 = Tp + (ty.i0 - r_lo) * BW + lane;
+                    const F2* t1 = Tp + (ty.i1 - r_lo) * BW + lane;
+                    const F2 l0 = pk1(ty.l0), l1 = pk1(ty.l1);
+#pragma unroll
+                    for (int c = 0; c < BW; c += 32) {
+                        float vx, vy;
+                        unpk(mul2(eight2, fma2(l0, t0[c], mul2(l1, t1[c]))), vx, vy);
+                        bxr[c] = vx;
+                        bxr[BW * BH + c] = vy;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BW; c += 32) { bxr[c] = 0.0f; bxr[BW * BH + c] = 0.0f; }
+                }
+            }
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0) {
+                const int bx0 = tap_origin(funkey(bb[0]), a.dw, a.half_w), bx1 = tap_origin(funkey(bb[1]), a.dw, a.half_w);
+                const int by0 = tap_origin(funkey(bb[2]), a.dh, a.half_h), by1 = tap_origin(funkey(bb[3]), a.dh, a.half_h);
+                int ox = bx0 - (BW - (bx1 + 2 - bx0)) / 2, oy = by0 - (BH - (by1 + 2 - by0)) / 2;
+                ox &= ~3;  // TMA: 16-byte aligned box start
+                origin = make_int2(ox, oy);
+                bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN;  // for the next link (ordered by the barrier below)
+                mbar_arrive_expect_tx(&full, BOX_BYTES);
+                tma_load_3d(fbt_smem, dir ? &tm1 : &tm0, ox, oy, b * a.plane_b + i * a.plane_n, &full);
+            }
+            mbar_wait_bounded(&full, i & 1);
+            o = origin;
+            lp = (dir ? a.links[1] : a.links[0]) + ((int64_t)b * a.plane_b + (int64_t)i * a.plane_n) * HW;
+        }
+        // ---- gather and advance ----------------------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < NX; c++)
+#pragma unroll
+            for (int k = 0; k < NR / 2; k++) {
+                const F2 gx = sub2(dW(mul2(two2, cx[c][k])), one2), gy = sub2(dH(mul2(two2, cy[c][k])), one2);
+                // products as fma(a, b, +0): an fma result cannot be contracted into the subtraction below;
+                // identical to the rounded product unless it is -0, which (g + 1) * half never is here
+                const F2 ix = mul2_nc(add2(gx, one2), hw2), iy = mul2_nc(add2(gy, one2), hh2);   // GridSampler.cuh:22-31
+                float ixs[2], iys[2], xws[2], yns[2], t[2][8];
+                unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
+                bool touches[2], miss[2];
+                int x0s[2], y0s[2];
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);  // saturates for huge, 0 for NaN
+                    x0s[p] = x0; y0s[p] = y0;
+                    xws[p] = __int2float_rn(x0); yns[p] = __int2float_rn(y0);
+                    // the 2x2 footprint touches the frame: -1 <= x0 <= W-1 and -1 <= y0 <= H-1
+                    touches[p] = (unsigned)(x0 + 1) <= (unsigned)W && (unsigned)(y0 + 1) <= (unsigned)H;
+                    const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
+                    miss[p] = touches[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
+                    const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
+                    t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
+                    t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
+                }
+                if (miss[0] || miss[1]) {  // rare: footprint outside the staged box, predicated taps from global memory
+#pragma unroll
+                    for (int p = 0; p < 2; p++)
+                        if (miss[p]) {
+                            const int x0 = x0s[p], y0 = y0s[p];
+                            const bool x0in = x0 >= 0, x1in = x0 + 1 < W, y0in = y0 >= 0, y1in = y0 + 1 < H;
+#pragma unroll
+                            for (int u = 0; u < 8; u++) t[p][u] = 0.0f;
+                            if (UP) {
+                                const UpLink L{(dir ? a.links[1] : a.links[0]) + b * a.lo_stride_b + i * a.lo_stride_n, a.h, a.w, a.rh, a.rw};
+                                if (x0in && y0in) { const float2 v = L.value(y0, x0); t[p][0] = v.x; t[p][4] = v.y; }
+                                if (x1in && y0in) { const float2 v = L.value(y0, x0 + 1); t[p][1] = v.x; t[p][5] = v.y; }
+                                if (x0in && y1in) { const float2 v = L.value(y0 + 1, x0); t[p][2] = v.x; t[p][6] = v.y; }
+                                if (x1in && y1in) { const float2 v = L.value(y0 + 1, x0 + 1); t[p][3] = v.x; t[p][7] = v.y; }
+                            } else {
+                                const float* g = lp + y0 * W + x0;
+                                if (x0in && y0in) { t[p][0] = __ldg(g); t[p][4] = __ldg(g + HW); }
+                                if (x1in && y0in) { t[p][1] = __ldg(g + 1); t[p][5] = __ldg(g + HW + 1); }
+                                if (x0in && y1in) { t[p][2] = __ldg(g + W); t[p][6] = __ldg(g + HW + W); }
+                                if (x1in && y1in) { t[p][3] = __ldg(g + W + 1); t[p][7] = __ldg(g + HW + W + 1); }
+                            }
+                        }
+                }
+                const F2 xw2 = pk(xws[0], xws[1]), yn2 = pk(yns[0], yns[1]);
+                const F2 wx = sub2(ix, xw2), e = sub2(add2(xw2, one2), ix), wy = sub2(iy, yn2), s_ = sub2(add2(yn2, one2), iy);
+                const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
+                float sxs[2], sys[2];
+                unpk(combine4_2(pk(t[0][0], t[1][0]), pk(t[0][1], t[1][1]), pk(t[0][2], t[1][2]), pk(t[0][3], t[1][3]), nw, ne, sw, se), sxs[0], sxs[1]);
+                unpk(combine4_2(pk(t[0][4], t[1][4]), pk(t[0][5], t[1][5]), pk(t[0][6], t[1][6]), pk(t[0][7], t[1][7]), nw, ne, sw, se), sys[0], sys[1]);
+                // a footprint entirely outside the frame samples only padding: +0 (its weights may be garbage)
+                const F2 sx = pk(touches[0] ? sxs[0] : 0.0f, touches[1] ? sxs[1] : 0.0f);
+                const F2 sy = pk(touches[0] ? sys[0] : 0.0f, touches[1] ? sys[1] : 0.0f);
+                cx[c][k] = add2(cx[c][k], sx);  // util.py:323
+                cy[c][k] = add2(cy[c][k], sy);
+            }
+    }
+    float* op = (dir ? a.out[1] : a.out[0]) + (int64_t)b * 2 * HW + Y0 * W + X0;
+#pragma unroll
+    for (int c = 0; c < NX; c++)
+#pragma unroll
+        for (int k = 0; k < NR / 2; k++) {
+            float ox[2], oy[2];
+            unpk(sub2(cx[c][k], pk1((float)(X0 + 32 * c))), ox[0], ox[1]);  // util.py:328
+            unpk(sub2(cy[c][k], pk((float)(Y0 + 16 * k), (float)(Y0 + 16 * k + 8))), oy[0], oy[1]);
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                float* q = ptr_at(op, (16 * k + 8 * p) * W + 32 * c);
+                q[0] = ox[p];
+                *ptr_at(q, HW) = oy[p];
+            }
+        }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -334,6 +585,78 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
         case 5: return launch_cfg<32, 48, 64, 72, 4>(a, B, st);
         default: return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
     }
+}
+
+template <bool UP, int TW, int TH, int BW, int BH, int MINB>
+static int launch_chain_cfg(const ChainBoxArgs& a, int64_t B, const float* base0, const float* base1, int64_t planes0,
+                            int64_t planes1, cudaStream_t st) {
+    auto kern = chainbox_kernel<UP, TW, TH, BW, BH, MINB>;
+    constexpr int smem = 2 * BW * BH * 4 + (UP ? 2 * (BH / 8 + 3) * BW * 4 : 0);
+    static bool ready = false;
+    if (a.W % TW != 0 || a.H % TH != 0) return -1;
+    if (!ready) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        ready = true;
+    }
+    CUtensorMap tm0, tm1;
+    memset(&tm0, 0, sizeof(tm0));
+    if (!UP && !make_map(&tm0, base0, planes0, a.H, a.W, BW, BH)) return -1;
+    if (!UP && a.ndir == 2) {
+        if (!make_map(&tm1, base1, planes1, a.H, a.W, BW, BH)) return -1;
+    } else {
+        tm1 = tm0;
+    }
+    dim3 grid(a.W / TW, a.H / TH, (unsigned)(B * a.ndir));
+    PP_LAUNCH(UP ? "chain_up_box" : "chain_dense", st, (kern<<<grid, 256, smem, st>>>(tm0, tm1, a)));
+    return check_launch("chainbox_kernel");
+}
+
+// Dense-link chain through the TMA-staged kernel; -1 = not applicable (caller uses the gather kernels).
+static int launch_chain_box(const float* l0, const float* l1, float* o0, float* o1, int ndir, int n, int64_t B, int H, int W,
+                            int64_t stride_n, int64_t stride_b, cudaStream_t st) {
+    if (chainbox_mode() < 1 || n < 2 || H < 2 || W < 64 || H >= 32768 || W >= 32768 || B * ndir > 65535) return -1;
+    // one CTA per 64x48 tile and link-by-link TMA round trips: pays off from ~3 waves of CTAs (measured: 1.2-1.3x
+    // faster than the gather kernel at 8-32 planes of 720x1280, slower for the 2-plane chunks of pp_flow_stage)
+    if ((int64_t)(W / 64) * (H / 48) * B * ndir < 1200) return -1;
+    const int64_t HW = (int64_t)H * W;
+    if (stride_n % HW != 0 || stride_b % HW != 0) return -1;
+    if (((uintptr_t)l0 | (uintptr_t)(ndir == 2 ? l1 : l0)) & 15) return -1;
+    ChainBoxArgs a;
+    a.links[0] = l0; a.links[1] = l1; a.out[0] = o0; a.out[1] = o1;
+    a.plane_n = (int)(stride_n / HW); a.plane_b = (int)(stride_b / HW);
+    a.n = n; a.H = H; a.W = W; a.ndir = ndir;
+    a.half_w = (float)(W - 1) / 2.0f; a.half_h = (float)(H - 1) / 2.0f;
+    a.dw = make_div<DM_FAST>((float)(W - 1)); a.dh = make_div<DM_FAST>((float)(H - 1));
+    // planes addressable from each base: the last link of the last sample ends at this plane
+    const int64_t planes = (B - 1) * a.plane_b + (int64_t)(n - 1) * a.plane_n + 2;
+    return launch_chain_cfg<false, 64, 48, 96, 72, 3>(a, B, l0, l1, planes, planes, st);
+}
+
+// The fused up-sampling chain measures on par with the chunked scratch path (3.9 vs 4.0 ms at B=64, n=5) but worse
+// end to end, so it is opt-in (PIXPRO_B200_CHAINBOX=2) until its box fill is cheaper.
+static bool chain_up_box_applicable(int n, int64_t B, int ndir, int h, int w) {
+    const int H = 8 * h, W = 8 * w;
+    return chainbox_mode() >= 2 && n >= 2 && W >= 64 && H < 32768 && W < 32768 && B * ndir <= 65535 && W % 64 == 0 && H % 48 == 0;
+}
+
+// Chain of n > 1 LOW-RES links with the x8 up-sampling fused in (no scratch, whole batch in one launch);
+// -1 = not applicable.
+static int launch_chain_up_box(const float* l0, const float* l1, float* o0, float* o1, int ndir, int n, int64_t B, int h, int w,
+                               int64_t stride_n, int64_t stride_b, cudaStream_t st) {
+    const int H = 8 * h, W = 8 * w;
+    if (!chain_up_box_applicable(n, B, ndir, h, w)) return -1;
+    ChainBoxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.links[0] = l0; a.links[1] = l1; a.out[0] = o0; a.out[1] = o1;
+    a.n = n; a.H = H; a.W = W; a.ndir = ndir;
+    a.half_w = (float)(W - 1) / 2.0f; a.half_h = (float)(H - 1) / 2.0f;
+    a.dw = make_div<DM_FAST>((float)(W - 1)); a.dh = make_div<DM_FAST>((float)(H - 1));
+    a.lo_stride_n = stride_n; a.lo_stride_b = stride_b; a.h = h; a.w = w;
+    a.rh = up_scale(h, H); a.rw = up_scale(w, W);
+    return launch_chain_cfg<true, 64, 48, 96, 72, 3>(a, B, nullptr, nullptr, 0, 0, st);
 }
 
 }  // namespace fbt

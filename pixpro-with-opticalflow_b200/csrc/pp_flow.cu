@@ -654,6 +654,16 @@ static int launch_chain_dm(const float* l0, const float* l1, float* o0, float* o
         PP_LAUNCH("chain_up", st, upchain1_kernel<DM><<<grid, block, 0, st>>>(a));
         return check_launch("upchain1_kernel");
     }
+    if constexpr (DM == DM_FAST) {
+        if (up && n > 1 && !is_norm) {  // x8 up-sampling fused into the box-staged chain; -1 = not applicable
+            const int rc = fbt::launch_chain_up_box(l0, l1, o0, o1, ndir, n, B, h, w, stride_n, stride_b, st);
+            if (rc != -1) return rc;
+        }
+        if (!up && n > 1 && !is_norm) {  // TMA-staged dense chain (pp_fbtile.cuh); -1 = not applicable
+            const int rc = fbt::launch_chain_box(l0, l1, o0, o1, ndir, n, B, H, W, stride_n, stride_b, st);
+            if (rc != -1) return rc;
+        }
+    }
     if (!up && n > 1 && !is_norm && (W % 128 == 0) && H >= 2) {
         dim3 grid4(W / 128, (H + 7) / 8, (unsigned)(B * ndir));
         if (W == 1280 && H == 720) PP_LAUNCH("chain_dense", st, (chain_dense4_kernel<DM, 1280, 720><<<grid4, block, 0, st>>>(a)));
@@ -819,7 +829,9 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
     int64_t link = 2 * (int64_t)h * w;  // loader layout [B,n,2,h,w]
     int rc;
     const int64_t per = chain_chunk_bytes(n, h, w);
-    if (flow_up && n > 1 && !is_norm && workspace && workspace_bytes >= per) {
+    const bool fused_up_chain = flow_up && n > 1 && !is_norm && div_mode != PP_DIV_RCP && div_certified((float)(W - 1)) &&
+                                div_certified((float)(H - 1)) && fbt::chain_up_box_applicable(n, B, 2, h, w);
+    if (!fused_up_chain && flow_up && n > 1 && !is_norm && workspace && workspace_bytes >= per) {
         // Chained links: evaluating the x8 up-sampling inside every one of the 4 taps of every chain
         // step costs ~1100 instructions per pixel (7.5 ms at B=64, n=5: profiles/r01_*).  Instead the
         // links of a chunk of samples are up-sampled ONCE by the strip kernel into an L2-sized scratch

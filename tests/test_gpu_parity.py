@@ -214,6 +214,38 @@ def test_fb_tile_kernel_rough_field_and_no_timeouts(ops, orc):
         assert after > before, "the tile kernel should have taken taps from global memory on white noise"
 
 
+def test_concat_flow_tma_staged_chain_vs_oracle(ops, orc, synth):
+    """Dense full-resolution links, enough tiles (4 planes of 720x1280 = 1200 CTAs) for pp_concat_flow to take
+    the TMA-staged chain kernel; one sample is pushed out of the frame, one is rough (taps outside the box)."""
+    f, _ = synth.flow_fields(4, 3, seed=21, magnitude=1.5)
+    f[1] *= 12.0   # leaves the frame after the first link
+    g = torch.Generator().manual_seed(3)
+    f[2] += torch.randn(f[2].shape, generator=g) * 0.8   # incoherent field: footprints miss the staged box
+    up = ops.upflow8(f.to(DEV).reshape(-1, 2, 90, 160)).reshape(4, 3, 2, 720, 1280).permute(1, 0, 2, 3, 4).contiguous()
+    want = orc.concat_flow(npy(up))
+    assert_bits_equal(npy(ops.concat_flow(up)), want, "concat_flow (TMA-staged)")
+
+
+def test_fused_upsampling_chain_opt_in_vs_default(synth):
+    """PIXPRO_B200_CHAINBOX=2 (fused x8 up-sampling + chain in one launch) is opt-in; it must give the
+    same bits as the default chunked path.  Runs in a subprocess: the mode is read once per process."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, torch; sys.path.insert(0, %r); from pixpro_b200 import ops, synth\n"
+        "f, b = synth.flow_fields(3, 5, seed=11)\n"
+        "o = ops.flow_stage(f.cuda(), b.cuda())\n"
+        "print(hashlib.sha256(b''.join(t.cpu().numpy().tobytes() for t in o)).hexdigest())\n"
+    ) % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pixpro-with-opticalflow_b200")
+    outs = []
+    for mode in ("1", "2"):
+        env = dict(os.environ, PIXPRO_B200_CHAINBOX=mode)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
+
+
 def test_flow_stage_empty_batch(ops):
     z = torch.zeros(0, 2, 2, 8, 8, device=DEV)
     ff, fb, mf, mb = ops.flow_stage(z, z)
