@@ -2,7 +2,7 @@
 // field staged in shared memory by TMA.  Included by pp_flow.cu (needs its FB helpers).
 //
 // Why: the gather-from-global kernels (fbmask4*_kernel) are bound by L1 data-pipe wavefronts, not
-// by DRAM or issue slots (profiles/r01_final_flow_ncu_summary.txt: 30 wavefronts per warp-pixel
+// by DRAM or issue slots (profiles/r01_n_flow_gather_ncu_summary.txt: 30 wavefronts per warp-pixel
 // for 11 memory instructions — every one of the 8 tap loads of a warp touches ~3.3 cache lines,
 // and the 8 loads touch the same lines again and again).  Here each TW x TH tile's gather
 // footprint is brought into shared memory ONCE by a single TMA box copy and the 8 taps per pixel

@@ -513,7 +513,7 @@ __device__ __noinline__ void fb_pixel_redo(const float* f, const float* g, uint8
 // fbmask4_kernel on packed fp32 pairs (certified-division mode only).  Same pixel layout (one
 // thread -> pixels X0 + lane + 32*j of its row); pixels (j, j+1) form the two halves of every FFMA2 /
 // FMUL2 / FADD2, which halves the issue slots of the ~60 exactly-rounded operations per pixel
-// (profiles/r01_final_flow_ncu_summary.txt: the scalar kernel is issue-bound, 119 instructions per
+// (profiles/r01_n_flow_gather_ncu_summary.txt: the scalar kernel is issue-bound, 119 instructions per
 // pixel).  Three more instruction savings, all value-preserving:
 //  * the 2-instruction certified division (pp_common.cuh);
 //  * floor as F2I.FLOOR + I2FP (one conversion-unit op instead of FRND + F2I);
