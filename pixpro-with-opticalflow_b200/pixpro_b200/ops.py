@@ -373,6 +373,17 @@ def ppm(feat, val, gamma=2.0, clamp_value=0.0, final_norm=True):
 
 # -------------------------------------------------------------------------- value transform --
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for independent launches inside an op (created lazily)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 class _Conv1x1(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -408,8 +419,21 @@ class _Conv1x1(torch.autograd.Function):
         db = torch.empty((Cout,), device=x.device, dtype=torch.float32) if need_b else None
         ws = torch.empty((L.pp_conv1x1_bwd_workspace(B, Cin, Cout, P),), device=x.device, dtype=torch.uint8)
         with torch.cuda.device(x.device):
-            _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
-                                         _stream()), "pp_conv1x1_bwd")
+            if need_x and (need_w or need_b):
+                # dgrad and wgrad (+ bias grad) are independent, latency-bound launches: issue the parameter
+                # gradients on a side stream (all buffers were allocated on the current one, which joins below)
+                cur = torch.cuda.current_stream(x.device)
+                side = _side_stream(x.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, _ptr(dw), _ptr(db), _ptr(ws),
+                                                 _stream()), "pp_conv1x1_bwd")
+                _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), None, None, _ptr(ws),
+                                             _stream()), "pp_conv1x1_bwd")
+                cur.wait_stream(side)
+            else:
+                _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
+                                             _stream()), "pp_conv1x1_bwd")
         return dx, (dw.view(ctx.w_shape) if dw is not None else None), db
 
 
