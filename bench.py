@@ -363,7 +363,7 @@ def run_b200(a):
     }
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_arm(a, steps=4, warmup=1)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -431,10 +431,24 @@ def run_reference(a):
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
+    # Libraries write banners to fd 1 (NCCL prints its version line there when a communicator is created):
+    # keep the original stdout for the JSON line only and send everything else to stderr.
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
