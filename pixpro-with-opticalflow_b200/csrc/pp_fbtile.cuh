@@ -87,7 +87,9 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, i
 }
 
 // grid = (W / TW, H / TH, planes); block = 256.  Requires W % TW == 0 and H % TH == 0.
-template <int TW, int TH, int BW, int BH, int MINB>
+// WC/HC > 0: the frame size is a compile-time constant (the 1280x720 frames of the published BDD100K runs): every
+// derived constant and row offset folds into instruction immediates (no per-pixel constant-bank loads).
+template <int TW, int TH, int BW, int BH, int MINB, int WC, int HC>
 __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant__ CUtensorMap tm0,
                                                           const __grid_constant__ CUtensorMap tm1,
                                                           const __grid_constant__ CUtensorMap tp0,
@@ -102,7 +104,14 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
     __shared__ int2 origin;
     __shared__ int nglobal_cta;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = a.W, H = a.H, HW = H * W;
+    const int W = WC ? WC : a.W, H = HC ? HC : a.H, HW = H * W;
+    if (WC) {  // fold every derived constant
+        a.half_w = (float)(WC - 1) / 2.0f; a.half_h = (float)(HC - 1) / 2.0f;
+        a.dw2 = const_div<DM>((float)(WC - 1) / 2.0f);
+        a.dh2 = const_div<DM>((float)(HC - 1) / 2.0f);
+        a.dw = const_div<DM>((float)(WC - 1));
+        a.dh = const_div<DM>((float)(HC - 1));
+    }
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
     const int b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
@@ -529,9 +538,9 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t planes, int H, 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int TW, int TH, int BW, int BH, int MINB>
+template <int TW, int TH, int BW, int BH, int MINB, int WC = 0, int HC = 0>
 static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
-    auto kern = fbbox_kernel<TW, TH, BW, BH, MINB>;
+    auto kern = fbbox_kernel<TW, TH, BW, BH, MINB, WC, HC>;
     constexpr int smem = 2 * BW * BH * 4;
     static bool ready = false;
     static const bool dbg = getenv("PIXPRO_B200_FBDBG") != nullptr;
@@ -583,7 +592,9 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
         case 3: return launch_cfg<64, 32, 96, 56, 4>(a, B, st);
         case 4: return launch_cfg<64, 32, 96, 48, 4>(a, B, st);
         case 5: return launch_cfg<32, 48, 64, 72, 4>(a, B, st);
-        default: return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
+        default:
+            if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
+            return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
     }
 }
 
