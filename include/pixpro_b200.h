@@ -153,6 +153,33 @@ PP_API int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P);
 PP_API int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
                           float* dw, float* db, void* workspace, void* stream);
 
+/* ---- multi-tensor optimizer-side kernels ------------------------------
+ * A parameter set = a DEVICE table of PpMtTensor entries + a DEVICE chunk map of int pairs
+ * {tensor index, chunk index within the tensor}, pp_mt_chunk_elems() elements per chunk, the chunks
+ * of one tensor contiguous and in order; first_chunk[t] .. first_chunk[t+1] are tensor t's chunks. */
+typedef struct PpMtTensor {
+    void* a;         /* EMA: online parameter q (read)        LARS/SGD: parameter p (read/write) */
+    void* b;         /* EMA: momentum parameter k (read/write) LARS/SGD: gradient g (read)       */
+    void* c;         /* LARS/SGD: momentum buffer (read/write), may be null when momentum == 0   */
+    int64_t numel;
+    float s0, s1, s2, s3; /* LARS/SGD: weight_decay, lr, momentum, dampening */
+    int flags;       /* PP_MT_* */
+    int pad_;
+} PpMtTensor;
+#define PP_MT_LARS 1        /* apply the adaptive rate (param group 'ignore' is False, lars.py:123) */
+#define PP_MT_FIRST_STEP 2  /* momentum buffer not initialised yet: buf = grad (torch.optim.SGD) */
+PP_API int pp_mt_chunk_elems(void);
+/* EMA of the key branch — contrast/models/PixPro.py:322-337: k = k*m + q*(1-m), all tensors, one launch.
+ * `one_minus_momentum` is passed separately because the reference forms 1-m in double precision. */
+PP_API int pp_ema_update(const PpMtTensor* table_dev, const int* chunk_map_dev, int nchunks, double momentum,
+                         double one_minus_momentum, void* stream);
+/* LARS.step() over all parameters — contrast/lars.py:109-152 wrapping torch.optim.SGD (no nesterov):
+ * weight decay folded into the gradient, per-tensor norms, adaptive rate, momentum, parameter update.
+ * Three launches, no host synchronisation.  workspace: pp_lars_workspace(ntensors, nchunks) bytes. */
+PP_API int64_t pp_lars_workspace(int ntensors, int nchunks);
+PP_API int pp_lars_sgd_step(const PpMtTensor* table_dev, int ntensors, const int* chunk_map_dev, const int* first_chunk_dev,
+                            int nchunks, double trust_coef, double eps, void* workspace, void* stream);
+
 /* ---- tensor-core building block (tcgen05, 3xTF32: fp32-accurate) ----------------------------
  * C[b] = A[b] * B[b]^T;  A [batch,M,K], B [batch,N,K], C [batch,M,N], all row-major fp32.
  * The PPM / loss contractions at large grids run on the same kernel with fused loaders; this

@@ -272,3 +272,28 @@ def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=
                          _D(alpha_1 or 0.0), _D(alpha_2 or 0.0), _I(int(is_norm)), _I(div_mode),
                          ffp, fbp, mfp, mbp)
     return ff, fb, (mf.astype(bool) if use_mask else None), (mb.astype(bool) if use_mask else None)
+
+
+# ------------------------------------------------------------------ optimizer side
+
+def ema_update(k, q, m, one_minus_m=None):
+    """contrast/models/PixPro.py:330-331, in place on a copy of k; returns the new k."""
+    k, kp = _f(np.array(k, dtype=np.float32, copy=True))
+    q, qp = _f(q)
+    L = lib()
+    L.orc_ema_update.argtypes = [_f32p, _f32p, _L, _D, _D]
+    L.orc_ema_update(kp, qp, k.size, float(m), float(1.0 - m if one_minus_m is None else one_minus_m))
+    return k
+
+
+def lars_sgd_step(p, g, buf, wd, lr, mom, damp=0.0, lars=True, first=False, trust=0.001, eps=1e-8):
+    """One tensor of LARS.step() around SGD (contrast/lars.py:109-152).  Returns (p, buf, rate)."""
+    p, pp_ = _f(np.array(p, dtype=np.float32, copy=True))
+    g, gp = _f(g)
+    buf, bp = _f(np.array(buf if buf is not None else np.zeros_like(p), dtype=np.float32, copy=True))
+    L = lib()
+    L.orc_lars_sgd_step.restype = ctypes.c_float
+    L.orc_lars_sgd_step.argtypes = [_f32p, _f32p, _f32p, _L, _D, _D, _D, _D, _I, _I, _D, _D]
+    rate = L.orc_lars_sgd_step(pp_, gp, bp, p.size, float(wd), float(lr), float(mom), float(damp), int(lars), int(first),
+                               float(trust), float(eps))
+    return p, buf, float(rate)

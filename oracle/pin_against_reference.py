@@ -322,6 +322,47 @@ def main():
                      d_weight=m.value_transform.weight.grad.numpy(), d_bias=m.value_transform.bias.grad.numpy())
         gold[f"featprop_{tag}"] = g
 
+    # ---------------- §8(f) rank 1: EMA of the key branch, LARS + SGD ----------------
+    # (the reference's own contrast/lars.py, loaded by path: the package import would pull in termcolor)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_lars", os.path.join(REF, "contrast", "lars.py"))
+    rlars = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rlars)
+    torch.manual_seed(123)
+    k0, q0 = torch.randn(3001), torch.randn(3001)
+    mom = 1. - (1. - 0.99) * (np.cos(np.pi * 7 / 100) + 1) / 2.   # PixPro.py:326 at k=7, K=100
+    ref = (k0 * mom + q0 * (1. - mom)).numpy()                    # PixPro.py:330
+    rep.exact("f1 EMA update", orc.ema_update(k0.numpy(), q0.numpy(), mom), ref)
+    gold["ema"] = dict(k=k0.numpy(), q=q0.numpy(), m=np.float64(mom), out=ref)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.ReLU(), torch.nn.Conv2d(8, 4, 1))
+    groups = rlars.add_weight_decay(net, 1e-5)
+    ropt = rlars.LARS(torch.optim.SGD(groups, lr=0.3, momentum=0.9), eps=1e-8, trust_coef=0.001)
+    plist = [p for g_ in ropt.param_groups for p in g_["params"]]
+    meta = [(g_["weight_decay"], g_["lr"], g_["momentum"], g_["dampening"], not g_["ignore"]) for g_ in ropt.param_groups
+            for _ in g_["params"]]
+    state = [(p.detach().numpy().copy(), None) for p in plist]
+    lg = dict(n_params=np.int64(len(plist)), n_steps=np.int64(3), trust=np.float64(0.001), eps=np.float64(1e-8),
+              meta=np.array([[m_[0], m_[1], m_[2], m_[3], float(m_[4])] for m_ in meta], np.float64))
+    for i, (p0, _) in enumerate(state):
+        lg[f"p{i}_init"] = p0
+    for step in range(3):
+        ropt.zero_grad()
+        net(torch.randn(4, 3, 8, 8)).square().mean().backward()
+        grads = [p.grad.detach().numpy().copy() for p in plist]
+        ropt.step()
+        for i, p in enumerate(plist):
+            wd, lr, mo, da, lars = meta[i]
+            pn, bn, _ = orc.lars_sgd_step(state[i][0], grads[i], state[i][1], wd, lr, mo, da, lars=lars, first=state[i][1] is None)
+            want = p.detach().numpy().copy()
+            if lars:
+                rep.close(f"f1 LARS step {step} tensor {i}", pn, want, 1e-6)
+            else:
+                rep.exact(f"f1 SGD  step {step} tensor {i} (LARS-ignored)", pn, want)
+            state[i] = (pn, bn)
+            lg[f"g{i}_s{step}"] = grads[i]
+            lg[f"p{i}_s{step}"] = want
+    gold["lars_sgd"] = lg
+
     width = max(len(r[0]) for r in rep.rows)
     for name, res in rep.rows:
         print(f"{name:<{width}}  {res}")

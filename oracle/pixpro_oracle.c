@@ -718,3 +718,58 @@ ORC_API void orc_set_num_threads(int n) {
     (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * optimizer-side loops (test oracle for pp_ema_update / pp_lars_sgd_step).
+ * ------------------------------------------------------------------------------------------ */
+
+/* contrast/models/PixPro.py:330-331  param_k = param_k * m + param_q * (1 - m)
+ * (tensor * python float: the scalar is rounded to fp32; three separately rounded ops). */
+ORC_API void orc_ema_update(float* k, const float* q, long n, double m, double one_minus_m) {
+    const float mf = (float)m, omf = (float)one_minus_m;
+    for (long i = 0; i < n; i++) {
+        volatile float a = k[i] * mf;
+        volatile float b = q[i] * omf;
+        k[i] = a + b;
+    }
+}
+
+/* One tensor of LARS.step() (contrast/lars.py:109-152) around torch.optim.SGD (no nesterov):
+ *   g' = g.add(p, alpha=wd)            -> fmaf(wd, p, g)        (ATen add-with-alpha fuses)
+ *   a  = trust * |p| / (|g'| + eps)    fp32 ops, if lars and both norms > 0, else 1
+ *   g''= g' * a                        (only when lars)
+ *   buf = g'' (first) | buf.mul_(mom).add_(g'', alpha=1-damp) ;  p.add_(buf, alpha=-lr)
+ * Norms are accumulated in double (torch's fp32 reduction order is not reproduced: tolerance).
+ * Returns the adaptive rate. */
+ORC_API float orc_lars_sgd_step(float* p, const float* g, float* buf, long n, double wd, double lr, double mom, double damp,
+                        int lars, int first, double trust, double eps) {
+    const float wdf = (float)wd, nlr = -(float)lr, momf = (float)mom, omd = 1.0f - (float)damp;
+    float a = 1.0f;
+    if (lars) {
+        double sp = 0.0, sg = 0.0;
+        for (long i = 0; i < n; i++) {
+            const float gv = wdf > 0.0f ? fmaf(wdf, p[i], g[i]) : g[i];
+            sp += (double)p[i] * p[i];
+            sg += (double)gv * gv;
+        }
+        const float pn = (float)sqrt(sp), gn = (float)sqrt(sg);
+        if (pn > 0.0f && gn > 0.0f) {
+            volatile float num = (float)trust * pn;
+            volatile float den = gn + (float)eps;
+            a = num / den;
+        }
+    }
+    for (long i = 0; i < n; i++) {
+        float gv = wdf > 0.0f ? fmaf(wdf, p[i], g[i]) : g[i];
+        if (lars) { volatile float t = gv * a; gv = t; }
+        if (momf != 0.0f) {
+            float b;
+            if (first) b = gv;
+            else { volatile float t = buf[i] * momf; b = fmaf(omd, gv, t); }
+            buf[i] = b;
+            gv = b;
+        }
+        p[i] = fmaf(nlr, gv, p[i]);
+    }
+    return a;
+}

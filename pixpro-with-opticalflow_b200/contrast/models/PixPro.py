@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from torch.distributed import get_world_size
 
 from pixpro_b200 import ops as _ops
+from pixpro_b200 import optim as _optim
 
 from .base import BaseModel
 
@@ -156,9 +157,12 @@ class PixPro(BaseModel):
         pairs = [(self.encoder, self.encoder_k), (self.projector, self.projector_k)]
         if self.pixpro_ins_loss_weight > 0.:
             pairs.append((self.projector_instance, self.projector_instance_k))
-        for online, momentum in pairs:
-            for p_q, p_k in zip(online.parameters(), momentum.parameters()):
-                p_k.data = p_k.data * m + p_q.data * (1. - m)
+        qk = [(p_q.data, p_k.data) for online, momentum in pairs for p_q, p_k in zip(online.parameters(), momentum.parameters())]
+        if qk and all(q.is_cuda and k.is_cuda and q.dtype == torch.float32 and q.is_contiguous() and k.is_contiguous() for q, k in qk):
+            _optim.ema_update(qk, m, cache_key=id(self))  # all parameters in one launch (pp_ema_update)
+        else:  # module kept on the host (construction-time checks, CPU unit tests): the reference's own loop
+            for p_q, p_k in qk:
+                p_k.copy_(p_k * m + p_q * (1. - m))
 
     def _value(self, feat):
         """value_transform(feat) (PixPro.py:343).  The published setting (transform_layer=1, a 1x1

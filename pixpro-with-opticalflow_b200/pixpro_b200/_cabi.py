@@ -24,6 +24,10 @@ SIGNATURES = {
     "pp_profile_enable": (_i, [_i]),
     "pp_profile_num_kernels": (_i, []),
     "pp_profile_get": (_i, [_i, ctypes.c_char_p, _i, ctypes.POINTER(_l), ctypes.POINTER(_d)]),
+    "pp_mt_chunk_elems": (_i, []),
+    "pp_ema_update": (_i, [_vp, _vp, _i, _d, _d, _vp]),
+    "pp_lars_workspace": (_l, [_i, _i]),
+    "pp_lars_sgd_step": (_i, [_vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp]),
     "pp_upflow8": (_i, [_vp, _l, _i, _i, _vp, _vp]),
     "pp_normalize": (_i, [_vp, _l, _i, _i, _i, _i, _vp, _vp]),
     "pp_concat_flow": (_i, [_vp, _i, _l, _i, _i, _l, _l, _i, _i, _vp, _vp]),

@@ -443,3 +443,82 @@ def test_chunked_chain_equals_scratch_free_chain(ops, synth):
     b_ = ops.flow_stage(f, b, use_workspace=False)
     for x, y in zip(a_, b_):
         assert torch.equal(x, y)
+
+
+# --------------------------------------------------------------------------- optimizer side
+
+def test_ema_update_kernel_golden_and_ragged(orc):
+    from pixpro_b200 import optim
+    g = load_golden("ema")
+    k = cu(g["k"])
+    optim.ema_update([(cu(g["q"]), k)], float(g["m"]), cache_key="t1")
+    assert_bits_equal(npy(k), g["out"], "pp_ema_update (golden)")
+    # many tensors of ragged sizes in one launch (several chunks, unaligned tails, views at odd offsets)
+    gen = torch.Generator().manual_seed(9)
+    sizes = [1, 7, 8191, 8192, 8193, 40000, 3 * 8192 + 5, 256 * 256]
+    base_q = torch.randn(sum(sizes) + 3, generator=gen)
+    base_k = torch.randn(sum(sizes) + 3, generator=gen)
+    dq, dk = base_q.to(DEV), base_k.to(DEV)
+    pairs, off = [], 3  # offset 3: 4-byte aligned views only
+    for n in sizes:
+        pairs.append((dq[off:off + n], dk[off:off + n]))
+        off += n
+    m = 0.9931
+    optim.ema_update(pairs, m, cache_key="t2")
+    want = base_k.numpy().copy()
+    want[3:] = orc.ema_update(base_k.numpy()[3:], base_q.numpy()[3:], m)
+    assert_bits_equal(npy(dk), want, "pp_ema_update (ragged)")
+
+
+def test_lars_sgd_kernel_golden(orc):
+    """pp_lars_sgd_step over all tensors of the golden model, one call per step, chained over 3 steps."""
+    from pixpro_b200.optim import LarsSgdStep
+    from test_oracle_golden import lars_golden_steps
+    g = load_golden("lars_sgd")
+    n, steps = int(g["n_params"]), int(g["n_steps"])
+    params = [cu(g[f"p{i}_init"]) for i in range(n)]
+    bufs = [torch.empty_like(p) for p in params]
+    fused = LarsSgdStep()
+    for s in range(steps):
+        entries = []
+        for i in range(n):
+            wd, lr, mom, damp, lars = g["meta"][i]
+            entries.append((params[i], cu(g[f"g{i}_s{s}"]), bufs[i], wd, lr, mom, damp, bool(lars), s == 0))
+        fused(entries, float(g["trust"]), float(g["eps"]))
+        for i in range(n):
+            want = g[f"p{i}_s{s}"]
+            if g["meta"][i][4]:
+                assert rel_err(npy(params[i]), want) <= 1e-6
+            else:
+                assert_bits_equal(npy(params[i]), want, f"SGD tensor {i} step {s}")
+
+
+def test_lars_mirror_matches_oracle_on_a_cuda_model(orc):
+    """contrast.lars.LARS (this package) driving torch.optim.SGD state on a small CUDA model, against the oracle
+    applied tensor by tensor; also checks that gradients are left untouched and the momentum buffers live in
+    the wrapped optimizer's state (checkpoint compatibility)."""
+    from contrast.lars import LARS, add_weight_decay
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3), torch.nn.BatchNorm2d(16), torch.nn.ReLU(),
+                              torch.nn.Conv2d(16, 300, 3), torch.nn.Flatten(), torch.nn.LazyLinear(10)).to(DEV)
+    net(torch.randn(2, 3, 12, 12, device=DEV))  # materialise the lazy layer
+    opt = LARS(torch.optim.SGD(add_weight_decay(net, 1e-4), lr=0.2, momentum=0.9), eps=1e-8, trust_coef=0.001)
+    state = {}
+    for step in range(3):
+        opt.zero_grad()
+        net(torch.randn(4, 3, 12, 12, device=DEV)).square().mean().backward()
+        before = {p: (npy(p).copy(), npy(p.grad).copy()) for grp in opt.param_groups for p in grp["params"]}
+        opt.step()
+        for grp in opt.param_groups:
+            for p in grp["params"]:
+                p0, g0 = before[p]
+                assert_bits_equal(npy(p.grad), g0, "gradient must be untouched")
+                want, buf, _ = orc.lars_sgd_step(p0, g0, state.get(p), grp["weight_decay"], grp["lr"], grp["momentum"],
+                                                 grp["dampening"], lars=not grp["ignore"], first=p not in state)
+                state[p] = buf
+                if grp["ignore"]:
+                    assert_bits_equal(npy(p), want, "LARS-ignored parameter")
+                else:
+                    assert rel_err(npy(p), want) <= 1e-6
+                assert rel_err(npy(opt.state[p]["momentum_buffer"]), buf) <= 1e-6
+    assert set(opt.state_dict().keys()) == {"state", "param_groups"}

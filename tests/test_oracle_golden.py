@@ -111,3 +111,40 @@ def test_featprop(orc, tag):
     else:
         dfeat = dfs + dv
     assert rel_err(dfeat, g["d_feat"]) < 2e-5
+
+
+# ------------------------------------------------------------------ optimizer side
+
+def test_ema_update_golden(orc):
+    g = load_golden("ema")
+    assert_bits_equal(orc.ema_update(g["k"], g["q"], float(g["m"])), g["out"], "EMA of the key branch")
+
+
+def lars_golden_steps(g):
+    """Yields (tensor index, step, hyper-parameters, p_before, grad, p_after_reference); p_before is the
+    reference's own parameter of the previous step."""
+    n, steps = int(g["n_params"]), int(g["n_steps"])
+    for i in range(n):
+        wd, lr, mom, damp, lars = g["meta"][i]
+        prev = g[f"p{i}_init"]
+        for s in range(steps):
+            yield i, s, (wd, lr, mom, damp, bool(lars)), prev, g[f"g{i}_s{s}"], g[f"p{i}_s{s}"]
+            prev = g[f"p{i}_s{s}"]
+
+
+def test_lars_sgd_golden(orc):
+    """The oracle's LARS + SGD restatement, chained over 3 steps from the initial parameters, against the
+    parameters the real reference optimizer produced: bit-exact where LARS does not scale, 1e-6 where the
+    (order-dependent) norms enter."""
+    g = load_golden("lars_sgd")
+    state = {}
+    for i, s, (wd, lr, mom, damp, lars), _, grad, want in lars_golden_steps(g):
+        p0, buf = state.get(i, (g[f"p{i}_init"], None))
+        p1, buf1, rate = orc.lars_sgd_step(p0, grad, buf, wd, lr, mom, damp, lars=lars, first=buf is None,
+                                           trust=float(g["trust"]), eps=float(g["eps"]))
+        if lars:
+            assert rel_err(p1, want) <= 1e-6 and 0.0 < rate
+        else:
+            assert rate == 1.0
+            assert_bits_equal(p1, want, f"SGD tensor {i} step {s}")
+        state[i] = (p1, buf1)
