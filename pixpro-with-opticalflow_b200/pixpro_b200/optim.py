@@ -27,30 +27,42 @@ def _check(t, what):
                                     f"{t.device} {t.dtype} contiguous={t.is_contiguous()}")
 
 
+def _all_ok(tensors, what):
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            _check(t, what)
+
+
 class _TensorSet:
-    """Device-side table + chunk map of one list of tensor records, cached on its content."""
+    """Device-side table + chunk map of one list of tensor records, cached on a cheap host-side signature
+    (the tuple of raw pointers and scalars): the per-step host cost is collecting the pointers."""
 
     def __init__(self):
-        self.key = None
+        self.sig = None
         self.table = self.cmap = self.first = None
         self.nchunks = 0
+        self.n = 0
 
-    def update(self, recs, device):
-        key = recs.tobytes()
-        if key == self.key:
+    def update(self, sig, build, device):
+        if sig == self.sig:
             return
+        recs = build()
         chunk = _cabi.lib().pp_mt_chunk_elems()
         per = (recs["numel"] + chunk - 1) // chunk
         first = np.zeros(len(recs) + 1, np.int32)
         np.cumsum(per, out=first[1:])
         self.nchunks = int(first[-1])
+        self.n = len(recs)
         cmap = np.empty((self.nchunks, 2), np.int32)
         cmap[:, 0] = np.repeat(np.arange(len(recs), dtype=np.int32), per)
         cmap[:, 1] = np.arange(self.nchunks, dtype=np.int32) - np.repeat(first[:-1], per)
-        self.table = torch.from_numpy(recs.view(np.uint8).copy()).to(device)
-        self.cmap = torch.from_numpy(cmap).to(device)
-        self.first = torch.from_numpy(first).to(device)
-        self.key = key
+        # one packed upload: [table | chunk map | first-chunk offsets]
+        blob = np.concatenate([recs.view(np.uint8), cmap.view(np.uint8).ravel(), first.view(np.uint8)])
+        dev_blob = torch.from_numpy(blob).to(device)
+        t_end = recs.nbytes
+        c_end = t_end + cmap.nbytes
+        self.table, self.cmap, self.first = dev_blob[:t_end], dev_blob[t_end:c_end], dev_blob[c_end:]
+        self.sig = sig
 
 
 _ema_sets = {}
@@ -62,16 +74,21 @@ def ema_update(pairs, momentum, cache_key=None):
     pairs = list(pairs)
     if not pairs:
         return
-    recs = np.zeros(len(pairs), _REC)
-    for i, (q, k) in enumerate(pairs):
-        _check(q, "ema_update q")
-        _check(k, "ema_update k")
-        if q.shape != k.shape:
-            raise ValueError("ema_update: shape mismatch")
-        recs[i]["a"], recs[i]["b"], recs[i]["numel"] = q.data_ptr(), k.data_ptr(), q.numel()
-    dev = pairs[0][1].device
+    qs, ks = [q for q, _ in pairs], [k for _, k in pairs]
+    sig = (tuple(t.data_ptr() for t in qs), tuple(t.data_ptr() for t in ks), tuple(t.numel() for t in ks))
+    dev = ks[0].device
     ts = _ema_sets.setdefault((cache_key, dev), _TensorSet())
-    ts.update(recs, dev)
+
+    def build():
+        _all_ok(qs, "ema_update q")
+        _all_ok(ks, "ema_update k")
+        if any(q.shape != k.shape for q, k in pairs):
+            raise ValueError("ema_update: shape mismatch")
+        recs = np.zeros(len(pairs), _REC)
+        recs["a"], recs["b"], recs["numel"] = sig[0], sig[1], sig[2]
+        return recs
+
+    ts.update(sig, build, dev)
     m = float(momentum)
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().pp_ema_update(ts.table.data_ptr(), ts.cmap.data_ptr(), ts.nchunks, m, 1. - m,
@@ -89,18 +106,24 @@ class LarsSgdStep:
         """entries: list of (param, grad, momentum_buffer or None, weight_decay, lr, momentum, dampening, lars, first)."""
         if not entries:
             return
-        recs = np.zeros(len(entries), _REC)
-        for i, (p, g, buf, wd, lr, mom, damp, lars, first) in enumerate(entries):
-            _check(p, "lars_sgd_step param")
-            _check(g, "lars_sgd_step grad")
-            if buf is not None:
-                _check(buf, "lars_sgd_step momentum buffer")
-            r = recs[i]
-            r["a"], r["b"], r["c"], r["numel"] = p.data_ptr(), g.data_ptr(), (buf.data_ptr() if buf is not None else 0), p.numel()
-            r["s0"], r["s1"], r["s2"], r["s3"] = wd, lr, mom, damp
-            r["flags"] = (MT_LARS if lars else 0) | (MT_FIRST_STEP if first else 0)
-        dev = entries[0][0].device
-        self.ts.update(recs, dev)
+        ps, gs, bs = [e[0] for e in entries], [e[1] for e in entries], [e[2] for e in entries]
+        sig = (tuple(t.data_ptr() for t in ps), tuple(t.data_ptr() for t in gs), tuple(0 if b is None else b.data_ptr() for b in bs),
+               tuple(e[3:] for e in entries))
+        dev = ps[0].device
+
+        def build():
+            _all_ok(ps, "lars_sgd_step param")
+            _all_ok(gs, "lars_sgd_step grad")
+            _all_ok([b for b in bs if b is not None], "lars_sgd_step momentum buffer")
+            recs = np.zeros(len(entries), _REC)
+            recs["a"], recs["b"], recs["c"] = sig[0], sig[1], sig[2]
+            recs["numel"] = [t.numel() for t in ps]
+            recs["s0"], recs["s1"] = [e[3] for e in entries], [e[4] for e in entries]
+            recs["s2"], recs["s3"] = [e[5] for e in entries], [e[6] for e in entries]
+            recs["flags"] = [(MT_LARS if e[7] else 0) | (MT_FIRST_STEP if e[8] else 0) for e in entries]
+            return recs
+
+        self.ts.update(sig, build, dev)
         L = _cabi.lib()
         need = L.pp_lars_workspace(len(entries), self.ts.nchunks)
         if self.ws is None or self.ws.numel() < need or self.ws.device != dev:
