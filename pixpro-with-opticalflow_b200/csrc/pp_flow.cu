@@ -806,6 +806,31 @@ int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int 
 static const int64_t kChainScratchTarget = 80ll << 20;
 static int64_t chain_chunk_bytes(int n, int h, int w) { return (int64_t)2 * n * 2 * (8 * h) * (8 * w) * sizeof(float); }
 
+// One helper stream + fork/join events per device for pp_flow_stage (the C ABI is called by one host thread per
+// process; created lazily, never destroyed).
+struct FlowSideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static FlowSideStream* flow_side_stream() {
+    static FlowSideStream cache[64];
+    static bool made[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!made[dev]) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        (void)cs;
+        if (cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        made[dev] = true;
+    }
+    return &cache[dev];
+}
+
 int64_t pp_flow_stage_workspace(int64_t B, int n, int h, int w, int flow_up) {
     if (!flow_up || n <= 1 || B <= 0) return 0;
     const int64_t per = chain_chunk_bytes(n, h, w);
@@ -843,16 +868,31 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
         const int64_t HW2 = 2 * (int64_t)H * W;
         float* s0 = (float*)workspace;
         float* s1 = s0 + chunk * n * HW2;
+        // The two directions are independent and have their own scratch halves: the backward direction runs on a
+        // side stream, so that its (HBM/L2-write-bound) up-sampling overlaps the (L1-bound) dense chain of the
+        // forward direction and vice versa.  Fork/join by events: capturable into a CUDA graph.
+        FlowSideStream* ss = flow_side_stream();
+        const bool two = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess &&
+                         cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
+        cudaStream_t st1 = two ? ss->stream : st;
         for (int64_t b0 = 0; b0 < B; b0 += chunk) {
             const int64_t s = (B - b0 < chunk) ? (B - b0) : chunk;
-            // (1) every link of the chunk is one "sample" of the n==1 up-sampling kernel
-            rc = launch_chain(lo_fwd + b0 * n * link, lo_bwd + b0 * n * link, s0, s1, 2, 1, s * n, H, W, h, w, true, link, link,
-                              0, div_mode, st);
-            if (rc) return rc;
-            // (2) chain the dense links
-            rc = launch_chain(s0, s1, flow_fwd + b0 * HW2, flow_bwd + b0 * HW2, 2, n, s, H, W, 0, 0, false, HW2, n * HW2, 0,
-                              div_mode, st);
-            if (rc) return rc;
+            for (int dir = 0; dir < 2; dir++) {
+                const float* lo = (dir ? lo_bwd : lo_fwd) + b0 * n * link;
+                float* sc = dir ? s1 : s0;
+                float* out = (dir ? flow_bwd : flow_fwd) + b0 * HW2;
+                cudaStream_t sd = dir ? st1 : st;
+                // (1) every link of the chunk is one "sample" of the n==1 up-sampling kernel
+                rc = launch_chain(lo, nullptr, sc, nullptr, 1, 1, s * n, H, W, h, w, true, link, link, 0, div_mode, sd);
+                if (rc) return rc;
+                // (2) chain the dense links
+                rc = launch_chain(sc, nullptr, out, nullptr, 1, n, s, H, W, 0, 0, false, HW2, n * HW2, 0, div_mode, sd);
+                if (rc) return rc;
+            }
+        }
+        if (two) {
+            PP_REQUIRE(cudaEventRecord(ss->join, ss->stream) == cudaSuccess && cudaStreamWaitEvent(st, ss->join, 0) == cudaSuccess,
+                       "pp_flow_stage: joining the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
     } else {
         rc = launch_chain(lo_fwd, lo_bwd, flow_fwd, flow_bwd, 2, n, B, H, W, h, w, flow_up != 0, link, (int64_t)n * link,
