@@ -112,3 +112,12 @@ def resnet50(**kw):
 
 def resnet101(**kw):
     return ResNet(Bottleneck, [3, 4, 23, 3], **kw)
+
+
+def resnet152(**kw):
+    return ResNet(Bottleneck, [3, 8, 36, 3], **kw)
+
+
+# names contrast/option.py enumerates for --arch (resnet.py:5-7 of the reference); the deep-stem / wide / ResNeXt
+# variants of the reference are not part of the published runs and are not provided here
+__all__ = ['ResNet', 'resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152']

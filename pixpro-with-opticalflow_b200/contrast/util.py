@@ -149,3 +149,36 @@ def apply_optical_flow(data, flow_model, args):
         else:
             mask_fwd, mask_bwd = mask_fwd[-1], mask_bwd[-1]
     return [flow_fwd, size, mask_fwd], [flow_bwd, size, mask_bwd]
+
+
+# ------------------------------------------------------------------------------------------------
+# Names of the reference's contrast/util.py that are NOT on the pixel path (AverageMeter,
+# MyHelpFormatter, dist_collect, reduce_tensor, ...) are served from the reference's own file when the
+# reference tree is on sys.path behind this package (see contrast/__init__.py), so that the reference's
+# unmirrored modules (`from contrast.util import MyHelpFormatter` in contrast/option.py) keep working.
+_reference_util = None
+
+
+def __getattr__(name):
+    global _reference_util
+    if name.startswith("__"):
+        raise AttributeError(name)
+    if _reference_util is None:
+        import importlib.util
+        import os
+        import contrast as _pkg
+        here = os.path.dirname(os.path.abspath(__file__))
+        for d in list(_pkg.__path__):
+            cand = os.path.join(d, "util.py")
+            if os.path.abspath(d) != here and os.path.isfile(cand):
+                spec = importlib.util.spec_from_file_location("contrast._reference_util", cand)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _reference_util = mod
+                break
+        else:
+            _reference_util = False
+    if _reference_util and hasattr(_reference_util, name):
+        return getattr(_reference_util, name)
+    raise AttributeError(f"module 'contrast.util' has no attribute {name!r} "
+                         "(not on the pixel path; put the reference tree on sys.path after this package to get its own)")

@@ -184,3 +184,25 @@ def test_two_rank_sharding_and_timing_reduction():
     assert s0 != s1                                  # different shards
     assert ms0 == ms1 == 15.0                        # max over ranks
     assert fps0 == fps1 == pytest.approx(4 * 2 * 2 / 15e-3)
+
+
+def test_reference_tree_resolves_behind_the_mirror_package():
+    """with this package first on sys.path and the reference tree behind it, mirrored modules
+    come from here and unmirrored ones (option, lr_scheduler, non-path names of util) from the reference."""
+    import os
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "contrast")):
+        pytest.skip("reference tree not present (GPU box)")
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pixpro-with-opticalflow_b200")
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import contrast.option as o, contrast.util as u, contrast.lars as l, contrast.lr_scheduler as s\n"
+        "from contrast.models import PixPro\n"
+        "assert o.__file__.startswith(%r) and s.__file__.startswith(%r)\n"
+        "assert u.__file__.startswith(%r) and l.__file__.startswith(%r)\n"
+        "assert u.MyHelpFormatter.__module__ == 'contrast._reference_util'\n"
+        "print('ok')\n") % (pkg, ref, ref, ref, pkg, pkg)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-1500:]
