@@ -376,9 +376,10 @@ def ppm(feat, val, gamma=2.0, clamp_value=0.0, final_norm=True):
 _side_streams = {}
 
 
-def _side_stream(device):
-    """One extra stream per device for independent launches inside an op (created lazily)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+def _side_stream(device, idx=0):
+    """Extra streams per device for independent launches inside an op (created lazily)."""
+    d = torch.device(device)
+    key = (d.index if d.index is not None else torch.cuda.current_device(), idx)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=device)
     return _side_streams[key]
@@ -426,11 +427,19 @@ class _Conv1x1(torch.autograd.Function):
                 side = _side_stream(x.device)
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
-                    _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, _ptr(dw), _ptr(db), _ptr(ws),
+                    _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, _ptr(dw), None, _ptr(ws),
                                                  _stream()), "pp_conv1x1_bwd")
+                if need_b:  # the bias gradient is a third independent launch
+                    side2 = _side_stream(x.device, 1)
+                    side2.wait_stream(cur)
+                    with torch.cuda.stream(side2):
+                        _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, None, _ptr(db), _ptr(ws),
+                                                     _stream()), "pp_conv1x1_bwd")
                 _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), None, None, _ptr(ws),
                                              _stream()), "pp_conv1x1_bwd")
                 cur.wait_stream(side)
+                if need_b:
+                    cur.wait_stream(side2)
             else:
                 _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
                                              _stream()), "pp_conv1x1_bwd")
