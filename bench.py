@@ -362,7 +362,7 @@ def run_b200(a):
         "samples_per_s": frames_per_s / a.n_frames,
     }
     if not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_arm(a, steps=4, warmup=1)
+        line["cpu_baseline"] = cpu_arm(a, steps=12, warmup=1)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
