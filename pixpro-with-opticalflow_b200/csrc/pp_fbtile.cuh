@@ -586,16 +586,11 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
     a.dw = make_div<DM_FAST>((float)(W - 1)); a.dh = make_div<DM_FAST>((float)(H - 1));
     a.dw2 = make_div<DM_FAST>((float)(W - 1) / 2.0f); a.dh2 = make_div<DM_FAST>((float)(H - 1) / 2.0f);
     static const int variant = [] { const char* e = getenv("PIXPRO_B200_FBTILE"); return e ? atoi(e) : 1; }();
-    switch (variant) {
-        case 0: return -1;  // disabled: gather kernels
-        case 2: return launch_cfg<64, 48, 96, 72, 3>(a, B, st);
-        case 3: return launch_cfg<64, 32, 96, 56, 4>(a, B, st);
-        case 4: return launch_cfg<64, 32, 96, 48, 4>(a, B, st);
-        case 5: return launch_cfg<32, 48, 64, 72, 4>(a, B, st);
-        default:
-            if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
-            return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
-    }
+    if (variant == 0) return -1;  // disabled: gather kernels
+    if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);  // the published frame size
+    if (H % 48 == 0) return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
+    if (H % 32 == 0) return launch_cfg<64, 32, 96, 56, 4>(a, B, st);
+    return -1;
 }
 
 template <bool UP, int TW, int TH, int BW, int BH, int MINB>
