@@ -286,6 +286,48 @@ def test_regression_loss_vs_oracle(ops, orc, synth, G, C, B, use_flow, use_mask)
     assert rel_err(npy(qg.grad), 3.0 * o["dq"]) < TOL
 
 
+@pytest.mark.parametrize("G", [7, 14])
+def test_regression_loss_adversarial_crops_vs_oracle(ops, orc, G):
+    """Edge cases of the positive mask: disjoint crops (no positive pair: loss_b = 0 by the 1e-6 in the
+    denominator, zero gradient), identical crops (every nearby pair positive), a horizontally flipped crop
+    (negative bin width), a fully invalid FB mask (no positives although the crops overlap), a non-square
+    frame size."""
+    def crop(j, i, w, h, W, H, flip=False):
+        c = [j / (W - 1), i / (H - 1), (j + w - 1) / (W - 1), (i + h - 1) / (H - 1), j, i, w, h, W, H]
+        if flip:
+            c[0], c[2] = c[2], c[0]
+        return [float(v) for v in c]
+    W, H = 640, 360
+    cq = torch.tensor([crop(0, 0, 100, 100, W, H), crop(200, 100, 150, 120, W, H), crop(50, 40, 300, 200, W, H, flip=True),
+                       crop(100, 50, 200, 200, W, H)])
+    ck = torch.tensor([crop(500, 250, 100, 100, W, H), crop(200, 100, 150, 120, W, H), crop(60, 50, 280, 190, W, H),
+                       crop(110, 60, 200, 200, W, H)])
+    B, C = 4, 64
+    gen = torch.Generator().manual_seed(77)
+    q = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1)
+    flow = torch.randn(B, 2, H, W, generator=gen) * 3.0
+    mask = torch.ones(B, H, W, dtype=torch.bool)
+    mask[3] = False  # sample 3: every correspondence rejected by the FB mask
+    for fl, mk in ((None, None), (flow, mask)):
+        o = orc.regression_loss(q.numpy(), k.numpy(), cq.numpy(), ck.numpy(), 0.7, flow=None if fl is None else fl.numpy(),
+                                size=(H, W), mask=None if mk is None else mk.numpy())
+        qg = q.to(DEV).requires_grad_(True)
+        loss, pos_num, _, pos_mask, _ = ops.regression_loss(qg, k.to(DEV), cq.to(DEV), ck.to(DEV), 0.7,
+                                                            flow=None if fl is None else fl.to(DEV), size=(H, W),
+                                                            mask=None if mk is None else mk.to(DEV), debug=True)
+        loss.backward()
+        assert_bits_equal(npy(pos_mask), o["pos_mask"], "pos_mask")
+        assert_bits_equal(npy(pos_num), o["pos_num"], "pos_num")
+        assert npy(pos_num)[0] == 0 and npy(qg.grad)[0].any() == False  # noqa: E712  disjoint crops
+        if fl is not None:
+            assert npy(pos_num)[3] == 0
+        else:
+            assert npy(pos_num)[1] > 0
+        assert abs(loss.item() - o["loss"]) <= TOL * max(abs(o["loss"]), 1e-3)
+        assert rel_err(npy(qg.grad), o["dq"]) < TOL
+
+
 @pytest.mark.parametrize("G,B,gamma,cv", [(7, 6, 2.0, 0.0), (14, 3, 2.0, 0.0), (28, 1, 2.0, 0.0), (7, 2, 1.0, 0.0),
                                           (7, 2, 0.5, 0.1), (9, 2, 3.0, 0.05)])
 @pytest.mark.parametrize("final_norm", [True, False])
