@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="samples per CPU-arm step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eagerly issued step instead of its CUDA-graph replay")
+    ap.add_argument("--sparse", action="store_true",
+                    help="headline = the sparse-correspondence step (flow stage evaluated only at the loss's grid centres, "
+                         "pp_sparse_corr; same loss / counts / gradients, no dense composites or masks)")
     ap.add_argument("--no-overlap", action="store_true", help="PPM forward on the same stream as the flow stage (A/B switch)")
     return ap.parse_args()
 
@@ -204,7 +207,7 @@ def run_b200(a):
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     side = torch.cuda.Stream(device=dev, priority=-1)
 
-    def hot_path(t):
+    def hot_path(t, sparse=a.sparse):
         """One pass of the path on device-resident tensors t; returns (loss, pos stats, grads)."""
         f1 = t["feat1"].detach().requires_grad_(True)
         f2 = t["feat2"].detach().requires_grad_(True)
@@ -220,7 +223,10 @@ def run_b200(a):
             # as PixPro.forward does: both views through the PPM as one batch
             f12 = torch.cat([f1, f2], dim=0)
             pred12 = ops.ppm(f12, ops.conv1x1(f12, w, bias), GAMMA, CLAMP, final_norm=True)
-        if use_flow:
+        if use_flow and sparse:
+            pair = ops.LazyFlowPair(t["lo_f"], t["lo_b"], flow_up=True, alpha_1=ALPHA1, alpha_2=ALPHA2)
+            (ff, fb), (mf, mb) = pair.flow, pair.mask
+        elif use_flow:
             ff, fb, mf, mb = ops.flow_stage(t["lo_f"], t["lo_b"], flow_up=True, alpha_1=ALPHA1, alpha_2=ALPHA2)
         else:
             ff = fb = mf = mb = None
@@ -291,7 +297,7 @@ def run_b200(a):
     e2e_keys = ["feat1", "feat2", "k1", "k2", "c1", "c2"] + (["lo_f", "lo_b"] if use_flow else [])
     host_in = {k: pinned[k] for k in e2e_keys}
     hstep = HostPixelStep(dev, a.batch, C_FEAT, a.grid, size=size, gamma=GAMMA, clamp=CLAMP, pos_ratio=POS_RATIO,
-                          alpha1=ALPHA1, alpha2=ALPHA2)
+                          alpha1=ALPHA1, alpha2=ALPHA2, sparse=a.sparse)
     h2d = hstep.h2d_bytes(host_in)
     d2h = hstep.d2h_bytes()
 
@@ -304,6 +310,41 @@ def run_b200(a):
     e2e_ms = max_over_ranks(sum(timed(e2e_step, a.steps)), world, dev) / a.steps
     barrier()
     e2e_fps = aggregate_frames_per_s(a.batch, world, a.n_frames, e2e_ms)
+
+    # -------- the same step through the sparse correspondence path (reported beside the headline) --------
+    sparse_info = None
+    if use_flow and not a.sparse:
+        for _ in range(3):
+            hot_path(d, sparse=True)
+        n0 = _cabi.launch_count()
+        ref_out = hot_path(d, sparse=False)
+        sp_out = hot_path(d, sparse=True)
+        sp_launches = (_cabi.launch_count() - n0) // 2  # not used for the headline count
+        identical = all(bool(torch.equal(x, y)) for x, y in zip(ref_out, sp_out))
+        sp_fn = lambda: hot_path(d, sparse=True)
+        if not a.no_graph:
+            torch.cuda.synchronize()
+            sp_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(sp_graph):
+                sp_graph_out = hot_path(d, sparse=True)
+            sp_fn = sp_graph.replay
+            for _ in range(2):
+                sp_fn()
+        barrier()
+        sp_ms = max_over_ranks(sum(timed(sp_fn, a.steps)), world, dev) / a.steps
+        sp_hstep = HostPixelStep(dev, a.batch, C_FEAT, a.grid, size=size, gamma=GAMMA, clamp=CLAMP, pos_ratio=POS_RATIO,
+                                 alpha1=ALPHA1, alpha2=ALPHA2, sparse=True)
+        for _ in range(max(3, a.warmup // 2)):
+            sp_hstep(host_in, d["w"], d["bias"])
+        barrier()
+        sp_e2e_ms = max_over_ranks(sum(timed(lambda: sp_hstep(host_in, d["w"], d["bias"]), a.steps)), world, dev) / a.steps
+        barrier()
+        sparse_info = {"what": "same step with the flow stage evaluated only at the loss's grid centres (pp_sparse_corr): "
+                               "no dense composites / FB masks; outputs compared with the dense step below",
+                       "ms_per_step": sp_ms, "value": aggregate_frames_per_s(a.batch, world, a.n_frames, sp_ms),
+                       "e2e_ms_per_step": sp_e2e_ms, "e2e_value": aggregate_frames_per_s(a.batch, world, a.n_frames, sp_e2e_ms),
+                       "unit": "frames/s", "outputs_bit_identical_to_dense_step": identical}
+        del sp_launches
 
     # -------- per-kernel device times -> roofline of the dominant kernel --------
     _cabi.profile_enable(True)
@@ -361,6 +402,10 @@ def run_b200(a):
         "kernels": kernels,
         "samples_per_s": frames_per_s / a.n_frames,
     }
+    if sparse_info is not None:
+        line["sparse_correspondence"] = sparse_info
+    if a.sparse:
+        line["config"]["flow_stage"] = "sparse correspondence (pp_sparse_corr): evaluated at the loss's grid centres only"
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_arm(a, steps=12, warmup=1)
     emit(line)

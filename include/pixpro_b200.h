@@ -128,6 +128,34 @@ PP_API int pp_regression_loss_pair(const float* const* q, const float* const* k,
                                    int div_mode, float* const* loss, float* const* pos_num, float* const* pos_mean,
                                    float* const* dq, void* const* workspace, void* stream);
 
+/* ---- a6+a7 fused, sparse: flow-guided correspondence evaluated only at the grid centres ------
+ * What regression_loss consumes of apply_optical_flow's dense outputs (contrast/util.py:175-248) is
+ * add_optical_flow's P = G*G samples per image (contrast/models/PixPro.py:46-89).  This entry
+ * evaluates exactly those: the composite flow (x8 up-sampling + chain, util.py:185-191,301-330) at
+ * the 4 integer neighbours of every grid centre (centres from the crop descriptors,
+ * PixPro.py:140-143,192-199) and the forward-backward test (util.py:253-297) at its nearest pixel,
+ * with the arithmetic of the dense kernels — bit-identical to pp_flow_stage + pp_add_optical_flow,
+ * without materialising [B,2,H,W] / [B,H,W].  lo_fwd/lo_bwd: loader layout [B,n,2,h,w] (full-res
+ * links if !flow_up).  coord_fwd [B,10]: descriptors of the view warped by the FORWARD composite
+ * (coord1 in PixPro.forward), coord_bwd: by the backward one; either pair (coord, warped) may be
+ * NULL.  warped_* [3,B,P] = (out_x, out_y, mask_grid as 0/1; all ones when !use_mask).
+ * Not supported: --flow_cat_norm (use pp_flow_stage).                                          */
+PP_API int pp_sparse_corr(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, int h, int w, int flow_up, int use_mask,
+                          double alpha_1, double alpha_2, const float* coord_fwd, const float* coord_bwd, int G, int H_orig,
+                          int W_orig, int div_mode, float* warped_fwd, float* warped_bwd, void* stream);
+
+/* regression_loss on centres already warped by pp_sparse_corr (`warped` [3,B,P]) instead of a dense
+ * flow / mask; everything else as pp_regression_loss / pp_regression_loss_pair.               */
+PP_API int pp_regression_loss_warped(const float* q, const float* k, int64_t B, int C, int G, const float* coord_q,
+                                     const float* coord_k, const float* warped, int H_orig, int W_orig, double pos_ratio,
+                                     int div_mode, float* loss, float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask,
+                                     float* centres, void* workspace, void* stream);
+PP_API int pp_regression_loss_pair_warped(const float* const* q, const float* const* k, int64_t B, int C, int G,
+                                          const float* const* coord_q, const float* const* coord_k,
+                                          const float* const* warped, int H_orig, int W_orig, double pos_ratio, int div_mode,
+                                          float* const* loss, float* const* pos_num, float* const* pos_mean,
+                                          float* const* dq, void* const* workspace, void* stream);
+
 /* ---- a9: PixPro.featprop (+ the caller's F.normalize) — contrast/models/PixPro.py:339-363,380
  * feat,val [B,C,P] (val = value_transform(feat), computed by the caller) -> out [B,C,P].
  * final_norm: also apply the L2 normalisation of PixPro.py:380.  saved: device scratch of

@@ -47,6 +47,10 @@ class MLP2d(nn.Module):
 def add_optical_flow(flow, x_grid, y_grid, size, mask=None, verbose=False):
     """PixPro.py:46-89: warp grid points (pixels of the original frame) by the flow sampled
     bilinearly at them; look the FB mask up at the nearest pixel."""
+    if isinstance(flow, _ops.LazyFlow):
+        flow = flow.dense()
+    if isinstance(mask, _ops.LazyMask):
+        mask = mask.dense()
     return _ops.add_optical_flow(flow, x_grid, y_grid, size, mask)
 
 

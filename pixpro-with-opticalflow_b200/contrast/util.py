@@ -2,6 +2,8 @@
 (contrast/util.py:75-366), backed by the sm_100a kernels.  Signatures and return structures
 are the reference's; tensors must live on a CUDA device (the reference hard-codes `.cuda()`
 at util.py:196-197 too)."""
+import os
+
 import torch
 
 from pixpro_b200 import ops as _ops
@@ -48,6 +50,8 @@ def calc_mask_ratio(mask):
     """contrast/util.py:361-366"""
     if mask is None:
         return None
+    if isinstance(mask, _ops.LazyMask):  # sparse mode: logging the ratio is what materialises the dense masks
+        mask = mask.dense()
     return _ops.calc_mask_ratio(mask)
 
 
@@ -104,6 +108,15 @@ def apply_optical_flow(data, flow_model, args):
                                   "precompute flows and pass --use_flow_file")
     _, flow_fwds, flow_bwds = data[5]
     debug = bool(getattr(args, 'debug', False))
+    sparse = bool(getattr(args, 'flow_sparse', False)) or os.environ.get("PIXPRO_B200_SPARSE", "0") == "1"
+    if sparse and not is_use_flow_frames and not debug and not args.flow_cat_norm:
+        # sparse correspondence (pp_sparse_corr): nothing is computed here.  The returned LazyFlow / LazyMask
+        # objects carry the low-res links; regression_loss evaluates the chain and the FB test only at its
+        # G*G grid centres (bit-identical to sampling the dense tensors), and `.dense()` / calc_mask_ratio
+        # materialise the dense tensors on demand through the fused path below.
+        pair = _ops.LazyFlowPair(flow_fwds.cuda(), flow_bwds.cuda(), flow_up=args.flow_up,
+                                 alpha_1=args.alpha1 if is_mask_flow else None, alpha_2=args.alpha2 if is_mask_flow else None)
+        return [pair.flow[0], size, pair.mask[0]], [pair.flow[1], size, pair.mask[1]]
     if not is_use_flow_frames and not debug:
         # fused path: x8 up-sampling, chaining and both FB masks in two launches, nothing else
         # materialised (util.py:185-244 in one pass)

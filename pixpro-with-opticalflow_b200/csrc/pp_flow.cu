@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "pp_common.cuh"
+#include "pp_warp.cuh"
 
 namespace pp {
 
@@ -157,18 +158,12 @@ struct ChainArgs {
     int ndir;
 };
 
-// generic chain: one thread per pixel; block 32x8.
+// One pixel of the composite flow (util.py:301-330): n == 1 clones link 0, else the chain of n
+// grid_samples starting at the pixel's own coordinate.
 //   UP: links are low-res fields up-sampled x8 on the fly;  IS_NORM: --flow_cat_norm arithmetic
 template <bool UP, bool IS_NORM, int DM>
-__global__ void __launch_bounds__(256) chain_kernel(ChainArgs<DM> a) {
-    int X = blockIdx.x * 32 + threadIdx.x;
-    int Y = blockIdx.y * 8 + threadIdx.y;
-    if (X >= a.W || Y >= a.H) return;
-    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
-    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
-    const float* links = (dir ? a.links[1] : a.links[0]) + b * a.stride_b;
-    int HW = a.H * a.W;
-    float ox, oy;
+__device__ __forceinline__ float2 chain_pixel(const ChainArgs<DM>& a, const float* links, int X, int Y) {
+    const int HW = a.H * a.W;
     if (a.n == 1) {  // util.py:303-308: clone (normalised when is_norm)
         float2 v;
         if (UP) {
@@ -178,36 +173,46 @@ __global__ void __launch_bounds__(256) chain_kernel(ChainArgs<DM> a) {
             DenseLink L{links, HW, a.W};
             v = L.value(Y, X);
         }
-        ox = IS_NORM ? norm_flow(v.x, a.dw) : v.x;
-        oy = IS_NORM ? norm_flow(v.y, a.dh) : v.y;
-    } else {
-        float c0x = (float)X, c0y = (float)Y;
-        if (IS_NORM) {
-            c0x = norm_coord(c0x, a.dw);
-            c0y = norm_coord(c0y, a.dh);
-        }
-        float cx = c0x, cy = c0y;
-        for (int i = 0; i < a.n; i++) {  // util.py:315-323
-            const float* lp = links + i * a.stride_n;
-            float gx = IS_NORM ? cx : norm_coord(cx, a.dw);
-            float gy = IS_NORM ? cy : norm_coord(cy, a.dh);
-            float2 s;
-            if (UP) {
-                UpLink L{lp, a.h, a.w, a.rh, a.rw};
-                s = sample_link<IS_NORM>(L, gx, gy, a.W, a.H, a.half_w, a.half_h, a.dw, a.dh);
-            } else {
-                DenseLink L{lp, HW, a.W};
-                s = sample_link<IS_NORM>(L, gx, gy, a.W, a.H, a.half_w, a.half_h, a.dw, a.dh);
-            }
-            cx = add(cx, s.x);
-            cy = add(cy, s.y);
-        }
-        ox = sub(cx, c0x);  // util.py:326,328
-        oy = sub(cy, c0y);
+        return make_float2(IS_NORM ? norm_flow(v.x, a.dw) : v.x, IS_NORM ? norm_flow(v.y, a.dh) : v.y);
     }
+    float c0x = (float)X, c0y = (float)Y;
+    if (IS_NORM) {
+        c0x = norm_coord(c0x, a.dw);
+        c0y = norm_coord(c0y, a.dh);
+    }
+    float cx = c0x, cy = c0y;
+    for (int i = 0; i < a.n; i++) {  // util.py:315-323
+        const float* lp = links + i * a.stride_n;
+        float gx = IS_NORM ? cx : norm_coord(cx, a.dw);
+        float gy = IS_NORM ? cy : norm_coord(cy, a.dh);
+        float2 s;
+        if (UP) {
+            UpLink L{lp, a.h, a.w, a.rh, a.rw};
+            s = sample_link<IS_NORM>(L, gx, gy, a.W, a.H, a.half_w, a.half_h, a.dw, a.dh);
+        } else {
+            DenseLink L{lp, HW, a.W};
+            s = sample_link<IS_NORM>(L, gx, gy, a.W, a.H, a.half_w, a.half_h, a.dw, a.dh);
+        }
+        cx = add(cx, s.x);
+        cy = add(cy, s.y);
+    }
+    return make_float2(sub(cx, c0x), sub(cy, c0y));  // util.py:326,328
+}
+
+// generic chain: one thread per pixel; block 32x8.
+template <bool UP, bool IS_NORM, int DM>
+__global__ void __launch_bounds__(256) chain_kernel(ChainArgs<DM> a) {
+    int X = blockIdx.x * 32 + threadIdx.x;
+    int Y = blockIdx.y * 8 + threadIdx.y;
+    if (X >= a.W || Y >= a.H) return;
+    int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
+    int64_t b = a.ndir == 2 ? (blockIdx.z >> 1) : blockIdx.z;
+    const float* links = (dir ? a.links[1] : a.links[0]) + b * a.stride_b;
+    int HW = a.H * a.W;
+    const float2 v = chain_pixel<UP, IS_NORM, DM>(a, links, X, Y);
     float* o = (dir ? a.out[1] : a.out[0]) + b * 2 * (int64_t)HW + Y * a.W + X;
-    o[0] = ox;
-    o[HW] = oy;
+    o[0] = v.x;
+    o[HW] = v.y;
 }
 
 // Dense-link chain, 4 pixels per thread (X0 + lane + 32*j: every gather of a warp covers 32
@@ -742,6 +747,153 @@ static int launch_fb(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1,
     return launch_fb_dm<DM_IEEE>(f0, f1, m0, m1, cycle, coords1, ndir, B, H, W, alpha_1, alpha_2, is_norm, mask_only4, st);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Sparse correspondence: the flow stage evaluated only where the loss looks at it.
+//
+// regression_loss consumes the dense composite flow and FB mask of apply_optical_flow at the P = G*G
+// grid centres of each sample only (add_optical_flow, PixPro.py:46-89: one bilinear grid_sample of the
+// flow, one nearest lookup of the mask).  Every op of the flow stage is point-wise, so the composite at
+// the 4 integer neighbours of a centre, and the FB test at its nearest pixel (which needs the opposite
+// composite at the 4 neighbours of that pixel's warped position), evaluated on the fly with the same
+// arithmetic, are bit-identical to sampling the dense tensors — at ~10^-3 of the work and no HBM
+// traffic beyond the low-res links.  8 lanes per grid point: lanes 0-3 evaluate the composite at the 4
+// taps, lane 4 at the nearest pixel (phase 1, concurrently); lanes 0-3 then evaluate the opposite
+// composite at the 4 taps of the FB sample (phase 2); lane 0 combines.
+// out[dir] = [3,B,P]: warped centre x, y (PixPro.py:76-83) and the mask bit (PixPro.py:65-70) as 0/1.
+// ------------------------------------------------------------------------------------------
+template <int DM>
+struct SparseArgs {
+    ChainArgs<DM> ch;        // links[0] = forward links, links[1] = backward links; out unused
+    const float* coord[2];   // crop descriptors [B,10] whose centres are warped by direction d (NULL: skip)
+    float* out[2];           // [3,B,P] per direction
+    int64_t B;
+    int G, P, use_mask;
+    float wo, ho;            // W_orig-1, H_orig-1
+    ScalarDiv dG;
+    WarpArgs warp;
+    float a1, a2;
+};
+
+template <bool UP, int DM>
+__global__ void __launch_bounds__(256) sparse_corr_kernel(SparseArgs<DM> a) {
+    const int64_t gid = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+    const int sl = threadIdx.x & 7, lane = threadIdx.x & 31, base = lane & ~7;
+    const unsigned gmask = 0xffu << base;
+    const int64_t BP = a.B * a.P;
+    if (gid >= 2 * BP) return;  // whole 8-lane groups leave together
+    const int dir = gid >= BP ? 1 : 0;
+    if (!a.coord[dir]) return;
+    const int64_t r = gid - (int64_t)dir * BP;
+    const int64_t b = r / a.P;
+    const int p = (int)(r - b * a.P);
+    const ChainArgs<DM>& ch = a.ch;
+    const int W = ch.W, H = ch.H;
+    const float* lf = (dir ? ch.links[1] : ch.links[0]) + b * ch.stride_b;  // this direction's links
+    const float* lg = (dir ? ch.links[0] : ch.links[1]) + b * ch.stride_b;  // the opposite direction's
+    float vqx, vqy;
+    grid_centre(a.coord[dir] + b * 10, p % a.G, p / a.G, a.dG, a.wo, a.ho, vqx, vqy);
+    // PixPro.py:61-62   2 * (x / (W_orig-1)) - 1
+    const float gx = sub(mul(2.0f, a.warp.dwo(vqx)), 1.0f), gy = sub(mul(2.0f, a.warp.dho(vqy)), 1.0f);
+    const Taps t = make_taps(gx, gy, W, H, a.warp.half_w, a.warp.half_h);
+    // ---- phase 1: composite at the 4 taps (lanes 0-3) and at the nearest pixel (lane 4) ----
+    int X = 0, Y = 0;
+    bool act = false;
+    if (sl < 4) {
+        X = t.x0 + (sl & 1); Y = t.y0 + (sl >> 1);
+        act = ((sl & 1) ? t.inx1 : t.inx0) && ((sl >> 1) ? t.iny1 : t.iny0);
+    } else if (sl == 4 && a.use_mask) {  // PixPro.py:65-70 nearest lookup (nearbyint, zeros padding)
+        const float ix = mul(add(gx, 1.0f), a.warp.half_w), iy = mul(add(gy, 1.0f), a.warp.half_h);
+        const float xr = rintf(ix), yr = rintf(iy);
+        act = (xr > -1.0f) && (xr < (float)W) && (yr > -1.0f) && (yr < (float)H);
+        X = act ? (int)xr : 0; Y = act ? (int)yr : 0;
+    }
+    float2 v = make_float2(0.0f, 0.0f);
+    if (act) v = chain_pixel<UP, false, DM>(ch, lf, X, Y);
+    float tx[4], ty[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        tx[c] = __shfl_sync(gmask, v.x, base + c);
+        ty[c] = __shfl_sync(gmask, v.y, base + c);
+    }
+    const float fgx = combine(t, tx[0], tx[1], tx[2], tx[3]);  // PixPro.py:64
+    const float fgy = combine(t, ty[0], ty[1], ty[2], ty[3]);
+    // ---- phase 2: forward-backward test at the nearest pixel (util.py:253-297, fb_kernel<false>) ----
+    bool mg = true;
+    if (a.use_mask) {
+        const float fx = __shfl_sync(gmask, v.x, base + 4), fy = __shfl_sync(gmask, v.y, base + 4);
+        const int Xn = __shfl_sync(gmask, X, base + 4), Yn = __shfl_sync(gmask, Y, base + 4);
+        const bool inb = __shfl_sync(gmask, (int)act, base + 4) != 0;
+        mg = false;
+        if (inb) {  // uniform over the 8-lane group
+            const float fnx = norm_flow(fx, ch.dw), fny = norm_flow(fy, ch.dh);                    // :264
+            const float c1x = add(norm_coord((float)Xn, ch.dw), fnx), c1y = add(norm_coord((float)Yn, ch.dh), fny);  // :271,275
+            const bool in1 = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);                           // :276
+            const Taps t2 = make_taps(c1x, c1y, W, H, ch.half_w, ch.half_h);
+            float2 gv = make_float2(0.0f, 0.0f);
+            if (sl < 4) {
+                const bool act2 = ((sl & 1) ? t2.inx1 : t2.inx0) && ((sl >> 1) ? t2.iny1 : t2.iny0);
+                if (act2) gv = chain_pixel<UP, false, DM>(ch, lg, t2.x0 + (sl & 1), t2.y0 + (sl >> 1));
+                gv.x = norm_flow(gv.x, ch.dw);  // :265 the sampled field is the normalised one
+                gv.y = norm_flow(gv.y, ch.dh);
+            }
+            float ux[4], uy[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                ux[c] = __shfl_sync(gmask, gv.x, base + c);
+                uy[c] = __shfl_sync(gmask, gv.y, base + c);
+            }
+            const float bix = combine(t2, ux[0], ux[1], ux[2], ux[3]), biy = combine(t2, uy[0], uy[1], uy[2], uy[3]);  // :278
+            const float cyx = add(fnx, bix), cyy = add(fny, biy);                                  // :279
+            const float cyc2 = add(mul(cyx, cyx), mul(cyy, cyy));                                  // :293
+            const float f2 = add(mul(fnx, fnx), mul(fny, fny)), b2 = add(mul(bix, bix), mul(biy, biy));
+            const float eps = add(mul(a.a1, add(f2, b2)), a.a2);                                   // :294
+            mg = in1 && (sub(cyc2, eps) <= 0.0f);                                                  // :296
+        }
+    }
+    if (sl == 0) {
+        float ox, oy;
+        if (a.warp.diff) {  // PixPro.py:76-80
+            ox = a.warp.drw(add(mul(vqx, a.warp.rw), fgx));
+            oy = a.warp.drh(add(mul(vqy, a.warp.rh), fgy));
+        } else {  // PixPro.py:82-83
+            ox = add(vqx, fgx);
+            oy = add(vqy, fgy);
+        }
+        float* o = a.out[dir] + b * a.P + p;
+        o[0] = ox;
+        o[BP] = oy;
+        o[2 * BP] = mg ? 1.0f : 0.0f;
+    }
+}
+
+template <int DM>
+static int launch_sparse_dm(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, int h, int w, bool up, bool use_mask,
+                            double alpha_1, double alpha_2, const float* coord_fwd, const float* coord_bwd, int G, int H_orig,
+                            int W_orig, int div_mode, float* warped_fwd, float* warped_bwd, cudaStream_t st) {
+    const int H = up ? 8 * h : h, W = up ? 8 * w : w;
+    SparseArgs<DM> a;
+    ChainArgs<DM>& c = a.ch;
+    c.links[0] = lo_fwd; c.links[1] = lo_bwd; c.out[0] = c.out[1] = nullptr;
+    c.stride_n = 2 * (int64_t)h * w; c.stride_b = (int64_t)n * c.stride_n;  // loader layout [B,n,2,h,w]
+    c.n = n; c.H = H; c.W = W; c.h = h; c.w = w;
+    c.rh = up ? up_scale(h, H) : 0.f; c.rw = up ? up_scale(w, W) : 0.f;
+    c.half_w = (float)(W - 1) / 2.0f; c.half_h = (float)(H - 1) / 2.0f;
+    c.dw = make_div<DM>((float)(W - 1)); c.dh = make_div<DM>((float)(H - 1));
+    c.ndir = 2;
+    a.coord[0] = coord_fwd; a.coord[1] = coord_bwd; a.out[0] = warped_fwd; a.out[1] = warped_bwd;
+    a.B = B; a.G = G; a.P = G * G; a.use_mask = use_mask ? 1 : 0;
+    a.wo = (float)(W_orig - 1); a.ho = (float)(H_orig - 1);
+    a.dG = make_div((float)G, div_mode);
+    a.warp = make_warp_args(H, W, H_orig, W_orig, div_mode);
+    a.a1 = (float)alpha_1; a.a2 = use_mask ? fb_alpha2_eff(alpha_2, H, W) : 0.0f;
+    const int64_t threads = 2 * B * a.P * 8;
+    const unsigned nb = (unsigned)((threads + 255) / 256);
+    if (up) PP_LAUNCH("sparse_corr", st, (sparse_corr_kernel<true, DM><<<nb, 256, 0, st>>>(a)));
+    else PP_LAUNCH("sparse_corr", st, (sparse_corr_kernel<false, DM><<<nb, 256, 0, st>>>(a)));
+    return check_launch("sparse_corr_kernel");
+}
+
 }  // namespace pp
 
 using namespace pp;
@@ -911,6 +1063,24 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
         if (rc) return rc;
     }
     return PP_OK;
+}
+
+int pp_sparse_corr(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, int h, int w, int flow_up, int use_mask,
+                   double alpha_1, double alpha_2, const float* coord_fwd, const float* coord_bwd, int G, int H_orig, int W_orig,
+                   int div_mode, float* warped_fwd, float* warped_bwd, void* stream) {
+    PP_REQUIRE(n >= 1 && B >= 0 && h > 1 && w > 1, "pp_sparse_corr: bad shape B=%lld n=%d h=%d w=%d", (long long)B, n, h, w);
+    PP_REQUIRE(G > 0 && G * G <= 1024 && H_orig > 1 && W_orig > 1, "pp_sparse_corr: bad grid %d or original size %dx%d", G, H_orig, W_orig);
+    PP_REQUIRE((int64_t)h * w * 128 < (1ll << 31) && B * (int64_t)G * G < (1ll << 26), "pp_sparse_corr: problem too large");
+    if (B == 0) return PP_OK;
+    PP_REQUIRE(lo_fwd && lo_bwd, "pp_sparse_corr: null links");
+    PP_REQUIRE((coord_fwd && warped_fwd) || (coord_bwd && warped_bwd), "pp_sparse_corr: no direction requested");
+    PP_REQUIRE((!coord_fwd) == (!warped_fwd) && (!coord_bwd) == (!warped_bwd), "pp_sparse_corr: coord / warped pointers must come in pairs");
+    // few points, latency-bound: plain IEEE division (what the certified fast forms of the dense kernels equal)
+    if (div_mode == PP_DIV_RCP)
+        return launch_sparse_dm<DM_RCP>(lo_fwd, lo_bwd, B, n, h, w, flow_up != 0, use_mask != 0, alpha_1, alpha_2, coord_fwd, coord_bwd,
+                                        G, H_orig, W_orig, div_mode, warped_fwd, warped_bwd, (cudaStream_t)stream);
+    return launch_sparse_dm<DM_IEEE>(lo_fwd, lo_bwd, B, n, h, w, flow_up != 0, use_mask != 0, alpha_1, alpha_2, coord_fwd, coord_bwd,
+                                     G, H_orig, W_orig, div_mode, warped_fwd, warped_bwd, (cudaStream_t)stream);
 }
 
 int64_t pp_fb_redo_count(int reset) {

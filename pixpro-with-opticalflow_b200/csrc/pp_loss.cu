@@ -16,19 +16,12 @@
 #include "pp_common.cuh"
 #include "pp_small.cuh"
 #include "pp_tc.cuh"
+#include "pp_warp.cuh"
 
 namespace pp {
 
 // ---- a7: warp one grid point through the flow ----------------------------------------------
-struct WarpArgs {
-    int Hin, Win;
-    float half_w, half_h;       // (Win-1)/2, (Hin-1)/2
-    ScalarDiv dwo, dho;         // / (W_orig-1), / (H_orig-1)
-    ScalarDiv drw, drh;         // / ratio_w, / ratio_h
-    float rw, rh;               // ratio_w = Win/W_orig, ratio_h = Hin/H_orig  (fp32 of the python double)
-    int diff;                   // flow resolution != original resolution
-};
-
+// (WarpArgs: pp_warp.cuh)
 __device__ __forceinline__ void warp_point(const float* __restrict__ flow, const uint8_t* __restrict__ mask, const WarpArgs& a,
                                            float xg, float yg, float& ox, float& oy, bool& mg) {
     // PixPro.py:61-62   2 * (x / (W_orig-1)) - 1
@@ -60,17 +53,6 @@ __device__ __forceinline__ void warp_point(const float* __restrict__ flow, const
         ox = add(xg, fgx);
         oy = add(yg, fgy);
     }
-}
-
-static WarpArgs make_warp_args(int Hin, int Win, int H_orig, int W_orig, int div_mode) {
-    WarpArgs a;
-    a.Hin = Hin; a.Win = Win;
-    a.half_w = (float)(Win - 1) / 2.0f; a.half_h = (float)(Hin - 1) / 2.0f;
-    a.dwo = make_div((float)(W_orig - 1), div_mode); a.dho = make_div((float)(H_orig - 1), div_mode);
-    a.rw = (float)((double)Win / (double)W_orig); a.rh = (float)((double)Hin / (double)H_orig);
-    a.drw = make_div(a.rw, div_mode); a.drh = make_div(a.rh, div_mode);
-    a.diff = (Hin != H_orig) || (Win != W_orig);
-    return a;
 }
 
 __global__ void __launch_bounds__(128) add_flow_kernel(const float* __restrict__ flow, const uint8_t* __restrict__ mask,
@@ -123,6 +105,7 @@ __device__ __forceinline__ bool pair_pos(float qx, float qy, float kx, float ky,
 struct PrepArgs {
     const float *coord_q, *coord_k, *flow;
     const uint8_t* mask;
+    const float* pre;   // [3,B,P] warped q centres (x, y) and mask bit from pp_sparse_corr, or NULL
     int G, P;
     float wo, ho;       // W_orig-1, H_orig-1
     ScalarDiv dG;       // / G
@@ -159,7 +142,10 @@ __global__ void __launch_bounds__(256) loss_prep_kernel(PrepArgs a) {
         float vkx = mul(add(mul(fx, kbw), ck[0]), a.wo);
         float vky = mul(add(mul(fy, kbh), ck[1]), a.ho);
         bool mg = true;
-        if (a.flow) {  // :200
+        if (a.pre) {  // :200, already evaluated by the sparse correspondence kernel
+            const int64_t BP = a.B * P;
+            vqx = a.pre[b * P + p]; vqy = a.pre[BP + b * P + p]; mg = a.pre[2 * BP + b * P + p] != 0.0f;
+        } else if (a.flow) {  // :200
             int64_t HW = (int64_t)a.warp.Hin * a.warp.Win;
             float ox, oy;
             warp_point(a.flow + b * 2 * HW, a.mask ? a.mask + b * HW : nullptr, a.warp, vqx, vqy, ox, oy, mg);
@@ -325,7 +311,10 @@ __global__ void __launch_bounds__(256) loss_centres_kernel(PrepArgs a) {
         float vqx = mul(add(mul(fx, qbw), cq[0]), a.wo), vqy = mul(add(mul(fy, qbh), cq[1]), a.ho);
         float vkx = mul(add(mul(fx, kbw), ck[0]), a.wo), vky = mul(add(mul(fy, kbh), ck[1]), a.ho);
         bool mg = true;
-        if (a.flow) {
+        if (a.pre) {
+            const int64_t BP = a.B * P;
+            vqx = a.pre[b * P + p]; vqy = a.pre[BP + b * P + p]; mg = a.pre[2 * BP + b * P + p] != 0.0f;
+        } else if (a.flow) {
             int64_t HW = (int64_t)a.warp.Hin * a.warp.Win;
             float ox, oy;
             warp_point(a.flow + b * 2 * HW, a.mask ? a.mask + b * HW : nullptr, a.warp, vqx, vqy, ox, oy, mg);
@@ -488,7 +477,10 @@ __global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs2 s
         float vqx = mul(add(mul(fx, qbw), cq[0]), a.wo), vqy = mul(add(mul(fy, qbh), cq[1]), a.ho);
         float vkx = mul(add(mul(fx, kbw), ck[0]), a.wo), vky = mul(add(mul(fy, kbh), ck[1]), a.ho);
         bool mg = true;
-        if (a.flow) {  // :200
+        if (a.pre) {  // :200, already evaluated by the sparse correspondence kernel
+            const int64_t BP = a.B * P;
+            vqx = a.pre[b * P + p]; vqy = a.pre[BP + b * P + p]; mg = a.pre[2 * BP + b * P + p] != 0.0f;
+        } else if (a.flow) {  // :200
             int64_t HW = (int64_t)a.warp.Hin * a.warp.Win;
             float ox, oy;
             warp_point(a.flow + b * 2 * HW, a.mask ? a.mask + b * HW : nullptr, a.warp, vqx, vqy, ox, oy, mg);
@@ -589,6 +581,7 @@ struct LossCall {
     uint8_t* pos_mask;
     float* centres;
     void* workspace;
+    const float* pre = nullptr;
 };
 
 static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int C, int G, int Hin, int Win, int H_orig,
@@ -606,7 +599,8 @@ static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int
         PP_REQUIRE(!L.flow || (Hin > 1 && Win > 1), "pp_regression_loss: bad flow size %dx%d", Hin, Win);
         PP_REQUIRE(!L.mask || L.flow, "pp_regression_loss: mask without flow");
         PrepArgs& a = pa[c];
-        a.coord_q = L.coord_q; a.coord_k = L.coord_k; a.flow = L.flow; a.mask = L.mask;
+        PP_REQUIRE(!L.pre || (!L.flow && !L.mask), "pp_regression_loss: warped centres and a dense flow are exclusive");
+        a.coord_q = L.coord_q; a.coord_k = L.coord_k; a.flow = L.flow; a.mask = L.mask; a.pre = L.pre;
         a.G = G; a.P = P;
         a.wo = (float)(W_orig - 1); a.ho = (float)(H_orig - 1);
         a.dG = make_div((float)G, div_mode);
@@ -693,6 +687,30 @@ int pp_regression_loss_pair(const float* const* q, const float* const* k, int64_
         c[i] = LossCall{q[i], k[i], coord_q[i], coord_k[i], flow[i], mask[i], loss[i], pos_num[i], pos_mean[i], dq[i],
                         nullptr, nullptr, workspace[i]};
     return regression_loss_impl(c, 2, B, C, G, Hin, Win, H_orig, W_orig, pos_ratio, div_mode, stream);
+}
+
+int pp_regression_loss_warped(const float* q, const float* k, int64_t B, int C, int G, const float* coord_q, const float* coord_k,
+                              const float* warped, int H_orig, int W_orig, double pos_ratio, int div_mode, float* loss,
+                              float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask, float* centres, void* workspace,
+                              void* stream) {
+    PP_REQUIRE(warped, "pp_regression_loss_warped: null warped centres");
+    LossCall c{q, k, coord_q, coord_k, nullptr, nullptr, loss, pos_num, pos_mean, dq, pos_mask, centres, workspace, warped};
+    return regression_loss_impl(&c, 1, B, C, G, 0, 0, H_orig, W_orig, pos_ratio, div_mode, stream);
+}
+
+int pp_regression_loss_pair_warped(const float* const* q, const float* const* k, int64_t B, int C, int G,
+                                   const float* const* coord_q, const float* const* coord_k, const float* const* warped,
+                                   int H_orig, int W_orig, double pos_ratio, int div_mode, float* const* loss,
+                                   float* const* pos_num, float* const* pos_mean, float* const* dq, void* const* workspace,
+                                   void* stream) {
+    PP_REQUIRE(q && k && coord_q && coord_k && warped && loss && pos_num && pos_mean && dq && workspace,
+               "pp_regression_loss_pair_warped: null pointer table");
+    PP_REQUIRE(warped[0] && warped[1], "pp_regression_loss_pair_warped: null warped centres");
+    LossCall c[2];
+    for (int i = 0; i < 2; i++)
+        c[i] = LossCall{q[i], k[i], coord_q[i], coord_k[i], nullptr, nullptr, loss[i], pos_num[i], pos_mean[i], dq[i],
+                        nullptr, nullptr, workspace[i], warped[i]};
+    return regression_loss_impl(c, 2, B, C, G, 0, 0, H_orig, W_orig, pos_ratio, div_mode, stream);
 }
 
 }  // extern "C"

@@ -41,6 +41,11 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pp_regression_loss_pair": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _d, _i,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pp_sparse_corr": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pp_regression_loss_warped": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _i, _i, _d, _i,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pp_regression_loss_pair_warped": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _i, _i, _d, _i,
+                                            _vp, _vp, _vp, _vp, _vp, _vp]),
     "pp_ppm_saved_bytes": (_l, [_l, _i, _i]),
     "pp_ppm_fwd": (_i, [_vp, _vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _vp]),
     "pp_ppm_bwd_workspace": (_l, [_l, _i, _i]),

@@ -26,10 +26,13 @@ from . import ops
 
 class HostPixelStep:
     def __init__(self, device, batch, channels=256, grid=7, size=(720, 1280), gamma=2.0, clamp=0.0, pos_ratio=0.7,
-                 alpha1=0.01, alpha2=0.5, flow_up=True, flow_chunks=4, use_graph=True):
+                 alpha1=0.01, alpha2=0.5, flow_up=True, flow_chunks=4, use_graph=True, sparse=False):
         self.dev = torch.device(device)
         self.size, self.gamma, self.clamp, self.pos_ratio = size, gamma, clamp, pos_ratio
         self.alpha1, self.alpha2, self.flow_up = alpha1, alpha2, flow_up
+        # sparse=True: the flow stage is evaluated only at the loss's grid centres (ops.sparse_corr), the dense
+        # composites / masks are never built; loss, counts and gradients are bit-identical to sparse=False
+        self.sparse = sparse
         self.side = torch.cuda.Stream(device=self.dev)
         self.aux = torch.cuda.Stream(device=self.dev, priority=-1)  # few latency-bound blocks: first free SM slots
         self.ready = torch.cuda.Event()
@@ -38,7 +41,7 @@ class HostPixelStep:
         self.calls = 0
         self.key = None
         self.param_grads = None
-        self.flow_chunks = max(1, min(flow_chunks, batch))
+        self.flow_chunks = 1 if sparse else max(1, min(flow_chunks, batch))
         self.chunk_ready = [torch.cuda.Event() for _ in range(self.flow_chunks)]
         self.out = {"loss": torch.empty((), dtype=torch.float32).pin_memory(),
                     "pos_num": torch.empty((2, batch), dtype=torch.float32).pin_memory(),
@@ -95,7 +98,15 @@ class HostPixelStep:
             t = {k: host[k].to(dev, non_blocking=True) for k in ("feat1", "feat2", "k1", "k2", "c1", "c2")}
             self.ready.record(self.side)
         ff = fb = mf = mb = None
-        if use_flow:
+        if use_flow and self.sparse:
+            (_, lf, lb, ev), = chunks
+            main.wait_event(ev)
+            if not capturing:
+                lf.record_stream(main)
+                lb.record_stream(main)
+            pair = ops.LazyFlowPair(lf, lb, flow_up=self.flow_up, alpha_1=self.alpha1, alpha_2=self.alpha2)
+            (ff, fb), (mf, mb) = pair.flow, pair.mask
+        elif use_flow:
             lo_h, lo_w = host["lo_f"].shape[-2:]
             H, W = (8 * lo_h, 8 * lo_w) if self.flow_up else (lo_h, lo_w)
             ff = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)

@@ -175,6 +175,103 @@ def calc_mask_ratio(mask):
     return out
 
 
+# --------------------------------------------------------------------- sparse correspondence --
+
+def sparse_corr(lo_fwd, lo_bwd, coord_fwd, coord_bwd, grid, size, flow_up=True, alpha_1=0.01, alpha_2=0.5):
+    """Flow stage + add_optical_flow evaluated only at the G*G grid centres of each sample
+    (pp_sparse_corr): bit-identical to flow_stage() followed by add_optical_flow(), without the
+    dense [B,2,H,W] composites and [B,H,W] masks.
+
+    lo_fwd/lo_bwd [B,n,2,h,w]; coord_fwd / coord_bwd [B,10] (either may be None): crop descriptors
+    of the view warped by the forward / backward composite; size = (H_orig, W_orig).
+    Returns (warped_fwd, warped_bwd), each [3,B,P] = (x, y, mask bit as 0/1) or None."""
+    f = _f32(lo_fwd, "lo_fwd")
+    b = _f32(lo_bwd, "lo_bwd")
+    assert f.ndim == 5 and f.shape == b.shape and f.shape[2] == 2, "sparse_corr expects [B,n,2,h,w]"
+    B, n, _, h, w = f.shape
+    H_orig, W_orig = _size_hw(size)
+    use_mask = alpha_1 is not None and alpha_2 is not None
+    P = grid * grid
+    cf = _f32(coord_fwd, "coord_fwd") if coord_fwd is not None else None
+    cb = _f32(coord_bwd, "coord_bwd") if coord_bwd is not None else None
+    for c in (cf, cb):
+        assert c is None or c.shape == (B, 10)
+    wf = torch.empty((3, B, P), device=f.device, dtype=torch.float32) if cf is not None else None
+    wb = torch.empty((3, B, P), device=f.device, dtype=torch.float32) if cb is not None else None
+    with torch.cuda.device(f.device):
+        _cabi.check(_cabi.lib().pp_sparse_corr(_ptr(f), _ptr(b), B, n, h, w, int(flow_up), int(use_mask), float(alpha_1 or 0.0),
+                                               float(alpha_2 or 0.0), _ptr(cf), _ptr(cb), grid, H_orig, W_orig, _div_mode,
+                                               _ptr(wf), _ptr(wb), _stream()), "pp_sparse_corr")
+    return wf, wb
+
+
+class LazyFlowPair:
+    """The flow stage of apply_optical_flow, deferred.  Holds the loader's low-res links; the loss takes
+    the sparse correspondence path (sparse_corr) from them, and anything that needs the dense tensors
+    (`.dense()`, mask-ratio logging) materialises them once through flow_stage() — same bits either way."""
+
+    def __init__(self, lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5):
+        self.lo_fwd, self.lo_bwd = _f32(lo_fwd, "lo_fwd"), _f32(lo_bwd, "lo_bwd")
+        self.flow_up, self.alpha_1, self.alpha_2 = flow_up, alpha_1, alpha_2
+        self._dense = None
+        B, n, _, h, w = self.lo_fwd.shape
+        self.flow_shape = (B, 2, 8 * h, 8 * w) if flow_up else (B, 2, h, w)
+        self.use_mask = alpha_1 is not None and alpha_2 is not None
+        self.flow = (LazyFlow(self, 0), LazyFlow(self, 1))
+        self.mask = (LazyMask(self, 0), LazyMask(self, 1)) if self.use_mask else (None, None)
+
+    def dense(self):
+        if self._dense is None:
+            self._dense = flow_stage(self.lo_fwd, self.lo_bwd, flow_up=self.flow_up, alpha_1=self.alpha_1, alpha_2=self.alpha_2)
+        return self._dense
+
+
+class LazyFlow:
+    """Stands in for one composite flow tensor [B,2,H,W] of apply_optical_flow's return value."""
+
+    def __init__(self, pair, direction):
+        self.pair, self.direction = pair, direction
+
+    @property
+    def shape(self):
+        return torch.Size(self.pair.flow_shape)
+
+    def dense(self):
+        return self.pair.dense()[self.direction]
+
+    def clone(self):
+        return self
+
+
+class LazyMask:
+    """Stands in for one FB mask [B,H,W] of apply_optical_flow's return value."""
+
+    def __init__(self, pair, direction):
+        self.pair, self.direction = pair, direction
+
+    @property
+    def shape(self):
+        B, _, H, W = self.pair.flow_shape
+        return torch.Size((B, H, W))
+
+    def dense(self):
+        return self.pair.dense()[2 + self.direction]
+
+    def clone(self):
+        return self
+
+
+def _lazy_warped(flow, mask, coord_q, grid, size):
+    """warped centres [3,B,P] of one loss direction from a LazyFlow (and its LazyMask or None)."""
+    pr = flow.pair
+    if mask is not None and not (isinstance(mask, LazyMask) and mask.pair is pr and mask.direction == flow.direction):
+        raise ValueError("a LazyFlow must come with the LazyMask of the same apply_optical_flow call (or None)")
+    a1, a2 = (pr.alpha_1, pr.alpha_2) if mask is not None else (None, None)
+    cf, cb = (coord_q, None) if flow.direction == 0 else (None, coord_q)
+    wf, wb = sparse_corr(pr.lo_fwd, pr.lo_bwd, cf, cb, grid, size, flow_up=pr.flow_up, alpha_1=a1, alpha_2=a2)
+    return wf if flow.direction == 0 else wb
+
+
 # ------------------------------------------------------------------------------------ loss --
 
 def _size_hw(size):
@@ -206,7 +303,7 @@ def add_optical_flow(flow, x_grid, y_grid, size, mask=None):
 
 class _RegressionLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, coord_q, coord_k, flow, mask, size, pos_ratio, debug):
+    def forward(ctx, q, k, coord_q, coord_k, flow, mask, size, pos_ratio, debug, warped=None):
         q = _f32(q, "q")
         k = _f32(k, "k")
         cq = _f32(coord_q, "coord_q")
@@ -231,10 +328,18 @@ class _RegressionLoss(torch.autograd.Function):
         pos_mask = torch.empty((B, P, P), device=dev, dtype=torch.uint8) if debug else None
         centres = torch.empty((4, B, P), device=dev, dtype=torch.float32) if debug else None
         with torch.cuda.device(dev):
-            _cabi.check(L.pp_regression_loss(_ptr(q), _ptr(k), B, C, G, _ptr(cq), _ptr(ck), _ptr(flow), Hin, Win, _ptr(m),
-                                             H_orig, W_orig, float(pos_ratio), _div_mode, _ptr(loss), _ptr(pos_num),
-                                             _ptr(pos_mean), _ptr(dq), _ptr(pos_mask), _ptr(centres), _ptr(ws), _stream()),
-                        "pp_regression_loss")
+            if warped is not None:
+                wp = _req(warped, "warped")
+                assert flow is None and mask is None and wp.shape == (3, B, P)
+                _cabi.check(L.pp_regression_loss_warped(_ptr(q), _ptr(k), B, C, G, _ptr(cq), _ptr(ck), _ptr(wp), H_orig, W_orig,
+                                                        float(pos_ratio), _div_mode, _ptr(loss), _ptr(pos_num), _ptr(pos_mean),
+                                                        _ptr(dq), _ptr(pos_mask), _ptr(centres), _ptr(ws), _stream()),
+                            "pp_regression_loss_warped")
+            else:
+                _cabi.check(L.pp_regression_loss(_ptr(q), _ptr(k), B, C, G, _ptr(cq), _ptr(ck), _ptr(flow), Hin, Win, _ptr(m),
+                                                 H_orig, W_orig, float(pos_ratio), _div_mode, _ptr(loss), _ptr(pos_num),
+                                                 _ptr(pos_mean), _ptr(dq), _ptr(pos_mask), _ptr(centres), _ptr(ws), _stream()),
+                            "pp_regression_loss")
         ctx.save_for_backward(dq)
         ctx.mark_non_differentiable(pos_num, pos_mean)
         if debug:
@@ -246,13 +351,24 @@ class _RegressionLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, *unused):
         (dq,) = ctx.saved_tensors
-        return (dq * g_loss,) + (None,) * 8
+        return (dq * g_loss,) + (None,) * 9
 
 
-def regression_loss(q, k, coord_q, coord_k, pos_ratio=0.5, flow=None, size=None, mask=None, debug=False):
+def regression_loss(q, k, coord_q, coord_k, pos_ratio=0.5, flow=None, size=None, mask=None, debug=False, warped=None):
     """contrast/models/PixPro.py:92-247 with the nested-list arguments already unpacked.
 
+    flow may be a dense composite [B,2,H,W] (+ dense mask), or a LazyFlow (+ its LazyMask): the
+    sparse correspondence path; or pass `warped` [3,B,P] from sparse_corr() directly (size required).
     Returns (loss, pos_num, pos_mean) — plus (pos_mask [B,P,P] bool, centres [4,B,P]) if debug."""
+    if isinstance(flow, LazyFlow):
+        if size is None:
+            size = tuple(flow.shape[-2:])
+        size = _size_hw(size)
+        warped = _lazy_warped(flow, mask, coord_q, q.shape[-1], size)
+        flow = mask = None
+    if warped is not None:
+        assert flow is None and mask is None and size is not None, "warped centres replace flow/mask; size is required"
+        return _RegressionLoss.apply(q, k.detach(), coord_q, coord_k, None, None, _size_hw(size), pos_ratio, debug, warped)
     if size is None:
         if flow is not None:
             size = tuple(flow.shape[-2:])                          # PixPro.py:121
@@ -266,7 +382,8 @@ class _RegressionLossPair(torch.autograd.Function):
     """Both directions of the pixel loss (PixPro.py:429-430) in one launch."""
 
     @staticmethod
-    def forward(ctx, q1, q2, k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2, size, pos_ratio):
+    def forward(ctx, q1, q2, k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2, size, pos_ratio, warped1=None,
+                warped2=None):
         import ctypes
         qs = [_f32(q1, "q1"), _f32(q2, "q2")]
         ks = [_f32(k1, "k1"), _f32(k2, "k2")]
@@ -297,9 +414,18 @@ class _RegressionLossPair(torch.autograd.Function):
                 table([pos_num[0], pos_num[1]]), table([pos_mean[0], pos_mean[1]]), table(dqs), table(ws)]
         ptrs = [ctypes.cast(t, ctypes.c_void_p) for t in keep]
         with torch.cuda.device(dev):
-            _cabi.check(L.pp_regression_loss_pair(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3], ptrs[4], Hin, Win, ptrs[5],
-                                                  H_orig, W_orig, float(pos_ratio), _div_mode, ptrs[6], ptrs[7], ptrs[8],
-                                                  ptrs[9], ptrs[10], _stream()), "pp_regression_loss_pair")
+            if warped1 is not None:
+                wps = [_req(warped1, "warped1"), _req(warped2, "warped2")]
+                assert all(f is None for f in flows + masks) and all(t.shape == (3, B, G * G) for t in wps)
+                wt = table(wps)
+                _cabi.check(L.pp_regression_loss_pair_warped(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3],
+                                                             ctypes.cast(wt, ctypes.c_void_p), H_orig, W_orig, float(pos_ratio),
+                                                             _div_mode, ptrs[6], ptrs[7], ptrs[8], ptrs[9], ptrs[10], _stream()),
+                            "pp_regression_loss_pair_warped")
+            else:
+                _cabi.check(L.pp_regression_loss_pair(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3], ptrs[4], Hin, Win, ptrs[5],
+                                                      H_orig, W_orig, float(pos_ratio), _div_mode, ptrs[6], ptrs[7], ptrs[8],
+                                                      ptrs[9], ptrs[10], _stream()), "pp_regression_loss_pair")
         ctx.save_for_backward(dqs[0], dqs[1])
         ctx.mark_non_differentiable(pos_num, pos_mean)
         return loss, pos_num, pos_mean
@@ -307,14 +433,38 @@ class _RegressionLossPair(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, *unused):
         dq1, dq2 = ctx.saved_tensors
-        return (dq1 * g_loss[0], dq2 * g_loss[1]) + (None,) * 12
+        return (dq1 * g_loss[0], dq2 * g_loss[1]) + (None,) * 14
 
 
 def regression_loss_pair(q1, k1, coord_q1, coord_k1, q2, k2, coord_q2, coord_k2, pos_ratio=0.5, flow1=None, flow2=None,
-                         size=None, mask1=None, mask2=None):
+                         size=None, mask1=None, mask2=None, warped1=None, warped2=None):
     """Two regression_loss calls (the two directions of PixPro.forward) fused into one launch.
 
+    flow1/flow2: dense composites (+ dense masks), or the two LazyFlows of one LazyFlowPair (sparse
+    correspondence: one pp_sparse_corr launch serves both directions); or pass warped1/warped2 directly.
     Returns (loss [2], pos_num [2,B], pos_mean [2,B]); loss[i] equals regression_loss(q_i, k_i, ...)."""
+    if isinstance(flow1, LazyFlow) or isinstance(flow2, LazyFlow):
+        if not (isinstance(flow1, LazyFlow) and isinstance(flow2, LazyFlow) and flow1.pair is flow2.pair
+                and flow1.direction != flow2.direction):
+            raise ValueError("regression_loss_pair: lazy flows must be the two directions of one LazyFlowPair")
+        pr = flow1.pair
+        for f, m in ((flow1, mask1), (flow2, mask2)):
+            if m is not None and not (isinstance(m, LazyMask) and m.pair is pr and m.direction == f.direction):
+                raise ValueError("a LazyFlow must come with the LazyMask of the same apply_optical_flow call (or None)")
+        if (mask1 is None) != (mask2 is None):
+            raise ValueError("regression_loss_pair: lazy masks must be given for both directions or neither")
+        if size is None:
+            size = tuple(flow1.shape[-2:])
+        size = _size_hw(size)
+        a1, a2 = (pr.alpha_1, pr.alpha_2) if mask1 is not None else (None, None)
+        cf, cb = (coord_q1, coord_q2) if flow1.direction == 0 else (coord_q2, coord_q1)
+        wf, wb = sparse_corr(pr.lo_fwd, pr.lo_bwd, cf, cb, q1.shape[-1], size, flow_up=pr.flow_up, alpha_1=a1, alpha_2=a2)
+        warped1, warped2 = (wf, wb) if flow1.direction == 0 else (wb, wf)
+        flow1 = flow2 = mask1 = mask2 = None
+    if warped1 is not None or warped2 is not None:
+        assert warped1 is not None and warped2 is not None and size is not None and flow1 is None and flow2 is None
+        return _RegressionLossPair.apply(q1, q2, k1.detach(), k2.detach(), coord_q1, coord_k1, coord_q2, coord_k2, None, None,
+                                         None, None, _size_hw(size), pos_ratio, warped1, warped2)
     if size is None:
         f = flow1 if flow1 is not None else flow2
         if f is not None:
