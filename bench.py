@@ -64,14 +64,20 @@ def workload_name(a):
             f"n_frames={a.n_frames}, batch {a.batch}/GPU, {a.grid}x{a.grid} grid, {C_FEAT}-d (BASELINE.json configs[1])")
 
 
-def algorithmic_bytes(kernel, B, n):
-    """SURVEY.md §8(d) per-sample figures (both directions) x samples per launch."""
+def algorithmic_bytes(kernel, B, n, G=7):
+    """Algorithmic bytes of one STEP's launches of `kernel` (SURVEY.md §8(d) per-sample figures, both
+    directions / both views, x the per-GPU batch); the caller divides by the launches per step."""
     lo = n * 2 * 2 * H_LO * W_LO * 4          # n links, 2 directions, 2 channels
     comp = 2 * 2 * H_FULL * W_FULL * 4        # 2 composite flows
     masks = 2 * H_FULL * W_FULL               # 2 byte masks
+    cp4 = C_FEAT * G * G * 4                  # one [C,P] fp32 map
     per_sample = {
-        "chain_up": lo + comp,                # F1: read low-res links, write composites
+        "chain_up": (lo + comp) if n == 1 else (lo + n * comp),  # F1 (n == 1); n > 1: the up-sampling pass into the scratch
+        "chain_dense": (n + 1) * comp,        # F1': read n dense links, write the composites
         "fb": comp + masks,                   # F2: read composites, write masks
+        "loss_small": 6 * cp4,                # F3: read q, k, write dq, both directions
+        "ppm_fwd_small": 2 * 3 * cp4,         # F4 forward, both views: read feat, val, write out
+        "ppm_bwd_small": 2 * 6 * cp4,         # F4 backward: read feat, val, out, g, write d_feat, d_val
     }
     return per_sample.get(kernel, 0) * B
 
@@ -359,7 +365,7 @@ def run_b200(a):
     if rep:
         top = max(rep, key=lambda k: rep[k][1])
         n_l, ms = rep[top]
-        alg = algorithmic_bytes(top, a.batch, a.n_frames - 1)
+        alg = algorithmic_bytes(top, a.batch, a.n_frames - 1, a.grid) / (n_l / prof_steps)  # per launch
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

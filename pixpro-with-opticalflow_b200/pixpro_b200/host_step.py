@@ -86,21 +86,32 @@ class HostPixelStep:
         capturing = torch.cuda.is_current_stream_capturing()  # graph-private memory needs no record_stream
         self.side.wait_stream(main)
         chunks = []
+        feat_keys = ("feat1", "feat2", "k1", "k2", "c1", "c2")
         with torch.cuda.stream(self.side):
-            if use_flow:  # first in the copy queue, chunk by chunk: the flow kernels depend on nothing else
-                B = host["lo_f"].shape[0]
-                step = (B + self.flow_chunks - 1) // self.flow_chunks
-                for i, b0 in enumerate(range(0, B, step)):
-                    lf = host["lo_f"][b0:b0 + step].to(dev, non_blocking=True)
-                    lb = host["lo_b"][b0:b0 + step].to(dev, non_blocking=True)
-                    self.chunk_ready[i].record(self.side)
-                    chunks.append((b0, lf, lb, self.chunk_ready[i]))
-            t = {k: host[k].to(dev, non_blocking=True) for k in ("feat1", "feat2", "k1", "k2", "c1", "c2")}
-            self.ready.record(self.side)
+            if use_flow and self.sparse:
+                # sparse correspondence: the flow work is ~10 us, so the copy queue is ordered for the PPM instead —
+                # features first (the PPM forward runs underneath the link copies), links last
+                t = {k: host[k].to(dev, non_blocking=True) for k in feat_keys}
+                self.ready.record(self.side)
+                lf = host["lo_f"].to(dev, non_blocking=True)
+                lb = host["lo_b"].to(dev, non_blocking=True)
+                self.chunk_ready[0].record(self.side)
+                chunks.append((0, lf, lb, self.chunk_ready[0]))
+            else:
+                if use_flow:  # first in the copy queue, chunk by chunk: the flow kernels depend on nothing else
+                    B = host["lo_f"].shape[0]
+                    step = (B + self.flow_chunks - 1) // self.flow_chunks
+                    for i, b0 in enumerate(range(0, B, step)):
+                        lf = host["lo_f"][b0:b0 + step].to(dev, non_blocking=True)
+                        lb = host["lo_b"][b0:b0 + step].to(dev, non_blocking=True)
+                        self.chunk_ready[i].record(self.side)
+                        chunks.append((b0, lf, lb, self.chunk_ready[i]))
+                t = {k: host[k].to(dev, non_blocking=True) for k in feat_keys}
+                self.ready.record(self.side)
         ff = fb = mf = mb = None
         if use_flow and self.sparse:
             (_, lf, lb, ev), = chunks
-            main.wait_event(ev)
+            main.wait_event(ev)  # main has nothing else to do until the loss; the PPM forward is on `aux`
             if not capturing:
                 lf.record_stream(main)
                 lb.record_stream(main)
