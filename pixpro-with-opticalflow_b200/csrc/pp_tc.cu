@@ -28,6 +28,11 @@ struct StoreC {
     int M, N;
     __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
         float* q = c + (b * M + m) * (int64_t)N + n;
+        if (n + 15 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < 16; i++)
             if (n + i < N) q[i] = v[i];
@@ -42,15 +47,6 @@ using namespace pp;
 extern "C" int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* stream) {
     PP_REQUIRE(A && B && C, "pp_tc_gemm_nt: null pointer");
     PP_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "pp_tc_gemm_nt: bad shape");
-    cudaStream_t st = (cudaStream_t)stream;
-    auto kern = tc::tc_gemm_kernel<tc::LoadRowK, tc::LoadRowK, tc::StoreC>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TC_SMEM_BYTES);
-        attr = true;
-    }
-    dim3 grid((N + tc::TN - 1) / tc::TN, (M + tc::TM - 1) / tc::TM, (unsigned)batch);
-    PP_LAUNCH("tc_gemm_nt", st,
-              kern<<<grid, tc::TC_THREADS, tc::TC_SMEM_BYTES, st>>>(M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N}));
-    return check_launch("tc_gemm_kernel");
+    return launch_tc("tc_gemm_nt", batch, M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N},
+                     (cudaStream_t)stream);
 }
