@@ -72,7 +72,7 @@ def algorithmic_bytes(kernel, B, n, G=7):
     masks = 2 * H_FULL * W_FULL               # 2 byte masks
     cp4 = C_FEAT * G * G * 4                  # one [C,P] fp32 map
     per_sample = {
-        "chain_up": (lo + comp) if n == 1 else (lo + n * comp),  # F1 (n == 1); n > 1: the up-sampling pass into the scratch
+        "chain_up": lo + comp,                # F1: read low-res links, write composites
         "chain_dense": (n + 1) * comp,        # F1': read n dense links, write the composites
         "fb": comp + masks,                   # F2: read composites, write masks
         "loss_small": 6 * cp4,                # F3: read q, k, write dq, both directions
