@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_bits_equal, rel_err
+from conftest import assert_bits_equal, load_golden, rel_err, unpack_mask
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -66,6 +66,35 @@ def test_sparse_corr_vs_oracle(ops, orc, synth, B, n, h, w, flow_up, use_mask, G
         assert_bits_equal(npy(wp[2]), want, f"mask bit, direction {d}")
         if use_mask and mag < 5 and h == 90:
             assert 0 < want.mean() < 1  # the case exercises both outcomes of the FB test
+
+
+@pytest.mark.parametrize("tag", ["flow_g7_n1_mask", "flow_g7_n5_mask", "flow_g7_big", "flow_g7_diffsize", "flow_g14_n2_nomask"])
+def test_sparse_path_against_reference_golden(ops, tag):
+    """The committed fixtures hold what the REFERENCE itself produced (oracle/pin_against_reference.py): warped
+    centres and mask bits from its add_optical_flow, loss / pos_num / dq from its regression_loss, for flows its
+    apply_optical_flow built from these low-res links.  The sparse path must reproduce them from the links alone."""
+    g = load_golden("loss_" + tag)
+    size = tuple(int(v) for v in g["size"])
+    use_mask = bool(g["use_mask"])
+    a1, a2 = (0.01, 0.5) if use_mask else (None, None)
+    q = cu(g["q"]).requires_grad_(True)
+    B, C, G, _ = q.shape
+    P = G * G
+    wf, _ = ops.sparse_corr(cu(g["lo_fwd"]), cu(g["lo_bwd"]), cu(g["coord_q"]), None, G, size, alpha_1=a1, alpha_2=a2)
+    assert_bits_equal(npy(wf[0]), g["cqx"], "warped centre x")
+    assert_bits_equal(npy(wf[1]), g["cqy"], "warped centre y")
+    if "mask_grid" in g:
+        assert_bits_equal(npy(wf[2]) != 0, g["mask_grid"].astype(bool), "mask_grid")
+    pair = ops.LazyFlowPair(cu(g["lo_fwd"]), cu(g["lo_bwd"]), alpha_1=a1, alpha_2=a2)
+    loss, pos_num, pos_mean, pos_mask, _ = ops.regression_loss(q, cu(g["k"]), cu(g["coord_q"]), cu(g["coord_k"]),
+                                                               float(g["pos_ratio"]), flow=pair.flow[0], size=size,
+                                                               mask=pair.mask[0], debug=True)
+    loss.backward()
+    assert pair._dense is None
+    assert_bits_equal(npy(pos_mask), unpack_mask(g["pos_mask"], (B, P, P)), "pos_mask (correspondence indices)")
+    assert_bits_equal(npy(pos_num), g["pos_num"], "pos_num")
+    assert abs(loss.item() - float(g["loss"])) <= TOL * max(abs(float(g["loss"])), 1e-3)
+    assert rel_err(npy(q.grad), g["dq"]) < TOL
 
 
 def test_sparse_corr_single_direction_and_validation(ops, synth):
