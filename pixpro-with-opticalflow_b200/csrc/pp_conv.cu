@@ -126,22 +126,25 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
     for (int k = 0; k < splits; k++) s += __ldg(part + (int64_t)k * total + e);
     dw[e] = s;
 }
-__global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __restrict__ dy, int B, int C, int P,
-                                                              float* __restrict__ db) {
-    __shared__ float red[256];
-    const int o = blockIdx.x;
+// db[o] = Σ_b Σ_p dy[b][o][p] in two deterministic passes: one warp per (b, o) row (coalesced, B*C warps in
+// flight), then one thread per channel sums the B row sums in order.  (One block per channel looping over B*P
+// elements took 0.36 ms at B=64, 28x28 and sat on the backward's critical path.)
+__global__ void __launch_bounds__(256) conv_bias_rows_kernel(const float* __restrict__ dy, int rows, int P,
+                                                              float* __restrict__ part) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* q = dy + (int64_t)row * P;
     float s = 0.0f;
-    for (int e = threadIdx.x; e < B * P; e += blockDim.x) {
-        int b = e / P, p = e - b * P;
-        s += __ldg(dy + ((int64_t)b * C + o) * P + p);
-    }
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) db[o] = red[0];
+    for (int p = lane; p < P; p += 32) s += __ldg(q + p);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) part[row] = s;
+}
+__global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __restrict__ part, int B, int C, float* __restrict__ db) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= C) return;
+    float s = 0.0f;
+    for (int b = 0; b < B; b++) s += __ldg(part + (int64_t)b * C + o);
+    db[o] = s;
 }
 
 constexpr int kWgradSplitK = 128;  // joint indices per split
@@ -163,7 +166,7 @@ int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B,
 
 int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P) {
     const int64_t splits = (B * P + kWgradSplitK - 1) / kWgradSplitK;
-    return splits * Cin * Cout * (int64_t)sizeof(float);
+    return (splits * Cin * Cout + B * Cout) * (int64_t)sizeof(float);  // split-K partials of dW, then the row sums of db
 }
 
 int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
@@ -191,7 +194,11 @@ int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, i
         if (rc) return rc;
     }
     if (db) {
-        PP_LAUNCH("conv1x1 bias grad", st, conv_bias_grad_kernel<<<Cout, 256, 0, st>>>(dy, (int)B, Cout, P, db));
+        // its own workspace region: the three gradients may run concurrently on different streams
+        float* rows = (float*)workspace + (int64_t)((NP + kWgradSplitK - 1) / kWgradSplitK) * Cin * Cout;
+        const int nrows = (int)(B * Cout);
+        PP_LAUNCH("conv1x1 bias grad", st, conv_bias_rows_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(dy, nrows, P, rows));
+        PP_LAUNCH("conv1x1 bias grad reduce", st, conv_bias_grad_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(rows, (int)B, Cout, db));
         rc = check_launch("conv_bias_grad_kernel");
         if (rc) return rc;
     }
