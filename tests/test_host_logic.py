@@ -206,3 +206,40 @@ def test_reference_tree_resolves_behind_the_mirror_package():
         "print('ok')\n") % (pkg, ref, ref, ref, pkg, pkg)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-1500:]
+
+
+def test_sparse_mode_has_no_cpu_fallback_and_keeps_the_list_structure():
+    """The lazy stand-ins of the sparse correspondence mode refuse CPU tensors like every other entry (no fallback),
+    and regression_loss_pair rejects lazy flows that do not belong together."""
+    import types
+    import torch
+    from pixpro_b200 import ops
+    from pixpro_b200._cabi import PixProB200Error
+    from contrast import util
+    lf = torch.zeros(2, 1, 2, 4, 4)
+    with pytest.raises(PixProB200Error):
+        ops.LazyFlowPair(lf, lf)
+    with pytest.raises(PixProB200Error):
+        ops.sparse_corr(lf, lf, torch.zeros(2, 10), None, 7, (32, 32))
+    args = types.SimpleNamespace(alpha1=0.01, alpha2=0.5, use_flow_frames=False, use_flow_file=True, flow_up=True,
+                                 flow_cat_norm=False, debug=False, flow_sparse=True)
+    data = [None] * 7
+    data[5] = [None, lf, lf]
+    data[6] = [torch.tensor([[32, 32]] * 2), torch.tensor([[2]] * 2)]
+    with pytest.raises((PixProB200Error, RuntimeError, AssertionError)):  # `.cuda()` of the mirror, as in the reference
+        util.apply_optical_flow(data, None, args)
+
+    class FakePair:  # structure checks run before any device work
+        flow_shape = (2, 2, 32, 32)
+        lo_fwd = lo_bwd = None
+        flow_up, alpha_1, alpha_2 = True, 0.01, 0.5
+    a, b = ops.LazyFlow(FakePair(), 0), ops.LazyFlow(FakePair(), 1)
+    assert tuple(a.shape) == (2, 2, 32, 32) and a.clone() is a
+    assert tuple(ops.LazyMask(FakePair(), 0).shape) == (2, 32, 32)
+    q = torch.zeros(2, 4, 7, 7)
+    c = torch.zeros(2, 10)
+    with pytest.raises(ValueError):  # two different pairs
+        ops.regression_loss_pair(q, q, c, c, q, q, c, c, 0.7, flow1=a, flow2=b, size=(32, 32))
+    with pytest.raises(ValueError):  # the same direction twice
+        p = FakePair()
+        ops.regression_loss_pair(q, q, c, c, q, q, c, c, 0.7, flow1=ops.LazyFlow(p, 0), flow2=ops.LazyFlow(p, 0), size=(32, 32))
