@@ -139,12 +139,22 @@ __global__ void __launch_bounds__(256) conv_bias_rows_kernel(const float* __rest
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) part[row] = s;
 }
+// block = 32 channels x 8 row groups: warp w sums rows b = w, w + 8, ... of channel 32 blockIdx.x + lane, then the eight
+// partial sums are added in warp order (deterministic)
 __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __restrict__ part, int B, int C, float* __restrict__ db) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= C) return;
+    __shared__ float red[8][33];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, o = blockIdx.x * 32 + lane;
     float s = 0.0f;
-    for (int b = 0; b < B; b++) s += __ldg(part + (int64_t)b * C + o);
-    db[o] = s;
+    if (o < C)
+        for (int b = w; b < B; b += 8) s += __ldg(part + (int64_t)b * C + o);
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && o < C) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += red[k][lane];
+        db[o] = t;
+    }
 }
 
 constexpr int kWgradSplitK = 128;  // joint indices per split
@@ -198,7 +208,7 @@ int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, i
         float* rows = (float*)workspace + (int64_t)((NP + kWgradSplitK - 1) / kWgradSplitK) * Cin * Cout;
         const int nrows = (int)(B * Cout);
         PP_LAUNCH("conv1x1 bias grad", st, conv_bias_rows_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(dy, nrows, P, rows));
-        PP_LAUNCH("conv1x1 bias grad reduce", st, conv_bias_grad_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(rows, (int)B, Cout, db));
+        PP_LAUNCH("conv1x1 bias grad reduce", st, conv_bias_grad_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(rows, (int)B, Cout, db));
         rc = check_launch("conv_bias_grad_kernel");
         if (rc) return rc;
     }

@@ -223,3 +223,24 @@ def test_host_pixel_step_sparse_matches_dense():
     assert torch.equal(outs[0]["pos_num"], outs[1]["pos_num"])
     assert torch.equal(outs[0]["loss"], outs[1]["loss"])
     assert torch.equal(outs[0]["d_feat"], outs[1]["d_feat"])
+
+
+def test_sparse_equals_dense_in_rcp_division_mode(ops, synth):
+    """PIXPRO_B200_DIV=rcp (tensor / scalar as torch's CUDA kernels round it): the sparse kernel follows the same mode."""
+    B, n, G, C = 6, 3, 7, 64
+    lf, lb = synth.flow_fields(B, n, seed=90)
+    lf, lb = lf.to(DEV), lb.to(DEV)
+    c1, c2 = synth.crop_coords(B, seed=91).to(DEV), synth.crop_coords(B, seed=92).to(DEV)
+    gen = torch.Generator().manual_seed(93)
+    q = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1).to(DEV)
+    k = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1).to(DEV)
+    ops.set_div_mode("rcp")
+    try:
+        ff, fb, mf, mb = ops.flow_stage(lf, lb)
+        ld, pnd, _ = ops.regression_loss_pair(q, k, c1, c2, q, k, c2, c1, 0.7, flow1=ff, flow2=fb, size=(720, 1280), mask1=mf, mask2=mb)
+        pair = ops.LazyFlowPair(lf, lb)
+        ls, pns, _ = ops.regression_loss_pair(q, k, c1, c2, q, k, c2, c1, 0.7, flow1=pair.flow[0], flow2=pair.flow[1],
+                                              size=(720, 1280), mask1=pair.mask[0], mask2=pair.mask[1])
+        assert torch.equal(pnd, pns) and torch.equal(ld, ls) and pns.sum().item() > 0
+    finally:
+        ops.set_div_mode("ieee")
