@@ -113,6 +113,8 @@ class PixPro(BaseModel):
         self.pixpro_transform_layer = args.pixpro_transform_layer
         self.pixpro_ins_loss_weight = args.pixpro_ins_loss_weight
         self.output_root = args.output_dir
+        self.graph_momentum_branch = bool(getattr(args, "graph_momentum_branch", False))  # see _momentum_branch_graphed
+        self._kgraph = None
 
         # online and momentum branches (PixPro.py:272-287)
         self.encoder = base_encoder(head_type='early_return')
@@ -168,6 +170,39 @@ class PixPro(BaseModel):
             for p_q, p_k in qk:
                 p_k.copy_(p_k * m + p_q * (1. - m))
 
+    def _momentum_branch(self, im_1, im_2):
+        proj_1_ng = F.normalize(self.projector_k(self.encoder_k(im_1)), dim=1)
+        proj_2_ng = F.normalize(self.projector_k(self.encoder_k(im_2)), dim=1)
+        return proj_1_ng, proj_2_ng
+
+    def _momentum_branch_graphed(self, im_1, im_2):
+        """Opt-in (`model.graph_momentum_branch = True`): the key branch — two gradient-free encoder + projector
+        passes, SyncBatchNorm collectives included — replayed from ONE CUDA graph.  Under DDP the multi-GPU step
+        is bound by the host's issue rate of ~5 000 small operations (profiles/r01_s3_pretrain_ddp.txt); this
+        removes the ~1 400 of the key branch.  Same kernels, same parameters (updated in place by the EMA
+        launch), same running-statistics updates; the first three calls run eagerly (lazy initialisation), the
+        fourth is captured.  Inputs are copied into the graph's fixed buffers; the outputs are the graph's
+        buffers and are valid until the next call."""
+        key = (tuple(im_1.shape), im_1.dtype, tuple(im_1.stride()), tuple(im_2.stride()), torch.is_autocast_enabled(),
+               torch.get_autocast_gpu_dtype())
+        st = self._kgraph
+        if st is None or st["key"] != key:
+            st = self._kgraph = {"key": key, "calls": 0, "graph": None}
+        if st["graph"] is None:
+            st["calls"] += 1
+            if st["calls"] <= 3:
+                return self._momentum_branch(im_1, im_2)
+            st["in"] = (im_1.clone(), im_2.clone())
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["out"] = self._momentum_branch(*st["in"])
+            st["graph"] = graph
+        st["in"][0].copy_(im_1)
+        st["in"][1].copy_(im_2)
+        st["graph"].replay()
+        return st["out"]
+
     def _value(self, feat):
         """value_transform(feat) (PixPro.py:343).  The published setting (transform_layer=1, a 1x1
         conv) runs on the tcgen05 3xTF32 kernel — same parameters, fp32-accurate; Identity and the
@@ -209,13 +244,16 @@ class PixPro(BaseModel):
         with torch.no_grad():
             if is_update_momentum:
                 self._momentum_update_key_encoder()
-            feat_1_ng = self.encoder_k(im_1)
-            proj_1_ng = F.normalize(self.projector_k(feat_1_ng), dim=1)
-            feat_2_ng = self.encoder_k(im_2)
-            proj_2_ng = F.normalize(self.projector_k(feat_2_ng), dim=1)
-            if ins:
-                proj_instance_1_ng = _ins(self.projector_instance_k(feat_1_ng))
-                proj_instance_2_ng = _ins(self.projector_instance_k(feat_2_ng))
+            if self.graph_momentum_branch and not ins and im_1.is_cuda and self.training:
+                proj_1_ng, proj_2_ng = self._momentum_branch_graphed(im_1, im_2)
+            else:
+                feat_1_ng = self.encoder_k(im_1)
+                proj_1_ng = F.normalize(self.projector_k(feat_1_ng), dim=1)
+                feat_2_ng = self.encoder_k(im_2)
+                proj_2_ng = F.normalize(self.projector_k(feat_2_ng), dim=1)
+                if ins:
+                    proj_instance_1_ng = _ins(self.projector_instance_k(feat_1_ng))
+                    proj_instance_2_ng = _ins(self.projector_instance_k(feat_2_ng))
 
         # pixel-level loss, both directions (PixPro.py:429-432), fused into one launch
         loss, pos_num_list = regression_loss_pair(pred_1, proj_2_ng, coord1, coord2, pred_2, proj_1_ng, coord2, coord1,

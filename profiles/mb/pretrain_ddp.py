@@ -36,6 +36,7 @@ ap.add_argument("--n-frames", type=int, default=2)
 ap.add_argument("--amp", default="bf16", choices=["bf16", "fp32"])
 ap.add_argument("--channels-last", action="store_true")
 ap.add_argument("--sparse", action="store_true")
+ap.add_argument("--graph-key-branch", action="store_true", help="momentum branch replayed from one CUDA graph")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=4)
 a = ap.parse_args()
@@ -52,6 +53,7 @@ margs = types.SimpleNamespace(pixpro_p=2.0, pixpro_momentum=0.99, pixpro_pos_rat
                               pixpro_transform_layer=1, pixpro_ins_loss_weight=0.0, output_dir="/tmp", num_instances=100000,
                               batch_size=B, epochs=100, start_epoch=1, feature_dim=256, head_type="early_return")
 model = PixPro(resnet.resnet50, margs).to(dev)
+model.graph_momentum_branch = a.graph_key_branch
 opt = LARS(torch.optim.SGD(add_weight_decay(model, 1e-5), lr=B * world / 256 * 1.0, momentum=0.9))
 ddp = DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False)  # main_pretrain.py:78
 g = torch.Generator(device="cpu").manual_seed(100 + rank)
@@ -103,8 +105,13 @@ if rank == 0:
     print(json.dumps({"metric": "PixPro+OF pretrain step (flow stage + ResNet-50 x2 branches fwd/bwd + DDP all-reduce + LARS), frames/sec",
                       "value": B * world * a.n_frames / ms * 1e3, "unit": "frames/s", "n_gpus": world, "ms_per_step": ms,
                       "samples_per_s": B * world / ms * 1e3, "per_gpu_batch": B, "n_frames": a.n_frames, "amp": a.amp,
-                      "channels_last": a.channels_last, "flow_stage": "sparse" if a.sparse else "dense", "scaling": "weak",
+                      "channels_last": a.channels_last, "flow_stage": "sparse" if a.sparse else "dense", "graph_key_branch": a.graph_key_branch, "scaling": "weak",
                       "grad_allreduce_mb": sum(p.numel() for p in model.parameters() if p.requires_grad) * 4 / 1e6,
                       "mean_loss": float(lv.item()) / world, "steps": a.steps, "warmup": a.warmup, "data": "synthetic"}))
+torch.cuda.synchronize()
 dist.barrier()
+if a.graph_key_branch:
+    # a CUDA graph that holds NCCL kernels must not outlive an orderly communicator teardown (it hangs): leave at once
+    sys.stdout.flush()
+    os._exit(0)
 dist.destroy_process_group()

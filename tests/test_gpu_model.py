@@ -291,3 +291,36 @@ def test_host_pixel_step_matches_device_path(use_graph):
         assert (dw - wg.grad).abs().max().item() <= 1e-5 * wg.grad.abs().max().item()
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_graphed_momentum_branch_matches_eager(group):
+    """Opt-in CUDA-graph replay of the key branch (contrast.models.PixPro._momentum_branch_graphed): same losses as the
+    eager branch step after step (EMA updates and BatchNorm running statistics included), outputs valid per call."""
+    from contrast import resnet
+    from contrast.models import PixPro
+    from pixpro_b200 import synth
+    B = 4
+    torch.manual_seed(0)
+    m1 = PixPro(resnet.resnet50, pixpro_args(batch_size=B)).to(DEV)
+    m2 = PixPro(resnet.resnet50, pixpro_args(batch_size=B)).to(DEV)
+    m2.load_state_dict(m1.state_dict())
+    m2.graph_momentum_branch = True
+    c1, c2 = synth.crop_coords(B, seed=1).to(DEV), synth.crop_coords(B, seed=2).to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for step in range(6):  # 3 eager warm-up calls, capture on the 4th, replays after
+            im1 = torch.randn(B, 3, 224, 224, generator=gen).to(DEV)
+            im2 = torch.randn(B, 3, 224, 224, generator=gen).to(DEV)
+            with torch.no_grad():
+                l1, p1 = m1(im1, im2, c1, c2)
+                l2, p2 = m2(im1, im2, c1, c2)
+            assert torch.equal(p1[0][0], p2[0][0]) and torch.equal(p1[1][0], p2[1][0]), step
+            assert abs(l1.item() - l2.item()) <= 1e-5 * max(abs(l1.item()), 1e-3), (step, l1.item(), l2.item())
+        assert m2._kgraph is not None and m2._kgraph["graph"] is not None
+        for (n_, b1), (_, b2) in zip(m1.encoder_k.named_buffers(), m2.encoder_k.named_buffers()):
+            assert torch.allclose(b1.float(), b2.float(), rtol=1e-5, atol=1e-6), n_
+    finally:
+        m2._kgraph = None
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
