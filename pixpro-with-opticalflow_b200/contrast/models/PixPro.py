@@ -183,8 +183,8 @@ class PixPro(BaseModel):
         launch), same running-statistics updates; the first three calls run eagerly (lazy initialisation), the
         fourth is captured.  Inputs are copied into the graph's fixed buffers; the outputs are the graph's
         buffers and are valid until the next call."""
-        key = (tuple(im_1.shape), im_1.dtype, tuple(im_1.stride()), tuple(im_2.stride()), torch.is_autocast_enabled(),
-               torch.get_autocast_gpu_dtype())
+        key = (tuple(im_1.shape), im_1.dtype, tuple(im_1.stride()), tuple(im_2.stride()), torch.is_autocast_enabled("cuda"),
+               torch.get_autocast_dtype("cuda"))
         st = self._kgraph
         if st is None or st["key"] != key:
             st = self._kgraph = {"key": key, "calls": 0, "graph": None}

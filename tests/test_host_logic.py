@@ -243,3 +243,23 @@ def test_sparse_mode_has_no_cpu_fallback_and_keeps_the_list_structure():
     with pytest.raises(ValueError):  # the same direction twice
         p = FakePair()
         ops.regression_loss_pair(q, q, c, c, q, q, c, c, 0.7, flow1=ops.LazyFlow(p, 0), flow2=ops.LazyFlow(p, 0), size=(32, 32))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) prints ONE JSON line with the
+    contract's keys; bounded to a 2-sample step here so that the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--batch", "2", "--cpu-sample", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
