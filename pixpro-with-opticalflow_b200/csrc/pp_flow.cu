@@ -954,8 +954,14 @@ int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int 
 }
 
 // Scratch for the chained (n > 1) flow_up path: the up-sampled links of `chunk` samples, both
-// directions.  Sized so that one chunk stays resident in the 126 MB L2.
-static const int64_t kChainScratchTarget = 80ll << 20;
+// directions.  Measured on a B200 (n=5, B=64, 720x1280; step time of bench.py --n-frames 6): 80 MB (one sample per
+// chunk, L2-resident) 3.54 ms, 160 MB 3.67, 320 MB 3.19, 640 MB 3.09, 1.3-5 GB 3.10 — chunks of 8 samples make every
+// launch large enough for the TMA-staged chain kernel (>= 1200 tiles) and cut the launch count from 267 to 43; keeping
+// the scratch inside the L2 matters less than that.  PIXPRO_B200_CHAINSCRATCH_MB overrides (A/B runs).
+static int64_t chain_scratch_target() {
+    static const int64_t t = [] { const char* e = getenv("PIXPRO_B200_CHAINSCRATCH_MB"); return (int64_t)(e ? atoi(e) : 640) << 20; }();
+    return t;
+}
 static int64_t chain_chunk_bytes(int n, int h, int w) { return (int64_t)2 * n * 2 * (8 * h) * (8 * w) * sizeof(float); }
 
 // One helper stream + fork/join events per device for pp_flow_stage (the C ABI is called by one host thread per
@@ -986,7 +992,7 @@ static FlowSideStream* flow_side_stream() {
 int64_t pp_flow_stage_workspace(int64_t B, int n, int h, int w, int flow_up) {
     if (!flow_up || n <= 1 || B <= 0) return 0;
     const int64_t per = chain_chunk_bytes(n, h, w);
-    int64_t chunk = kChainScratchTarget / per;
+    int64_t chunk = chain_scratch_target() / per;
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
     return chunk * per;
