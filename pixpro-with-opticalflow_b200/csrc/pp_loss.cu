@@ -407,22 +407,26 @@ struct TcStDq {  // dq[b][c][i..i+15] = M * (-2 / (B den_b))
     }
 };
 
-// partial[b] = Σ q∘M = (Σ q∘dq) * den_b / scale   (deterministic block reduction per sample)
+// partial[b][t] = slice t of Σ q∘M = (Σ q∘dq) * den_b / scale: kDotSplit blocks per sample (one block per sample left
+// 32-64 blocks on 148 SMs: 0.24 ms at 28x28), each a deterministic block reduction; loss_final adds the slices in order.
+constexpr int kDotSplit = 8;
 __global__ void __launch_bounds__(256) loss_dot_kernel(const float* __restrict__ q, const float* __restrict__ dq, LossWs ws,
                                                         int64_t CP, float scale) {
     __shared__ float red[256];
-    const int64_t b = blockIdx.x;
+    const int64_t b = blockIdx.y;
+    const int64_t per = (CP + kDotSplit - 1) / kDotSplit;
+    const int64_t e0 = blockIdx.x * per, e1 = (e0 + per < CP) ? e0 + per : CP;
     const float* qb = q + b * CP;
     const float* db = dq + b * CP;
     float s = 0.0f;
-    for (int64_t e = threadIdx.x; e < CP; e += blockDim.x) s = fmaf(__ldg(qb + e), __ldg(db + e), s);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) s = fmaf(__ldg(qb + e), __ldg(db + e), s);
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) ws.partial[b] = red[0] * (ws.den[b] / scale);
+    if (threadIdx.x == 0) ws.partial[b * kDotSplit + blockIdx.x] = red[0] * (ws.den[b] / scale);
 }
 
 // ---- a8 for small grids (P <= 64): ONE block per sample does stages 1 and 2 ------------------
@@ -630,7 +634,7 @@ static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int
         rc = check_launch("loss_small_kernel");
         if (rc) return rc;
     } else if (use_tensor_cores(P) && P > PMAX && calls[0].dq && (ncall == 1 || calls[1].dq)) {
-        ntile = 1;
+        ntile = kDotSplit;  // <= loss_ntile(P) for every P > PMAX, so the workspace's partial[] region is large enough
         for (int c = 0; c < ncall; c++) {
             uint8_t* posb = calls[c].pos_mask ? calls[c].pos_mask : pa[c].ws.posb;
             PP_LAUNCH("loss_centres", st, loss_centres_kernel<<<(unsigned)B, 256, 0, st>>>(pa[c]));
@@ -641,7 +645,7 @@ static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int
             rc = launch_tc("loss M=K*pos^T (tcgen05)", B, C, P, P, TcLdN{calls[c].k, C, P}, TcLdPos{posb, P},
                            TcStDq{calls[c].dq, pa[c].ws.den, scale, C, P}, st);
             if (rc) return rc;
-            PP_LAUNCH("loss_dot", st, loss_dot_kernel<<<(unsigned)B, 256, 0, st>>>(calls[c].q, calls[c].dq, pa[c].ws, (int64_t)C * P, scale));
+            PP_LAUNCH("loss_dot", st, loss_dot_kernel<<<dim3(kDotSplit, (unsigned)B), 256, 0, st>>>(calls[c].q, calls[c].dq, pa[c].ws, (int64_t)C * P, scale));
             rc = check_launch("loss_dot_kernel");
             if (rc) return rc;
         }
