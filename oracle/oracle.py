@@ -276,6 +276,26 @@ def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=
 
 # ------------------------------------------------------------------ optimizer side
 
+
+def sparse_corr(lo_fwd, lo_bwd, coord_fwd, coord_bwd, grid, size, flow_up=True, alpha_1=0.01, alpha_2=0.5, div_mode=0):
+    """Flow stage + add_optical_flow evaluated only at the grid centres (orc_sparse_corr): the restatement of the
+    sparse correspondence mode.  Returns (warped_fwd, warped_bwd), each [3,B,P] = (x, y, mask bit) or None."""
+    lo_fwd, fp = _f(lo_fwd)
+    lo_bwd, bp = _f(lo_bwd)
+    B, n, _, h, w = lo_fwd.shape
+    use_mask = alpha_1 is not None and alpha_2 is not None
+    P = grid * grid
+    cf = cb = cfp = cbp = wf = wb = wfp = wbp = None
+    if coord_fwd is not None:
+        cf, cfp = _f(coord_fwd)
+        wf, wfp = _out_f((3, B, P))
+    if coord_bwd is not None:
+        cb, cbp = _f(coord_bwd)
+        wb, wbp = _out_f((3, B, P))
+    lib().orc_sparse_corr(fp, bp, _L(B), _I(n), _I(h), _I(w), _I(int(flow_up)), _I(int(use_mask)), _D(alpha_1 or 0.0),
+                          _D(alpha_2 or 0.0), cfp, cbp, _I(grid), _I(int(size[0])), _I(int(size[1])), _I(div_mode), wfp, wbp)
+    return wf, wb
+
 def ema_update(k, q, m, one_minus_m=None):
     """contrast/models/PixPro.py:330-331, in place on a copy of k; returns the new k."""
     k, kp = _f(np.array(k, dtype=np.float32, copy=True))

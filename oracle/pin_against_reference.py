@@ -250,6 +250,13 @@ def main():
                                                (H, W), mask)
             rep.exact(f"a7 {tag} out_x", o["cqx"].reshape(B, G, G), ox.numpy())
             rep.exact(f"a7 {tag} out_y", o["cqy"].reshape(B, G, G), oy.numpy())
+            # the sparse restatement (flow stage evaluated at the grid centres only) against the reference's dense route
+            swf, _ = orc.sparse_corr(f.numpy(), b.numpy(), cq.numpy(), None, G, (H, W), alpha_1=0.01 if use_mask else None,
+                                     alpha_2=0.5 if use_mask else None)
+            rep.exact(f"sparse {tag} out_x", swf[0].reshape(B, G, G), ox.numpy())
+            rep.exact(f"sparse {tag} out_y", swf[1].reshape(B, G, G), oy.numpy())
+            if mg is not None:
+                rep.exact(f"sparse {tag} mask_grid", swf[2].reshape(mg.shape) != 0, mg.numpy())
             g.update(lo_fwd=f.numpy(), lo_bwd=b.numpy(), use_mask=np.bool_(use_mask), cqx=ox.numpy().reshape(B, P),
                      cqy=oy.numpy().reshape(B, P))
             if mg is not None:

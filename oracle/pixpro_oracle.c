@@ -703,6 +703,154 @@ ORC_API void orc_flow_stage(const float* lo_fwd, const float* lo_bwd, long B, in
     }
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* sparse correspondence — what regression_loss consumes of apply_optical_flow           */
+/* (contrast/util.py:175-248) through add_optical_flow (contrast/models/PixPro.py:46-89),*/
+/* restated WITHOUT the dense tensors: the composite flow (util.py:185-191,301-330) is   */
+/* evaluated at single integer pixels, the FB test (util.py:253-297) at single pixels.   */
+/* Every op of the dense stage is point-wise, so this must equal sampling the dense      */
+/* outputs bit for bit — tests/test_oracle_golden.py checks it against orc_flow_stage +  */
+/* orc_add_optical_flow and against the reference's own outputs in tests/golden.         */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* links; /* link i at links + i*stride_n: [2,h,w] (up) or [2,H,W] */
+    int n, up, h, w, H, W, div_mode;
+    long stride_n;
+    const axis_tap *ty, *tx; /* up-sampling taps per full-res row / column (up only) */
+} comp_field;
+
+/* value of link i at integer pixel (Y,X): 8 * bilinear x8 (flow/utils/utils.py:87-89) or the dense value */
+static inline void comp_link_value(const comp_field* f, int i, int Y, int X, float v[2]) {
+    const float* p = f->links + i * f->stride_n;
+    if (f->up) {
+        v[0] = 8.0f * up_eval(p, f->w, &f->ty[Y], &f->tx[X]);
+        v[1] = 8.0f * up_eval(p + (long)f->h * f->w, f->w, &f->ty[Y], &f->tx[X]);
+    } else {
+        v[0] = p[(long)Y * f->W + X];
+        v[1] = p[(long)f->H * f->W + (long)Y * f->W + X];
+    }
+}
+
+typedef void (*pixel_fn)(const comp_field*, int, int, int, float*);
+
+/* F.grid_sample(bilinear, zeros, align_corners=True) of a 2-channel field given by `value` at normalised (gx,gy);
+ * norm_taps: the sampled field is normalize_flow(field) (util.py:264-265,278) */
+static inline void comp_grid_sample(const comp_field* f, pixel_fn value, int arg, float gx, float gy, int norm_taps, float out[2]) {
+    int H = f->H, W = f->W;
+    float ix = (gx + 1.0f) * ((float)(W - 1) / 2.0f);
+    float iy = (gy + 1.0f) * ((float)(H - 1) / 2.0f);
+    float xw = floorf(ix), yn = floorf(iy), xe = xw + 1.0f, ys = yn + 1.0f;
+    float w = ix - xw, e = xe - ix, nn = iy - yn, ss = ys - iy;
+    float nw = ss * e, ne = ss * w, sw = nn * e, se = nn * w;
+    int inx0 = (xw > -1.0f) && (xw < (float)W), inx1 = (xe > -1.0f) && (xe < (float)W);
+    int iny0 = (yn > -1.0f) && (yn < (float)H), iny1 = (ys > -1.0f) && (ys < (float)H);
+    int x0 = inx0 ? (int)xw : 0, x1 = inx1 ? (int)xe : 0, y0 = iny0 ? (int)yn : 0, y1 = iny1 ? (int)ys : 0;
+    float t[4][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
+    if (inx0 && iny0) value(f, arg, y0, x0, t[0]);
+    if (inx1 && iny0) value(f, arg, y0, x1, t[1]);
+    if (inx0 && iny1) value(f, arg, y1, x0, t[2]);
+    if (inx1 && iny1) value(f, arg, y1, x1, t[3]);
+    for (int c = 0; c < 2; c++) {
+        float v[4];
+        for (int k = 0; k < 4; k++) v[k] = norm_taps ? norm_flow1(t[k][c], c ? H : W, f->div_mode) : t[k][c];
+        out[c] = tap_combine(v[0], v[1], v[2], v[3], nw, ne, sw, se, 0);
+    }
+}
+
+/* composite flow at integer pixel (Y,X): util.py:303-308 (n == 1: the link itself) / :309-328 (chain) */
+static void comp_value(const comp_field* f, int unused, int Y, int X, float v[2]) {
+    (void)unused;
+    if (f->n == 1) {
+        comp_link_value(f, 0, Y, X, v);
+        return;
+    }
+    float c0x = (float)X, c0y = (float)Y, cx = c0x, cy = c0y;
+    for (int i = 0; i < f->n; i++) { /* util.py:321-323 */
+        float gx = norm_coord1(cx, f->W, f->div_mode), gy = norm_coord1(cy, f->H, f->div_mode), s[2];
+        comp_grid_sample(f, comp_link_value, i, gx, gy, 0, s);
+        cx = cx + s[0];
+        cy = cy + s[1];
+    }
+    v[0] = cx - c0x; /* util.py:328 */
+    v[1] = cy - c0y;
+}
+
+/* lo_fwd/lo_bwd: loader layout [B,n,2,h,w] (dense links if !flow_up).  coord_fwd [B,10]: descriptors whose centres are
+ * warped by the forward composite (mask = FB(fwd,bwd)); coord_bwd: by the backward one.  Either (coord, warped) pair may
+ * be NULL.  warped_* [3,B,P]: out_x, out_y (PixPro.py:76-83), mask_grid as 0/1 (PixPro.py:65-70; ones if !use_mask). */
+ORC_API void orc_sparse_corr(const float* lo_fwd, const float* lo_bwd, long B, int n, int h, int w, int flow_up, int use_mask,
+                             double alpha_1, double alpha_2, const float* coord_fwd, const float* coord_bwd, int G,
+                             int H_orig, int W_orig, int div_mode, float* warped_fwd, float* warped_bwd) {
+    int H = flow_up ? 8 * h : h, W = flow_up ? 8 * w : w, P = G * G;
+    axis_tap* ty = (axis_tap*)malloc(sizeof(axis_tap) * H);
+    axis_tap* tx = (axis_tap*)malloc(sizeof(axis_tap) * W);
+    if (flow_up) {
+        make_axis_taps(h, H, ty);
+        make_axis_taps(w, W, tx);
+    }
+    long link = 2L * h * w;
+    float a1 = (float)alpha_1, a2 = orc_fb_alpha2_eff(alpha_2, H, W);
+    int diff = (H != H_orig) || (W != W_orig);
+    float rh = (float)((double)H / (double)H_orig), rw = (float)((double)W / (double)W_orig);
+    for (int d = 0; d < 2; d++) {
+        const float* coord = d ? coord_bwd : coord_fwd;
+        float* out = d ? warped_bwd : warped_fwd;
+        if (!coord || !out) continue;
+        float* cx = (float*)malloc(sizeof(float) * B * P);
+        float* cy = (float*)malloc(sizeof(float) * B * P);
+        float* dg = (float*)malloc(sizeof(float) * B);
+        orc_grid_centres(coord, B, G, H_orig, W_orig, div_mode, cx, cy, dg);
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
+        for (long b = 0; b < B; b++)
+            for (int p = 0; p < P; p++) {
+                comp_field f = {(d ? lo_bwd : lo_fwd) + b * n * link, n, flow_up, h, w, H, W, div_mode, link, ty, tx};
+                comp_field g = {(d ? lo_fwd : lo_bwd) + b * n * link, n, flow_up, h, w, H, W, div_mode, link, ty, tx};
+                float xg = cx[b * P + p], yg = cy[b * P + p];
+                float gx = 2.0f * div_scalar(xg, (float)(W_orig - 1), div_mode) - 1.0f; /* PixPro.py:61-62 */
+                float gy = 2.0f * div_scalar(yg, (float)(H_orig - 1), div_mode) - 1.0f;
+                float fg[2];
+                comp_grid_sample(&f, comp_value, 0, gx, gy, 0, fg); /* :64 */
+                float mg = 1.0f;
+                if (use_mask) { /* :65-70 nearest lookup of the FB mask, evaluated at that pixel only */
+                    float ix = (gx + 1.0f) * ((float)(W - 1) / 2.0f), iy = (gy + 1.0f) * ((float)(H - 1) / 2.0f);
+                    float xr = nearbyintf(ix), yr = nearbyintf(iy);
+                    mg = 0.0f;
+                    if (xr > -1.0f && xr < (float)W && yr > -1.0f && yr < (float)H) {
+                        int X = (int)xr, Y = (int)yr;
+                        float fv[2], bi[2];
+                        comp_value(&f, 0, Y, X, fv);
+                        float fnx = norm_flow1(fv[0], W, div_mode), fny = norm_flow1(fv[1], H, div_mode); /* util.py:264 */
+                        float c1x = norm_coord1((float)X, W, div_mode) + fnx;                             /* :271,275 */
+                        float c1y = norm_coord1((float)Y, H, div_mode) + fny;
+                        int inb = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);                             /* :276 */
+                        comp_grid_sample(&g, comp_value, 0, c1x, c1y, 1, bi);                             /* :278 */
+                        float cyx = fnx + bi[0], cyy = fny + bi[1];                                       /* :279 */
+                        float cyc2 = cyx * cyx + cyy * cyy;                                               /* :293 */
+                        float f2 = fnx * fnx + fny * fny, b2 = bi[0] * bi[0] + bi[1] * bi[1];
+                        float eps = a1 * (f2 + b2) + a2;                                                  /* :294 */
+                        mg = (inb && ((cyc2 - eps) <= 0.0f)) ? 1.0f : 0.0f;                               /* :296 */
+                    }
+                }
+                float ox, oy;
+                if (diff) { /* PixPro.py:76-80 */
+                    ox = div_scalar(xg * rw + fg[0], rw, div_mode);
+                    oy = div_scalar(yg * rh + fg[1], rh, div_mode);
+                } else { /* :82-83 */
+                    ox = xg + fg[0];
+                    oy = yg + fg[1];
+                }
+                out[b * P + p] = ox;
+                out[B * P + b * P + p] = oy;
+                out[2 * B * P + b * P + p] = mg;
+            }
+        free(cx);
+        free(cy);
+        free(dg);
+    }
+    free(ty);
+    free(tx);
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -244,3 +244,16 @@ def test_sparse_equals_dense_in_rcp_division_mode(ops, synth):
         assert torch.equal(pnd, pns) and torch.equal(ld, ls) and pns.sum().item() > 0
     finally:
         ops.set_div_mode("ieee")
+
+
+@pytest.mark.parametrize("B,n,G", [(64, 1, 7), (16, 5, 7), (8, 2, 14)])
+def test_sparse_corr_full_size_vs_oracle_restatement(ops, orc, synth, B, n, G):
+    """At the bench sizes the dense oracle is too slow for a unit test, but the oracle's own sparse restatement
+    (orc_sparse_corr, pinned against the reference's dense route on CPU) is not: bit-exact at full batch."""
+    lf, lb = synth.flow_fields(B, n, seed=120 + n)
+    c1, c2 = synth.crop_coords(B, seed=121), synth.crop_coords(B, seed=122)
+    wf, wb = ops.sparse_corr(lf.to(DEV), lb.to(DEV), c1.to(DEV), c2.to(DEV), G, (720, 1280))
+    of, ob = orc.sparse_corr(lf.numpy(), lb.numpy(), c1.numpy(), c2.numpy(), G, (720, 1280))
+    assert_bits_equal(npy(wf), of, "forward direction")
+    assert_bits_equal(npy(wb), ob, "backward direction")
+    assert 0.2 < of[2].mean() < 1.0

@@ -148,3 +148,46 @@ def test_lars_sgd_golden(orc):
             assert rate == 1.0
             assert_bits_equal(p1, want, f"SGD tensor {i} step {s}")
         state[i] = (p1, buf1)
+
+
+# ---- sparse correspondence restatement (orc_sparse_corr): flow stage + add_optical_flow at the grid centres only ----
+
+@pytest.mark.parametrize("tag", ["flow_g7_n1_mask", "flow_g7_n5_mask", "flow_g7_big", "flow_g7_diffsize", "flow_g14_n2_nomask"])
+def test_sparse_corr_against_reference_golden(orc, tag):
+    """Warped centres and mask bits the REFERENCE produced (its add_optical_flow on the flows its apply_optical_flow built
+    from these links), reproduced from the low-res links alone."""
+    g = load_golden("loss_" + tag)
+    use_mask = bool(g["use_mask"])
+    G = g["q"].shape[-1]
+    wf, wb = orc.sparse_corr(g["lo_fwd"], g["lo_bwd"], g["coord_q"], None, G, tuple(int(v) for v in g["size"]),
+                             alpha_1=0.01 if use_mask else None, alpha_2=0.5 if use_mask else None)
+    assert wb is None
+    assert_bits_equal(wf[0], g["cqx"], "warped centre x")
+    assert_bits_equal(wf[1], g["cqy"], "warped centre y")
+    if "mask_grid" in g:
+        assert_bits_equal(wf[2] != 0, g["mask_grid"].astype(bool), "mask_grid")
+    else:
+        assert (wf[2] == 1).all()
+
+
+@pytest.mark.parametrize("n,h,w,flow_up,size,G,mag,div_mode", [
+    (1, 18, 32, True, (144, 256), 7, 0.4, 0), (3, 18, 32, True, (144, 256), 7, 0.4, 0), (5, 18, 32, True, (144, 256), 5, 3.0, 0),
+    (2, 18, 32, True, (720, 1280), 7, 0.4, 0), (3, 48, 64, False, (48, 64), 7, 4.0, 0), (2, 18, 32, True, (144, 256), 7, 0.4, 1)])
+def test_sparse_corr_equals_sampling_the_dense_stage(orc, n, h, w, flow_up, size, G, mag, div_mode):
+    """The property the sparse mode rests on: evaluating the chain / FB test at single pixels equals sampling the dense
+    composites and masks (both directions, out-of-frame flows, flow resolution != image resolution, rcp division)."""
+    from pixpro_b200 import synth
+    B = 3
+    lf, lb = synth.flow_fields(B, n, h=h, w=w, magnitude=mag, seed=7 * n + G, coarse=(3, 4))
+    lf, lb = lf.numpy(), lb.numpy()
+    c1 = synth.crop_coords(B, size[1], size[0], seed=n).numpy()
+    c2 = synth.crop_coords(B, size[1], size[0], seed=n + 50).numpy()
+    ff, fb, mf, mb = orc.flow_stage(lf, lb, flow_up=flow_up, div_mode=div_mode)
+    wf, wb = orc.sparse_corr(lf, lb, c1, c2, G, size, flow_up=flow_up, div_mode=div_mode)
+    z = np.zeros((B, 1, G, G), np.float32)
+    for wp, c, fl, mk in ((wf, c1, ff, mf), (wb, c2, fb, mb)):
+        o = orc.regression_loss(z, z, c, c, 0.7, flow=None, size=size, want_grad=False, div_mode=div_mode)  # un-warped centres
+        ox, oy, mg = orc.add_optical_flow(fl, o["cqx"].reshape(B, G, G), o["cqy"].reshape(B, G, G), size, mk, div_mode=div_mode)
+        assert_bits_equal(wp[0], ox.reshape(B, -1), "warped x")
+        assert_bits_equal(wp[1], oy.reshape(B, -1), "warped y")
+        assert_bits_equal(wp[2] != 0, mg.reshape(B, -1), "mask bit")
