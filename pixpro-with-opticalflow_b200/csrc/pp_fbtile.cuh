@@ -638,7 +638,7 @@ static int launch_chain_box(const float* l0, const float* l1, float* o0, float* 
     a.dw = make_div<DM_FAST>((float)(W - 1)); a.dh = make_div<DM_FAST>((float)(H - 1));
     // planes addressable from each base: the last link of the last sample ends at this plane
     const int64_t planes = (B - 1) * a.plane_b + (int64_t)(n - 1) * a.plane_n + 2;
-    return launch_chain_cfg<false, 64, 48, 96, 72, 3>(a, B, l0, l1, planes, planes, st);
+    return launch_chain_cfg<false, 64, 48, 96, 72, 4>(a, B, l0, l1, planes, planes, st);
 }
 
 // The fused up-sampling chain measures on par with the chunked scratch path (3.9 vs 4.0 ms at B=64, n=5) but worse
