@@ -137,7 +137,9 @@ class ClockSampler:
     def start(self):
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
-        time.sleep(0.02)  # let the first sample land before the timed region opens
+        deadline = time.perf_counter() + 5.0  # NVML initialisation can take a while on a fresh box:
+        while not self.samples and time.perf_counter() < deadline:  # wait for the first sample before the timed region opens
+            time.sleep(0.005)
         self.t0 = time.perf_counter()
 
     def stop(self):
