@@ -263,3 +263,25 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_algorithmic_bytes_of_the_other_kernels():
+    """Per-kernel figures behind `roofline` for the non-default configurations (DESIGN.md §4 / SURVEY.md §8d)."""
+    import bench
+    comp, cp4 = 2 * 2 * 720 * 1280 * 4, 256 * 49 * 4
+    assert bench.algorithmic_bytes("chain_dense", 64, 5) == 64 * 6 * comp           # F1': n links in, composites out
+    assert bench.algorithmic_bytes("fb", 64, 1) == 64 * (comp + 2 * 720 * 1280)      # F2
+    assert bench.algorithmic_bytes("loss_small", 64, 1, 7) == 64 * 6 * cp4           # F3: q, k in; dq out; both directions
+    assert bench.algorithmic_bytes("ppm_fwd_small", 64, 1, 7) == 64 * 6 * cp4
+    assert bench.algorithmic_bytes("ppm_bwd_small", 64, 1, 7) == 64 * 12 * cp4
+    assert bench.algorithmic_bytes("no such kernel", 64, 1) == 0
+
+
+def test_profiles_index_names_existing_files():
+    import re
+    txt = open(os.path.join(ROOT, "profiles", "INDEX.md")).read()
+    names = set(re.findall(r"`((?:mb/)?r?[\w./-]+\.(?:json|csv|txt|ncu-rep|py|cu))`", txt))
+    assert len(names) > 20
+    names -= {"bench.py", "_summary.txt"}  # the repo-root script and a suffix mentioned in passing
+    missing = [n for n in names if "*" not in n and not os.path.exists(os.path.join(ROOT, "profiles", n))]
+    assert not missing, missing
