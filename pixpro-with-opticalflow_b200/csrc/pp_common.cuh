@@ -39,6 +39,21 @@ class ProfScope {
         ::pp::count_launch();                  \
     } while (0)
 
+// One-time opt-in of a kernel to more than 48 KB of dynamic shared memory, PER DEVICE: the attribute belongs to the
+// (function, device) pair, so a process that drives several GPUs must set it on each.  `done` is one bit mask per
+// call site (i.e. per kernel instantiation), bit = device ordinal; racing first calls both set the attribute (idempotent).
+template <class K>
+static inline cudaError_t smem_opt_in(K kern, int bytes, unsigned long long& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) __atomic_fetch_or(&done, bit, __ATOMIC_RELEASE);
+    return e;
+}
+
 #define PP_REQUIRE(cond, ...)                 \
     do {                                      \
         if (!(cond)) {                        \
@@ -180,6 +195,12 @@ __device__ __forceinline__ F2 mul2(F2 a, F2 b) {
 __device__ __forceinline__ F2 add2(F2 a, F2 b) {
     F2 r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+// round-down add (FADD2.RM): see the packed floor of fbbox_kernel
+__device__ __forceinline__ F2 add2_rm(F2 a, F2 b) {
+    F2 r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
     return r;
 }
 __device__ __forceinline__ F2 sub2(F2 a, F2 b) {

@@ -89,7 +89,12 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, i
 // grid = (W / TW, H / TH, planes); block = 256.  Requires W % TW == 0 and H % TH == 0.
 // WC/HC > 0: the frame size is a compile-time constant (the 1280x720 frames of the published BDD100K runs): every
 // derived constant and row offset folds into instruction immediates (no per-pixel constant-bank loads).
-template <int TW, int TH, int BW, int BH, int MINB, int WC, int HC>
+// OPT (A/B switches, all value-preserving): 1 = own-flow loads and mask stores address with immediate offsets off one
+// per-thread pointer (compile-time frame size only); 2 = floor by a round-down add of 1.5*2^23 on packed pairs
+// (FADD2.RM: the integer sits in the low mantissa bits, the float floor is one exact subtraction) instead of
+// F2I.FLOOR + I2FP per coordinate; 4 = the rare global-memory path re-derives its tap origin instead of every pixel
+// packing one.
+template <int TW, int TH, int BW, int BH, int MINB, int WC, int HC, int OPT>
 __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant__ CUtensorMap tm0,
                                                           const __grid_constant__ CUtensorMap tm1,
                                                           const __grid_constant__ CUtensorMap tp0,
@@ -171,9 +176,14 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
         for (int c = 0; c < NX; c++)
 #pragma unroll
             for (int p = 0; p < 2; p++) {
-                const float* q = ptr_at(fp, (kp + p) * rstep + 32 * c);
-                nfx[c][p] = __ldg(q);
-                nfy[c][p] = __ldg(ptr_at(q, HW));
+                if ((OPT & 1) && WC) {
+                    nfx[c][p] = __ldg(fp + ((kp + p) * 8 * WC + 32 * c));
+                    nfy[c][p] = __ldg(fp + (WC * HC + (kp + p) * 8 * WC + 32 * c));
+                } else {
+                    const float* q = ptr_at(fp, (kp + p) * rstep + 32 * c);
+                    nfx[c][p] = __ldg(q);
+                    nfy[c][p] = __ldg(ptr_at(q, HW));
+                }
             }
     };
     prefetch(0);
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
     const float* sp = reinterpret_cast<const float*>(fbt_smem);
     int nglobal = 0;  // pixels of this thread whose footprint was outside the staged box
     const float* g = (dir ? a.flow[0] : a.flow[1]) + (int64_t)b * 2 * HW;
-#pragma unroll
+#pragma unroll(OPT & 8 ? 1 : NR / 2)
     for (int kp = 0; kp < NR; kp += 2) {
         float fxs[NX][2], fys[NX][2];
 #pragma unroll
@@ -203,15 +213,32 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
             bool inb[2], outside[2];
             int gofs[2];
             float t[2][8], xws[2], yws[2];
+            if (OPT & 2) {
+                // x + 1.5*2^23 rounded DOWN = 1.5*2^23 + floor(x) exactly for |x| < 2^22 (ulp is 1 there); the bits are
+                // 0x4B400000 + floor(x).  Garbage (NaN / huge) only occurs for pixels outside the frame, whose tap
+                // address is clamped below and whose mask bit is 0 whatever they read.
+                const F2 mg = pk1(12582912.0f);
+                const F2 tx = add2_rm(ix, mg), ty = add2_rm(iy, mg);
+                unpk(sub2(tx, mg), xws[0], xws[1]);
+                unpk(sub2(ty, mg), yws[0], yws[1]);
+                unpk(tx, ixs[0], ixs[1]);  // reuse as bit carriers
+                unpk(ty, iys[0], iys[1]);
+            }
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);                       // :276
-                const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
-                xws[p] = __int2float_rn(x0);
-                yws[p] = __int2float_rn(y0);
+                int x0, y0;
+                if (OPT & 2) {
+                    x0 = __float_as_int(ixs[p]) - 0x4B400000; y0 = __float_as_int(iys[p]) - 0x4B400000;
+                } else {
+                    x0 = __float2int_rd(ixs[p]); y0 = __float2int_rd(iys[p]);
+                    xws[p] = __int2float_rn(x0);
+                    yws[p] = __int2float_rn(y0);
+                }
                 const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
                 outside[p] = inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
-                gofs[p] = (y0 << 16) | (x0 & 0xffff);  // only read for in-frame pixels (launcher: W, H < 32768)
+                if (OPT & 4) gofs[p] = 0;
+                else gofs[p] = (y0 << 16) | (x0 & 0xffff);  // only read for in-frame pixels (launcher: W, H < 32768)
                 // clamp: a pixel outside the box or the frame still addresses the staged box
                 const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
                 t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
@@ -223,7 +250,10 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
 #pragma unroll
                 for (int p = 0; p < 2; p++)
                     if (outside[p]) {
-                        const int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
+                        int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
+                        if (OPT & 4) {  // in-frame pixel: xws / yws are exact small non-negative integers
+                            x0 = (int)xws[p]; y0 = (int)yws[p];
+                        }
                         const float* q = ptr_at(g, y0 * W + x0);
                         const bool xin = x0 < W - 1, yin = y0 < H - 1;
                         t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
@@ -248,8 +278,11 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
             float ds[2];
             unpk(sub2(cyc2, eps), ds[0], ds[1]);
 #pragma unroll
-            for (int p = 0; p < 2; p++)
-                *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = (inb[p] && (ds[p] <= 0.0f)) ? 1 : 0;   // :296
+            for (int p = 0; p < 2; p++) {
+                const uint8_t bit = (inb[p] && (ds[p] <= 0.0f)) ? 1 : 0;                             // :296
+                if ((OPT & 1) && WC) mp[(kp + p) * 8 * WC + 32 * c] = bit;
+                else *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = bit;
+            }
         }
     }
     // diagnostics counter: one global atomic per CTA at most (per-thread atomics on one address
@@ -538,26 +571,20 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t planes, int H, 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int TW, int TH, int BW, int BH, int MINB, int WC = 0, int HC = 0>
+template <int TW, int TH, int BW, int BH, int MINB, int WC = 0, int HC = 0, int OPT = 0>
 static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
-    auto kern = fbbox_kernel<TW, TH, BW, BH, MINB, WC, HC>;
+    auto kern = fbbox_kernel<TW, TH, BW, BH, MINB, WC, HC, OPT>;
     constexpr int smem = 2 * BW * BH * 4;
-    static bool ready = false;
+    static unsigned long long opted = 0;  // one bit per device
     static const bool dbg = getenv("PIXPRO_B200_FBDBG") != nullptr;
     if (a.W % TW != 0 || a.H % TH != 0) return -1;
-    if (!ready) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = smem_opt_in(kern, smem, opted);
         if (e != cudaSuccess) {
             if (dbg) fprintf(stderr, "fbbox: cudaFuncSetAttribute(%d) failed: %s\n", smem, cudaGetErrorString(e));
             cudaGetLastError();
             return -1;
         }
-        if (dbg) {
-            int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
-            fprintf(stderr, "fbbox<%d,%d,%d,%d>: %d blocks/SM, %d B smem\n", TW, TH, BW, BH, occ, smem);
-        }
-        ready = true;
     }
     CUtensorMap tm0, tm1, tp0, tp1;
     if (!make_map(&tm0, a.flow[0], B * 2, a.H, a.W, BW, BH) || !make_map(&tm1, a.flow[1], B * 2, a.H, a.W, BW, BH) ||
@@ -587,7 +614,18 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
     a.dw2 = make_div<DM_FAST>((float)(W - 1) / 2.0f); a.dh2 = make_div<DM_FAST>((float)(H - 1) / 2.0f);
     static const int variant = [] { const char* e = getenv("PIXPRO_B200_FBTILE"); return e ? atoi(e) : 1; }();
     if (variant == 0) return -1;  // disabled: gather kernels
-    if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);  // the published frame size
+    if (W == 1280 && H == 720) {  // the published frame size
+        switch (variant) {
+            case 2: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 1>(a, B, st);
+            case 3: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 5>(a, B, st);
+            case 4: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 7>(a, B, st);
+            case 5: return launch_cfg<64, 48, 96, 72, 3, 1280, 720, 5>(a, B, st);
+            case 6: return launch_cfg<64, 48, 96, 72, 3, 1280, 720, 7>(a, B, st);
+            case 7: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 12>(a, B, st);
+            case 8: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 14>(a, B, st);
+            default: return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
+        }
+    }
     if (H % 48 == 0) return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
     if (H % 32 == 0) return launch_cfg<64, 32, 96, 56, 4>(a, B, st);
     return -1;
@@ -598,14 +636,11 @@ static int launch_chain_cfg(const ChainBoxArgs& a, int64_t B, const float* base0
                             int64_t planes1, cudaStream_t st) {
     auto kern = chainbox_kernel<UP, TW, TH, BW, BH, MINB>;
     constexpr int smem = 2 * BW * BH * 4 + (UP ? 2 * (BH / 8 + 3) * BW * 4 : 0);
-    static bool ready = false;
+    static unsigned long long opted = 0;  // one bit per device
     if (a.W % TW != 0 || a.H % TH != 0) return -1;
-    if (!ready) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            cudaGetLastError();
-            return -1;
-        }
-        ready = true;
+    if (smem_opt_in(kern, smem, opted) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
     }
     CUtensorMap tm0, tm1;
     memset(&tm0, 0, sizeof(tm0));

@@ -620,10 +620,10 @@ static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int
     int ntile = loss_ntile(P);
     int rc;
     if (P <= PMAX && ((C * P) % 4 == 0) && small_loss_smem_bytes(C, P) <= 226 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(loss_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            attr_set = true;
+        static unsigned long long opted = 0;  // one bit per device
+        if (smem_opt_in(loss_small_kernel, 227 * 1024, opted) != cudaSuccess) {
+            set_error("loss_small_kernel: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return PP_ERR_CUDA;
         }
         SmallLossArgs2 sa2;
         for (int c = 0; c < ncall; c++) {

@@ -191,18 +191,15 @@ __global__ void __launch_bounds__(PT) ppm_bwd_small_kernel(SmallArgs a) {
 
 // opt in to > 48 KB of dynamic shared memory, once per process, with the result checked
 static int ensure_small_attrs() {
-    static int state = -1;  // -1 unknown, 0 ok, else error code
-    if (state >= 0) return state;
-    cudaError_t e1 = cudaFuncSetAttribute(ppm_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaError_t e2 = cudaFuncSetAttribute(ppm_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static unsigned long long opted_f = 0, opted_b = 0;  // one bit per device
+    cudaError_t e1 = smem_opt_in(ppm_fwd_small_kernel, 227 * 1024, opted_f);
+    cudaError_t e2 = smem_opt_in(ppm_bwd_small_kernel, 227 * 1024, opted_b);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         cudaGetLastError();
         set_error("ppm small: cudaFuncSetAttribute failed: %s / %s", cudaGetErrorString(e1), cudaGetErrorString(e2));
-        state = PP_ERR_CUDA;
-    } else {
-        state = PP_OK;
+        return PP_ERR_CUDA;
     }
-    return state;
+    return PP_OK;
 }
 
 bool ppm_small_supported(int C, int P) {

@@ -253,172 +253,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(int M, int N, in
     if (warp == 0) tmem_dealloc(tmem_d, 2 * TN);
 }
 
-// ---- warp-specialised variant ---------------------------------------------------------------
-// Same tile shape and MMA sequence as tc_gemm_kernel, restructured around what bounds that kernel: the
-// L1/shared-memory data pipe (ncu: the staging stores, the operand loads' L1 wavefronts and the tensor
-// core's own operand reads share it), not the barrier.
-//  * 32-wide K chunks: a warp's operand load covers 4 rows x 128 contiguous bytes (4 L1 wavefronts per
-//    512 B instead of 8), and with 8 threads per row a quarter-warp's STS.128 writes one row's eight
-//    16-byte K columns, WS_LBO = 2048 + 16 bytes apart: eight distinct bank groups, conflict-free.
-//  * no CTA-wide barrier per chunk: warps 0-7 are PRODUCERS (global -> registers -> hi/lo split -> shared
-//    memory) running up to WS_STAGES chunks ahead through a ring of stages, warp 8 ISSUES the MMAs.
-//    Two mbarriers per stage: full[s] (count 8: lane 0 of every producer warp arrives after its warp's
-//    stores + async-proxy fence), empty[s] (count 1: tcgen05.commit arrives when the MMAs that read the
-//    stage have completed); `done` (commit after the last chunk) releases the epilogue, which all 8
-//    producer warps share (warp w and w+4 own the same 32 TMEM lanes and split the columns).
-//  * one CTA per SM (3 stages x 65 KB): the overlap two co-resident CTAs gave the synchronous kernel
-//    now happens inside the CTA.
-constexpr int WS_TK = 32;
-constexpr uint32_t WS_LBO = (TM / 8) * 128 + 16;
-constexpr uint32_t WS_TILE_BYTES = (WS_TK / 4) * WS_LBO;
-constexpr uint32_t WS_STAGE_BYTES = 4 * WS_TILE_BYTES;
-constexpr int WS_STAGES = 3;
-constexpr int WS_GROUP = TC_THREADS;  // producer threads per chunk (measured: two groups of 128 alternating chunks, i.e. two
-                                      // chunks of loads in flight per thread set, is 2.5x SLOWER - 16 outstanding LDG.128 per thread)
-constexpr int WS_ITEMS = (TM * (WS_TK / 4)) / WS_GROUP;  // float4 items per producer thread per operand per chunk (= 4)
-constexpr int WS_THREADS = TC_THREADS + 32;
-constexpr uint32_t WS_SMEM_BYTES = WS_STAGES * WS_STAGE_BYTES + 128;
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint64_t ws_desc(uint32_t saddr) {  // make_desc with the WS leading-dimension offset
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(WS_LBO >> 4) << 16;
-    d |= (uint64_t)(SBO >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-template <class L>
-__device__ __forceinline__ void ws_item_coords(int it, int& row, int& kc) {
-    const int item = it * WS_GROUP + (threadIdx.x & (WS_GROUP - 1));
-    constexpr int KC = WS_TK / 4;
-    row = L::kRowMajorK ? (item / KC) : (item & (TM - 1));
-    kc = L::kRowMajorK ? (item % KC) : (item >> 7);
-}
-template <class L>
-__device__ __forceinline__ void ws_load_operand(const L& ld, int64_t b, int row0, int k0, float4 r[WS_ITEMS]) {
-#pragma unroll
-    for (int it = 0; it < WS_ITEMS; it++) {
-        int row, kc;
-        ws_item_coords<L>(it, row, kc);
-        r[it] = ld.load4(b, row0 + row, k0 + 4 * kc);
-    }
-}
-template <class L>
-__device__ __forceinline__ void ws_store_operand(const float4 r[WS_ITEMS], uint8_t* hi, uint8_t* lo) {
-#pragma unroll
-    for (int it = 0; it < WS_ITEMS; it++) {
-        int row, kc;
-        ws_item_coords<L>(it, row, kc);
-        const uint32_t off = (uint32_t)kc * WS_LBO + (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16;
-        const float4 v = r[it];
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
-    }
-}
-
-template <class LA, class LB, class EP>
-__global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(int M, int N, int K, LA la, LB lb, EP ep) {
-    extern __shared__ __align__(128) uint8_t tc_smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(tc_smem + WS_STAGES * WS_STAGE_BYTES);
-    uint64_t* empty = full + WS_STAGES;
-    uint64_t* done = empty + WS_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-    const int64_t b = blockIdx.z;
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < WS_STAGES; s++) {
-            mbar_init(&full[s], WS_GROUP / 32);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == TC_THREADS / 32) tmem_alloc(tmem_slot, 2 * TN);  // the MMA warp owns the allocation
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem_d = *tmem_slot;
-    const int nchunk = (K + WS_TK - 1) / WS_TK;
-    if (warp < TC_THREADS / 32) {
-        // ---------------- producers ----------------
-        float4 ra[WS_ITEMS], rb[WS_ITEMS];
-        ws_load_operand(la, b, m0, 0, ra);
-        ws_load_operand(lb, b, n0, 0, rb);
-        int s = 0, use = 0;  // stage of chunk c, how many times the ring wrapped
-        for (int c = 0; c < nchunk; c++) {
-            uint8_t* st = tc_smem + s * WS_STAGE_BYTES;
-            float4 na[WS_ITEMS], nb[WS_ITEMS];
-            if (c + 1 < nchunk) {  // next chunk's global loads in flight during this chunk's stores
-                ws_load_operand(la, b, m0, (c + 1) * WS_TK, na);
-                ws_load_operand(lb, b, n0, (c + 1) * WS_TK, nb);
-            }
-            if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);  // the MMAs of chunk c - WS_STAGES have completed
-            ws_store_operand<LA>(ra, st, st + WS_TILE_BYTES);
-            ws_store_operand<LB>(rb, st + 2 * WS_TILE_BYTES, st + 3 * WS_TILE_BYTES);
-            fence_smem_to_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            if (c + 1 < nchunk) {
-#pragma unroll
-                for (int it = 0; it < WS_ITEMS; it++) { ra[it] = na[it]; rb[it] = nb[it]; }
-            }
-            if (++s == WS_STAGES) { s = 0; use++; }
-        }
-        // ---------------- epilogue: thread t of warp w owns TMEM lane 32 (w % 4) + t, columns split by w / 4
-        mbar_wait(done, 0);
-        fence_after_sync();
-        const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
-        const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
-        const int j0 = (warp >> 2) * (TN / 2);
-#pragma unroll 1
-        for (int j = j0; j < j0 + TN / 2; j += 16) {
-            float v[16], w[16];
-            tmem_ld16(lane_addr + j, v);
-            tmem_ld16(lane_addr + TN + j, w);
-#pragma unroll
-            for (int i = 0; i < 16; i++) v[i] += w[i];
-            if (m < M && n0 + j < N) ep.store16(b, m, n0 + j, v);
-        }
-    } else {
-        // ---------------- MMA issuer ----------------
-        const uint32_t idesc = make_idesc(TM, TN);
-        int s = 0, use = 0;
-        for (int c = 0; c < nchunk; c++) {
-            mbar_wait(&full[s], use & 1);
-            fence_after_sync();
-            if (lane == 0) {
-                const uint32_t a_hi = smem_u32(tc_smem + s * WS_STAGE_BYTES), a_lo = a_hi + WS_TILE_BYTES,
-                               b_hi = a_hi + 2 * WS_TILE_BYTES, b_lo = a_hi + 3 * WS_TILE_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < WS_TK / 8; kk++) {  // one MMA consumes K = 8 fp32 = two 16-byte columns
-                    const uint32_t ko = kk * 2 * WS_LBO;
-                    const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-                    mma_tf32(tmem_d, ws_desc(a_hi + ko), ws_desc(b_hi + ko), idesc, acc);
-                    mma_tf32(tmem_d + TN, ws_desc(a_hi + ko), ws_desc(b_lo + ko), idesc, acc);
-                    mma_tf32(tmem_d + TN, ws_desc(a_lo + ko), ws_desc(b_hi + ko), idesc, 1u);
-                }
-                mma_commit(&empty[s]);
-                if (c == nchunk - 1) mma_commit(done);
-            }
-            __syncwarp();
-            if (++s == WS_STAGES) { s = 0; use++; }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == TC_THREADS / 32) tmem_dealloc(tmem_d, 2 * TN);
-}
-
 }  // namespace tc
 
 // ---- loaders / epilogues shared by the PPM and loss contractions -----------------------------------
@@ -455,32 +289,14 @@ struct TcStN {  // out[b][m][n..n+15]
         }
     }
 };
-// PIXPRO_B200_TCWS=1 selects the warp-specialised ring kernel (A/B runs).  Measured on a B200 (profiles/mb/
-// tc_gemm_bench.py, conv_ws_bench.py): on par or slower on the large shapes (8x2048^3: 115 vs 125 TFLOP/s useful,
-// 28x28 similarity 46.9 vs 52.5), 10 % faster on the 16-chunk conv GEMMs - both kernels are bound by global-load
-// latency per chunk (one register set of prefetch), not by the barrier - so the CTA-synchronous kernel stays the default.
-static inline bool tc_warp_specialised() {
-    static const int on = [] { const char* e = getenv("PIXPRO_B200_TCWS"); return e ? atoi(e) : 0; }();
-    return on != 0;
-}
 template <class LA, class LB, class EP>
 static inline int launch_tc(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
     dim3 grid((N + tc::TN - 1) / tc::TN, (M + tc::TM - 1) / tc::TM, (unsigned)B);
-    if (tc_warp_specialised()) {
-        auto kern = tc::tc_gemm_ws_kernel<LA, LB, EP>;
-        static bool attr = false;  // one flag per template instantiation
-        if (!attr) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM_BYTES);
-            attr = true;
-        }
-        PP_LAUNCH(what, st, kern<<<grid, tc::WS_THREADS, tc::WS_SMEM_BYTES, st>>>(M, N, K, la, lb, ep));
-        return check_launch(what);
-    }
     auto kern = tc::tc_gemm_kernel<LA, LB, EP>;
-    static bool attr = false;  // one flag per template instantiation
-    if (!attr) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TC_SMEM_BYTES);
-        attr = true;
+    static unsigned long long opted = 0;  // per template instantiation, one bit per device
+    if (smem_opt_in(kern, (int)tc::TC_SMEM_BYTES, opted) != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%u B of shared memory) failed: %s", what, tc::TC_SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
+        return PP_ERR_CUDA;
     }
     PP_LAUNCH(what, st, kern<<<grid, tc::TC_THREADS, tc::TC_SMEM_BYTES, st>>>(M, N, K, la, lb, ep));
     return check_launch(what);

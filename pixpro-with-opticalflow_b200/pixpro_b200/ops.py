@@ -25,6 +25,16 @@ def get_div_mode():
     return {v: k for k, v in _DIV_MODES.items()}[_div_mode]
 
 
+_serial = False
+
+
+def set_serial(on):
+    """True: ops issue every launch on the current stream (no internal side streams) — for per-kernel timing
+    passes, where an overlapped launch's device time would include its overlap partner's."""
+    global _serial
+    _serial = bool(on)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -570,7 +580,7 @@ class _Conv1x1(torch.autograd.Function):
         db = torch.empty((Cout,), device=x.device, dtype=torch.float32) if need_b else None
         ws = torch.empty((L.pp_conv1x1_bwd_workspace(B, Cin, Cout, P),), device=x.device, dtype=torch.uint8)
         with torch.cuda.device(x.device):
-            if need_x and (need_w or need_b):
+            if need_x and (need_w or need_b) and not _serial:
                 # dgrad and wgrad (+ bias grad) are independent, latency-bound launches: issue the parameter
                 # gradients on a side stream (all buffers were allocated on the current one, which joins below)
                 cur = torch.cuda.current_stream(x.device)
