@@ -385,8 +385,9 @@ def graphed(ctx, fn):
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         keep = fn()
-    replay = graph.replay
-    replay.keep = (graph, keep)  # keep the graph and its output buffers alive
+    def replay(graph=graph, keep=keep):  # the closure keeps the graph and its output buffers alive
+        graph.replay()
+
     for _ in range(2):
         replay()
     return replay

@@ -53,6 +53,10 @@ PP_API int64_t pp_launch_count(void);
  * gather footprint fell outside the staged box and were recomputed from global memory.
  * Synchronises the device.  -1 on error. */
 PP_API int64_t pp_fb_redo_count(int reset);
+/* Diagnostics of the fused x8-up-sampling chain kernel (pp_flow_stage, n > 1, flow_up): number of pixel-links
+ * (since load / last reset) whose tap footprint fell outside the staged region and were evaluated from the
+ * low-res link directly (same values, slow path).  Synchronises the device.  -1 on error. */
+PP_API int64_t pp_chain_slow_count(int reset);
 /* Per-kernel device timing (tracing aid).  pp_profile_enable(1) clears the records and makes
  * every launch bracket its kernel with a cudaEvent pair on the launch stream;
  * pp_profile_num_kernels() synchronises those events and aggregates by kernel name;

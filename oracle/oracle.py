@@ -224,6 +224,24 @@ def regression_loss(q, k, coord_q, coord_k, pos_ratio=0.5, flow=None, size=None,
                 cqx=cqx, cqy=cqy, ckx=ckx, cky=cky, dq=dq)
 
 
+def near_threshold_pairs(o, coord_q, coord_k, G, size, pos_ratio, tol=1e-5):
+    """Number of (i, j) pairs per sample whose normalised centre distance lies within `tol` of pos_ratio
+    (SURVEY.md §8d asks for this count beside every positive-mask comparison: such pairs are the ones a 1-ulp
+    difference in a coordinate could flip).  o: the dict regression_loss() returned; distances are recomputed in
+    fp32 with the reference's formula (PixPro.py:140-157,217-218)."""
+    cq = np.asarray(coord_q, np.float32)
+    ck = np.asarray(coord_k, np.float32)
+    H, W = np.float32(size[0] - 1), np.float32(size[1] - 1)
+    g = np.float32(G)
+    qd = np.sqrt((((cq[:, 2] - cq[:, 0]) / g) * W) ** 2 + (((cq[:, 3] - cq[:, 1]) / g) * H) ** 2)
+    kd = np.sqrt((((ck[:, 2] - ck[:, 0]) / g) * W) ** 2 + (((ck[:, 3] - ck[:, 1]) / g) * H) ** 2)
+    md = np.maximum(qd, kd).astype(np.float32)[:, None, None]
+    dx = o["cqx"][:, :, None] - o["ckx"][:, None, :]
+    dy = o["cqy"][:, :, None] - o["cky"][:, None, :]
+    dist = np.sqrt(dx * dx + dy * dy).astype(np.float32) / md
+    return (np.abs(dist - np.float32(pos_ratio)) < tol).reshape(dist.shape[0], -1).sum(1)
+
+
 def featprop(feat, val, gamma=2.0, clamp_value=0.0, final_norm=True):
     """contrast/models/PixPro.py:339-363 (+ F.normalize at :380 when final_norm).
 

@@ -241,7 +241,9 @@ def main():
         g = dict(q=q.detach().numpy(), k=k.numpy(), coord_q=cq.numpy(), coord_k=ck.numpy(),
                  pos_ratio=np.float64(pos_ratio), size=np.array([H, W]), loss=np.float32(loss.item()),
                  pos_num=pos_num.numpy(), pos_mean=pos_mean.numpy(), dq=q.grad.numpy(),
-                 pos_mask=np.packbits(o["pos_mask"]))
+                 pos_mask=np.packbits(o["pos_mask"]),
+                 near_threshold_pairs=orc.near_threshold_pairs(o, cq.numpy(), ck.numpy(), G, (H, W), pos_ratio))
+        rep.rows.append((f"a8 {tag} pairs within 1e-5 of the threshold", f"{g['near_threshold_pairs'].tolist()} of {G ** 4} per sample"))
         if use_flow:
             # a7 directly
             P = G * G
@@ -328,6 +330,67 @@ def main():
             g.update(weight=m.value_transform.weight.detach().numpy(), bias=m.value_transform.bias.detach().numpy(),
                      d_weight=m.value_transform.weight.grad.numpy(), d_bias=m.value_transform.bias.grad.numpy())
         gold[f"featprop_{tag}"] = g
+
+    # ---------------- a4 / a6 general path: use_flow_frames (all sub-chains) and the debug return structure ----------------
+    for tag, B, n, h, w, kw in [("frames_n3", 2, 3, 9, 16, dict(use_flow_frames=True)),
+                                ("debug_n2", 2, 2, 9, 16, dict(debug=True))]:
+        args = make_args(**kw)
+        f, b = synth.flow_fields(B, n, h=h, w=w, seed=80 + n, magnitude=0.25)
+        H, W = 8 * h, 8 * w
+        data = [None] * 7
+        data[5] = [torch.zeros(B), f, b]
+        data[6] = [torch.tensor([[H, W]] * B), torch.tensor([[n + 1]] * B)]
+        (ff, size, mf), (fb_, _, mb) = rutil.apply_optical_flow(data, None, args)
+        g = dict(lo_fwd=f.numpy(), lo_bwd=b.numpy(), use_flow_frames=np.bool_(args.use_flow_frames), debug=np.bool_(args.debug),
+                 flow_fwd=ff.numpy(), flow_bwd=fb_.numpy(), size=np.asarray(size))
+        if args.debug:  # masks come back as [mask, cycle] lists (util.py:218-227)
+            g.update(mask_fwd=np.packbits(mf[0].numpy()), mask_bwd=np.packbits(mb[0].numpy()), mask_shape=np.array(mf[0].shape),
+                     cycle_fwd=mf[1].numpy(), cycle_bwd=mb[1].numpy())
+            want = orc.flow_stage(f.numpy(), b.numpy())
+            rep.exact(f"a6 general path {tag} flow_fwd", want[0], ff.numpy())
+            rep.exact(f"a6 general path {tag} mask_fwd", want[2], mf[0].numpy())
+        else:   # stacks over the n(n+1)/2 contiguous sub-chains (util.py:111-126), shortest first
+            g.update(mask_fwd=np.packbits(mf.numpy()), mask_bwd=np.packbits(mb.numpy()), mask_shape=np.array(mf.shape))
+            up_f = rflow.upflow8(f.permute(1, 0, 2, 3, 4).reshape(-1, 2, h, w)).reshape(n, B, 2, H, W).numpy()
+            idx = 0
+            for span in range(1, n + 1):
+                for s0 in range(n - span + 1):
+                    rep.exact(f"a4 all_concat_flow {tag} sub-chain [{s0}:{s0 + span}]", orc.concat_flow(up_f[s0:s0 + span]), ff[idx].numpy())
+                    idx += 1
+        gold[f"apply_general_{tag}"] = g
+
+    # ---------------- a10 / a12 / cfg 0: the whole reference model, one fwd+bwd step on CPU ----------------
+    # BASELINE configs[0]: PixPro ResNet-50, n_frames=1 (no flow), batch 4, 224x224 two-view crops, 7x7 grid.  Weights come
+    # from synth.seeded_init_ (a function of each parameter's NAME, so the drop-in model can rebuild them on the GPU
+    # box); inputs from seeded generators.  Stored: loss, pos_num, per-parameter gradient norms, a strided gradient sample.
+    def ref_model_step(ins_weight, seed):
+        torch.manual_seed(seed)
+        m = rpix.PixPro(rresnet.resnet50, pixpro_args(pixpro_ins_loss_weight=ins_weight))
+        for mod in list(m.modules()):   # SURVEY 8c shim 2: SyncBatchNorm has no CPU forward
+            for cname, child in list(mod.named_children()):
+                if isinstance(child, torch.nn.SyncBatchNorm):
+                    bn = torch.nn.BatchNorm2d(child.num_features, child.eps, child.momentum, child.affine, child.track_running_stats)
+                    bn.load_state_dict(child.state_dict())
+                    setattr(mod, cname, bn)
+        synth.seeded_init_(m, seed)
+        m.train()
+        gen = torch.Generator().manual_seed(seed)
+        im1 = torch.randn(4, 3, 224, 224, generator=gen)
+        im2 = torch.randn(4, 3, 224, 224, generator=gen)
+        c1, c2 = synth.crop_coords(4, seed=seed + 1), synth.crop_coords(4, seed=seed + 2)
+        loss, ((pn1, _), (pn2, _)) = m(im1, im2, c1, c2, is_update_momentum=False)
+        loss.backward()
+        names = [n_ for n_, p_ in m.named_parameters() if p_.grad is not None]
+        gn = np.array([float(dict(m.named_parameters())[n_].grad.double().norm()) for n_ in names])
+        sample = np.concatenate([dict(m.named_parameters())[n_].grad.flatten()[::997][:8].numpy() for n_ in names[:40]])
+        return dict(seed=np.int64(seed), ins_weight=np.float64(ins_weight), loss=np.float64(loss.item()), pos_num_1=pn1.numpy(),
+                    pos_num_2=pn2.numpy(), grad_names=np.array(names), grad_norms=gn, grad_sample=sample)
+
+    for tag, insw in [("cfg0", 0.0), ("cfg0_ins", 1.0)]:
+        g = ref_model_step(insw, 90)
+        rep.rows.append((f"a10/a12 reference model step {tag}", f"loss {float(g['loss']):.6f}, pos_num {g['pos_num_1'].tolist()}, "
+                         f"{len(g['grad_names'])} gradient tensors"))
+        gold[f"model_{tag}"] = g
 
     # ---------------- §8(f) rank 1: EMA of the key branch, LARS + SGD ----------------
     # (the reference's own contrast/lars.py, loaded by path: the package import would pull in termcolor)

@@ -155,20 +155,24 @@ class PixPro(BaseModel):
             p_k.data.copy_(p_q.data)
             p_k.requires_grad = False
 
-    @torch.no_grad()
-    def _momentum_update_key_encoder(self):
-        """EMA of the key branch with the cosine momentum schedule (PixPro.py:322-337)."""
+    def _next_momentum(self):
+        """Cosine momentum schedule (PixPro.py:326-327): value for this step; advances the step counter."""
         m = 1. - (1. - self.pixpro_momentum) * (np.cos(np.pi * self.k / self.K) + 1) / 2.
         self.k = self.k + 1
+        return m
+
+    @torch.no_grad()
+    def _momentum_update_key_encoder(self):
+        """EMA of the key branch with the cosine momentum schedule (PixPro.py:322-337): every parameter pair in ONE
+        launch (pp_ema_update).  CUDA only, like the rest of the path: a module kept on the host raises
+        PixProB200Error (construction and state_dict handling work on the host; stepping does not)."""
+        m = self._next_momentum()
         pairs = [(self.encoder, self.encoder_k), (self.projector, self.projector_k)]
         if self.pixpro_ins_loss_weight > 0.:
             pairs.append((self.projector_instance, self.projector_instance_k))
-        qk = [(p_q.data, p_k.data) for online, momentum in pairs for p_q, p_k in zip(online.parameters(), momentum.parameters())]
-        if qk and all(q.is_cuda and k.is_cuda and q.dtype == torch.float32 and q.is_contiguous() and k.is_contiguous() for q, k in qk):
-            _optim.ema_update(qk, m, cache_key=id(self))  # all parameters in one launch (pp_ema_update)
-        else:  # module kept on the host (construction-time checks, CPU unit tests): the reference's own loop
-            for p_q, p_k in qk:
-                p_k.copy_(p_k * m + p_q * (1. - m))
+        qk = [(p_q.data if p_q.is_contiguous() else p_q.data.contiguous(), p_k.data)
+              for online, momentum in pairs for p_q, p_k in zip(online.parameters(), momentum.parameters())]
+        _optim.ema_update(qk, m, cache_key=id(self))  # validates device / dtype / layout and raises; no fallback
 
     def _momentum_branch(self, im_1, im_2):
         proj_1_ng = F.normalize(self.projector_k(self.encoder_k(im_1)), dim=1)

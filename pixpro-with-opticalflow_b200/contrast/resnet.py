@@ -3,7 +3,8 @@
 with the same state_dict keys as the reference (contrast/resnet.py): conv1, bn1,
 layer{1..4}.{i}.conv{1,2,3} / bn{1,2,3} / downsample.{0,1}.  Stride sits on the 3x3 conv,
 He-normal conv init, unit BN, zero-gamma on each block's last BN (contrast/resnet.py:155-173).
-Only the heads PixPro uses ('early_return', 'pass', 'multi_layer') are provided."""
+Only the feature-map heads ('early_return' — what PixPro uses — and 'multi_layer') are provided; every other
+head and every non-default architecture keyword of the reference's ResNet raises."""
 import math
 
 import torch.nn as nn
@@ -51,10 +52,23 @@ class Bottleneck(nn.Module):
 
 
 class ResNet(nn.Module):
-    def __init__(self, block, layers, in_channel=3, low_dim=128, head_type='early_return', **unused):
+    # keyword arguments of the reference's ResNet (contrast/resnet.py) that select architectures outside the published
+    # runs; accepted only at their default values — anything else raises instead of silently building a plain ResNet
+    _UNSUPPORTED_DEFAULTS = dict(width=1, groups=1, width_per_group=64, deep_stem=False, avg_down=False, layer4_dilation=1,
+                                 mid_dim=1024, low_dim=128)  # mid_dim / low_dim only size the pooled heads: ignored
+
+    def __init__(self, block, layers, in_channel=3, head_type='early_return', **kw):
         super().__init__()
-        if head_type not in ('pass', 'early_return', 'multi_layer'):
-            raise NotImplementedError(f"head_type {head_type!r}: only the feature-map heads are in scope")
+        for k, v in kw.items():
+            if k not in self._UNSUPPORTED_DEFAULTS:
+                raise TypeError(f"ResNet: unexpected keyword argument {k!r}")
+            if v != self._UNSUPPORTED_DEFAULTS[k] and k not in ('low_dim', 'mid_dim'):
+                raise NotImplementedError(f"ResNet: {k}={v!r} is outside the pixel-pretext scope (only the plain ResNet of the "
+                                          "published runs is provided; the backbone stays on PyTorch/cuDNN)")
+        if head_type not in ('early_return', 'multi_layer'):
+            raise NotImplementedError(f"head_type {head_type!r}: only the feature-map heads 'early_return' (PixPro) and "
+                                      "'multi_layer' are provided; the reference's pooled heads ('pass', 'mlp_head', "
+                                      "'linear_head') belong to its linear-eval tooling, which is out of scope")
         self.head_type = head_type
         self.inplanes = 64
         self.conv1 = nn.Conv2d(in_channel, 64, 7, 2, 3, bias=False)

@@ -303,8 +303,7 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
 // fit).  Taps outside the frame are TMA zero fill (= grid_sample's zero padding); a pixel whose
 // footprint misses the box reads global memory in line.  Arithmetic = chain_kernel<false,false>.
 // grid = (W / TW, H / TH, B * ndir); block = 256.
-// PIXPRO_B200_CHAINBOX: 0 = gather kernels only, 1 (default) = TMA-staged dense chain where it pays,
-// 2 = also the fused x8-up-sampling chain in pp_flow_stage
+// PIXPRO_B200_CHAINBOX: 0 = gather kernels only, 1 (default) = TMA-staged dense chain where it pays
 static int chainbox_mode() {
     static const int m = [] { const char* e = getenv("PIXPRO_B200_CHAINBOX"); return e ? atoi(e) : 1; }();
     return m;
@@ -326,13 +325,9 @@ struct ChainBoxArgs {
     int n, H, W, ndir;
     float half_w, half_h;
     Div<DM_FAST> dw, dh;
-    // UP variant: links are LOW-RES [2,h,w] fields (strides in floats), up-sampled x8 into the box on the fly
-    int64_t lo_stride_n, lo_stride_b;
-    int h, w;
-    float rh, rw;
 };
 
-template <bool UP, int TW, int TH, int BW, int BH, int MINB>
+template <int TW, int TH, int BW, int BH, int MINB>
 __global__ void __launch_bounds__(256, MINB) chainbox_kernel(const __grid_constant__ CUtensorMap tm0,
                                                              const __grid_constant__ CUtensorMap tm1, ChainBoxArgs a) {
     constexpr int NX = TW / 32, NR = TH / 8;
@@ -341,8 +336,6 @@ __global__ void __launch_bounds__(256, MINB) chainbox_kernel(const __grid_consta
     __shared__ uint64_t full;
     __shared__ int bb[4];  // min x0, max x0, min y0, max y0 of the taps that touch the frame
     __shared__ int2 origin;
-    constexpr int TR = BH / 8 + 3;  // low-res rows a BH-row box can touch (scale < 1/8), +1 slack
-    float* Tb = reinterpret_cast<float*>(fbt_smem + 2 * BW * BH * 4);  // UP: [2][TR][BW] horizontally interpolated rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = a.W, H = a.H, HW = H * W;
     const int dir = a.ndir == 2 ? (blockIdx.z & 1) : 0;
@@ -395,61 +388,7 @@ __global__ void __launch_bounds__(256, MINB) chainbox_kernel(const __grid_consta
         __syncthreads();  // also: every thread is done reading the previous link's box
         const float* lp = nullptr;
         int2 o;
-        if (UP) {
-            // ---- box <- 8 * bilinear x8 of the low-res link, ATen's arithmetic (UpSample.cuh), separable:
-            // T(r, X) = fma(l0x, L[r][i0x], l1x * L[r][i1x]) once per low-res row and column, then
-            // value(Y, X) = 8 * fma(l0y, T(i0y, X), l1y * T(i1y, X)).  Cells outside the frame are 0.
-            const int bx0 = tap_origin(funkey(bb[0]), a.dw, a.half_w), bx1 = tap_origin(funkey(bb[1]), a.dw, a.half_w);
-            const int by0 = tap_origin(funkey(bb[2]), a.dh, a.half_h), by1 = tap_origin(funkey(bb[3]), a.dh, a.half_h);
-            const int ox = bx0 - (BW - (bx1 + 2 - bx0)) / 2, oy = by0 - (BH - (by1 + 2 - by0)) / 2;
-            o = make_int2(ox, oy);
-            __syncthreads();  // everyone has read bb
-            if (threadIdx.x == 0) { bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN; }
-            const float* lo = (dir ? a.links[1] : a.links[0]) + b * a.lo_stride_b + i * a.lo_stride_n;
-            const int hw = a.h * a.w;
-            const int ya = max(oy, 0), yb = min(oy + BH - 1, H - 1);
-            const int r_lo = axis_tap(ya, a.rh, a.h).i0;
-            const int nrow = ya <= yb ? axis_tap(yb, a.rh, a.h).i1 - r_lo + 1 : 0;
-            F2* Tp = reinterpret_cast<F2*>(Tb);  // [TR][BW] of (x, y) channel pairs
-            constexpr int RG = (256 + BW - 1) / BW;  // row groups: one column per thread
-            for (int e = threadIdx.x; e < BW * RG; e += 256) {
-                const int c = e % BW, rg = e / BW, X = ox + c;
-                const bool xin = X >= 0 && X < W;
-                const AxisTap tx = axis_tap(xin ? X : 0, a.rw, a.w);
-                const F2 l0 = pk1(tx.l0), l1 = pk1(tx.l1);
-                for (int r = rg; r < nrow; r += RG) {
-                    const float* row = lo + (r_lo + r) * a.w;
-                    F2 v;
-                    v.v = 0ull;  // columns outside the frame hold zeros: the vertical pass needs no column test
-                    if (xin) v = fma2(l0, pk(__ldg(row + tx.i0), __ldg(row + hw + tx.i0)), mul2(l1, pk(__ldg(row + tx.i1), __ldg(row + hw + tx.i1))));
-                    Tp[r * BW + c] = v;
-                }
-            }
-            __syncthreads();
-            float* box = reinterpret_cast<float*>(fbt_smem);
-            const F2 eight2 = pk1(8.0f);
-            for (int y = warp; y < BH; y += 8) {
-                const int Y = oy + y;
-                float* bxr = box + y * BW + lane;
-                if (Y >= 0 && Y < H) {  // warp-uniform
-                    const AxisTap ty = axis_tap(Y, a.rh, a.h);
-                    const F2* t0 = Tp + (ty.i0 - r_lo) * BW + lane;
-                    const F2* t1 = Tp + (ty.i1 - r_lo) * BW + lane;
-                    const F2 l0 = pk1(ty.l0), l1 = pk1(ty.l1);
-#pragma unroll
-                    for (int c = 0; c < BW; c += 32) {
-                        float vx, vy;
-                        unpk(mul2(eight2, fma2(l0, t0[c], mul2(l1, t1[c]))), vx, vy);
-                        bxr[c] = vx;
-                        bxr[BW * BH + c] = vy;
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < BW; c += 32) { bxr[c] = 0.0f; bxr[BW * BH + c] = 0.0f; }
-                }
-            }
-            __syncthreads();
-        } else {
+        {
             if (threadIdx.x == 0) {
                 const int bx0 = tap_origin(funkey(bb[0]), a.dw, a.half_w), bx1 = tap_origin(funkey(bb[1]), a.dw, a.half_w);
                 const int by0 = tap_origin(funkey(bb[2]), a.dh, a.half_h), by1 = tap_origin(funkey(bb[3]), a.dh, a.half_h);
@@ -498,19 +437,11 @@ __global__ void __launch_bounds__(256, MINB) chainbox_kernel(const __grid_consta
                             const bool x0in = x0 >= 0, x1in = x0 + 1 < W, y0in = y0 >= 0, y1in = y0 + 1 < H;
 #pragma unroll
                             for (int u = 0; u < 8; u++) t[p][u] = 0.0f;
-                            if (UP) {
-                                const UpLink L{(dir ? a.links[1] : a.links[0]) + b * a.lo_stride_b + i * a.lo_stride_n, a.h, a.w, a.rh, a.rw};
-                                if (x0in && y0in) { const float2 v = L.value(y0, x0); t[p][0] = v.x; t[p][4] = v.y; }
-                                if (x1in && y0in) { const float2 v = L.value(y0, x0 + 1); t[p][1] = v.x; t[p][5] = v.y; }
-                                if (x0in && y1in) { const float2 v = L.value(y0 + 1, x0); t[p][2] = v.x; t[p][6] = v.y; }
-                                if (x1in && y1in) { const float2 v = L.value(y0 + 1, x0 + 1); t[p][3] = v.x; t[p][7] = v.y; }
-                            } else {
-                                const float* g = lp + y0 * W + x0;
-                                if (x0in && y0in) { t[p][0] = __ldg(g); t[p][4] = __ldg(g + HW); }
-                                if (x1in && y0in) { t[p][1] = __ldg(g + 1); t[p][5] = __ldg(g + HW + 1); }
-                                if (x0in && y1in) { t[p][2] = __ldg(g + W); t[p][6] = __ldg(g + HW + W); }
-                                if (x1in && y1in) { t[p][3] = __ldg(g + W + 1); t[p][7] = __ldg(g + HW + W + 1); }
-                            }
+                            const float* g = lp + y0 * W + x0;
+                            if (x0in && y0in) { t[p][0] = __ldg(g); t[p][4] = __ldg(g + HW); }
+                            if (x1in && y0in) { t[p][1] = __ldg(g + 1); t[p][5] = __ldg(g + HW + 1); }
+                            if (x0in && y1in) { t[p][2] = __ldg(g + W); t[p][6] = __ldg(g + HW + W); }
+                            if (x1in && y1in) { t[p][3] = __ldg(g + W + 1); t[p][7] = __ldg(g + HW + W + 1); }
                         }
                 }
                 const F2 xw2 = pk(xws[0], xws[1]), yn2 = pk(yns[0], yns[1]);
@@ -631,11 +562,11 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
     return -1;
 }
 
-template <bool UP, int TW, int TH, int BW, int BH, int MINB>
+template <int TW, int TH, int BW, int BH, int MINB>
 static int launch_chain_cfg(const ChainBoxArgs& a, int64_t B, const float* base0, const float* base1, int64_t planes0,
                             int64_t planes1, cudaStream_t st) {
-    auto kern = chainbox_kernel<UP, TW, TH, BW, BH, MINB>;
-    constexpr int smem = 2 * BW * BH * 4 + (UP ? 2 * (BH / 8 + 3) * BW * 4 : 0);
+    auto kern = chainbox_kernel<TW, TH, BW, BH, MINB>;
+    constexpr int smem = 2 * BW * BH * 4;
     static unsigned long long opted = 0;  // one bit per device
     if (a.W % TW != 0 || a.H % TH != 0) return -1;
     if (smem_opt_in(kern, smem, opted) != cudaSuccess) {
@@ -644,14 +575,14 @@ static int launch_chain_cfg(const ChainBoxArgs& a, int64_t B, const float* base0
     }
     CUtensorMap tm0, tm1;
     memset(&tm0, 0, sizeof(tm0));
-    if (!UP && !make_map(&tm0, base0, planes0, a.H, a.W, BW, BH)) return -1;
-    if (!UP && a.ndir == 2) {
+    if (!make_map(&tm0, base0, planes0, a.H, a.W, BW, BH)) return -1;
+    if (a.ndir == 2) {
         if (!make_map(&tm1, base1, planes1, a.H, a.W, BW, BH)) return -1;
     } else {
         tm1 = tm0;
     }
     dim3 grid(a.W / TW, a.H / TH, (unsigned)(B * a.ndir));
-    PP_LAUNCH(UP ? "chain_up_box" : "chain_dense", st, (kern<<<grid, 256, smem, st>>>(tm0, tm1, a)));
+    PP_LAUNCH("chain_dense", st, (kern<<<grid, 256, smem, st>>>(tm0, tm1, a)));
     return check_launch("chainbox_kernel");
 }
 
@@ -673,31 +604,7 @@ static int launch_chain_box(const float* l0, const float* l1, float* o0, float* 
     a.dw = make_div<DM_FAST>((float)(W - 1)); a.dh = make_div<DM_FAST>((float)(H - 1));
     // planes addressable from each base: the last link of the last sample ends at this plane
     const int64_t planes = (B - 1) * a.plane_b + (int64_t)(n - 1) * a.plane_n + 2;
-    return launch_chain_cfg<false, 64, 48, 96, 72, 4>(a, B, l0, l1, planes, planes, st);
-}
-
-// The fused up-sampling chain measures on par with the chunked scratch path (3.9 vs 4.0 ms at B=64, n=5) but worse
-// end to end, so it is opt-in (PIXPRO_B200_CHAINBOX=2) until its box fill is cheaper.
-static bool chain_up_box_applicable(int n, int64_t B, int ndir, int h, int w) {
-    const int H = 8 * h, W = 8 * w;
-    return chainbox_mode() >= 2 && n >= 2 && W >= 64 && H < 32768 && W < 32768 && B * ndir <= 65535 && W % 64 == 0 && H % 48 == 0;
-}
-
-// Chain of n > 1 LOW-RES links with the x8 up-sampling fused in (no scratch, whole batch in one launch);
-// -1 = not applicable.
-static int launch_chain_up_box(const float* l0, const float* l1, float* o0, float* o1, int ndir, int n, int64_t B, int h, int w,
-                               int64_t stride_n, int64_t stride_b, cudaStream_t st) {
-    const int H = 8 * h, W = 8 * w;
-    if (!chain_up_box_applicable(n, B, ndir, h, w)) return -1;
-    ChainBoxArgs a;
-    memset(&a, 0, sizeof(a));
-    a.links[0] = l0; a.links[1] = l1; a.out[0] = o0; a.out[1] = o1;
-    a.n = n; a.H = H; a.W = W; a.ndir = ndir;
-    a.half_w = (float)(W - 1) / 2.0f; a.half_h = (float)(H - 1) / 2.0f;
-    a.dw = make_div<DM_FAST>((float)(W - 1)); a.dh = make_div<DM_FAST>((float)(H - 1));
-    a.lo_stride_n = stride_n; a.lo_stride_b = stride_b; a.h = h; a.w = w;
-    a.rh = up_scale(h, H); a.rw = up_scale(w, W);
-    return launch_chain_cfg<true, 64, 48, 96, 72, 3>(a, B, nullptr, nullptr, 0, 0, st);
+    return launch_chain_cfg<64, 48, 96, 72, 4>(a, B, l0, l1, planes, planes, st);
 }
 
 }  // namespace fbt

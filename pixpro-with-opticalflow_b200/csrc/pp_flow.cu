@@ -619,6 +619,7 @@ __global__ void __launch_bounds__(256) fbmask4p_kernel(FbArgs<DM_FAST> a) {
 
 }  // namespace pp
 #include "pp_fbtile.cuh"
+#include "pp_chainup.cuh"
 namespace pp {
 
 // a11 calc_mask_ratio: one block per sample, integer count of zeros (exact), one division.
@@ -660,8 +661,8 @@ static int launch_chain_dm(const float* l0, const float* l1, float* o0, float* o
         return check_launch("upchain1_kernel");
     }
     if constexpr (DM == DM_FAST) {
-        if (up && n > 1 && !is_norm) {  // x8 up-sampling fused into the box-staged chain; -1 = not applicable
-            const int rc = fbt::launch_chain_up_box(l0, l1, o0, o1, ndir, n, B, h, w, stride_n, stride_b, st);
+        if (up && n > 1 && !is_norm) {  // x8 up-sampling fused into the chain, no scratch (pp_chainup.cuh); -1 = not applicable
+            const int rc = cup::launch(l0, l1, o0, o1, ndir, n, B, h, w, stride_n, stride_b, st);
             if (rc != -1) return rc;
         }
         if (!up && n > 1 && !is_norm) {  // TMA-staged dense chain (pp_fbtile.cuh); -1 = not applicable
@@ -953,49 +954,11 @@ int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int 
                      (cudaStream_t)stream);
 }
 
-// Scratch for the chained (n > 1) flow_up path: the up-sampled links of `chunk` samples, both
-// directions.  Measured on a B200 (n=5, B=64, 720x1280; step time of bench.py --n-frames 6): 80 MB (one sample per
-// chunk, L2-resident) 3.54 ms, 160 MB 3.67, 320 MB 3.19, 640 MB 3.09, 1.3-5 GB 3.10 — chunks of 8 samples make every
-// launch large enough for the TMA-staged chain kernel (>= 1200 tiles) and cut the launch count from 267 to 43; keeping
-// the scratch inside the L2 matters less than that.  PIXPRO_B200_CHAINSCRATCH_MB overrides (A/B runs).
-static int64_t chain_scratch_target() {
-    static const int64_t t = [] { const char* e = getenv("PIXPRO_B200_CHAINSCRATCH_MB"); return (int64_t)(e ? atoi(e) : 640) << 20; }();
-    return t;
-}
-static int64_t chain_chunk_bytes(int n, int h, int w) { return (int64_t)2 * n * 2 * (8 * h) * (8 * w) * sizeof(float); }
-
-// One helper stream + fork/join events per device for pp_flow_stage (the C ABI is called by one host thread per
-// process; created lazily, never destroyed).
-struct FlowSideStream {
-    cudaStream_t stream;
-    cudaEvent_t fork, join;
-};
-static FlowSideStream* flow_side_stream() {
-    static FlowSideStream cache[64];
-    static bool made[64] = {false};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!made[dev]) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        (void)cs;
-        if (cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        made[dev] = true;
-    }
-    return &cache[dev];
-}
-
+// The n > 1 flow_up path needs no scratch since round 2 (the x8 up-sampling is fused into the chain kernel,
+// pp_chainup.cuh); the entry stays in the ABI and returns 0.
 int64_t pp_flow_stage_workspace(int64_t B, int n, int h, int w, int flow_up) {
-    if (!flow_up || n <= 1 || B <= 0) return 0;
-    const int64_t per = chain_chunk_bytes(n, h, w);
-    int64_t chunk = chain_scratch_target() / per;
-    if (chunk < 1) chunk = 1;
-    if (chunk > B) chunk = B;
-    return chunk * per;
+    (void)B; (void)n; (void)h; (void)w; (void)flow_up;
+    return 0;
 }
 
 int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, int h, int w, int flow_up, int use_mask,
@@ -1011,52 +974,10 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
     int H = flow_up ? 8 * h : h, W = flow_up ? 8 * w : w;
     int64_t link = 2 * (int64_t)h * w;  // loader layout [B,n,2,h,w]
     int rc;
-    const int64_t per = chain_chunk_bytes(n, h, w);
-    const bool fused_up_chain = flow_up && n > 1 && !is_norm && div_mode != PP_DIV_RCP && div_certified((float)(W - 1)) &&
-                                div_certified((float)(H - 1)) && fbt::chain_up_box_applicable(n, B, 2, h, w);
-    if (!fused_up_chain && flow_up && n > 1 && !is_norm && workspace && workspace_bytes >= per) {
-        // Chained links: evaluating the x8 up-sampling inside every one of the 4 taps of every chain
-        // step costs ~1100 instructions per pixel (7.5 ms at B=64, n=5: profiles/r01_*).  Instead the
-        // links of a chunk of samples are up-sampled ONCE by the strip kernel into an L2-sized scratch
-        // and chained from there by the dense-link kernel; the scratch is reused chunk after chunk, so
-        // it lives in L2 and the composite output stays the only compulsory HBM write.  Values are
-        // identical (the reference materialises the same up-sampled links).
-        int64_t chunk = workspace_bytes / per;
-        if (chunk > B) chunk = B;
-        const int64_t HW2 = 2 * (int64_t)H * W;
-        float* s0 = (float*)workspace;
-        float* s1 = s0 + chunk * n * HW2;
-        // The two directions are independent and have their own scratch halves: the backward direction runs on a
-        // side stream, so that its (HBM/L2-write-bound) up-sampling overlaps the (L1-bound) dense chain of the
-        // forward direction and vice versa.  Fork/join by events: capturable into a CUDA graph.
-        FlowSideStream* ss = flow_side_stream();
-        const bool two = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess &&
-                         cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
-        cudaStream_t st1 = two ? ss->stream : st;
-        for (int64_t b0 = 0; b0 < B; b0 += chunk) {
-            const int64_t s = (B - b0 < chunk) ? (B - b0) : chunk;
-            for (int dir = 0; dir < 2; dir++) {
-                const float* lo = (dir ? lo_bwd : lo_fwd) + b0 * n * link;
-                float* sc = dir ? s1 : s0;
-                float* out = (dir ? flow_bwd : flow_fwd) + b0 * HW2;
-                cudaStream_t sd = dir ? st1 : st;
-                // (1) every link of the chunk is one "sample" of the n==1 up-sampling kernel
-                rc = launch_chain(lo, nullptr, sc, nullptr, 1, 1, s * n, H, W, h, w, true, link, link, 0, div_mode, sd);
-                if (rc) return rc;
-                // (2) chain the dense links
-                rc = launch_chain(sc, nullptr, out, nullptr, 1, n, s, H, W, 0, 0, false, HW2, n * HW2, 0, div_mode, sd);
-                if (rc) return rc;
-            }
-        }
-        if (two) {
-            PP_REQUIRE(cudaEventRecord(ss->join, ss->stream) == cudaSuccess && cudaStreamWaitEvent(st, ss->join, 0) == cudaSuccess,
-                       "pp_flow_stage: joining the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
-        }
-    } else {
-        rc = launch_chain(lo_fwd, lo_bwd, flow_fwd, flow_bwd, 2, n, B, H, W, h, w, flow_up != 0, link, (int64_t)n * link,
-                          is_norm, div_mode, st);
-        if (rc) return rc;
-    }
+    (void)workspace; (void)workspace_bytes;
+    rc = launch_chain(lo_fwd, lo_bwd, flow_fwd, flow_bwd, 2, n, B, H, W, h, w, flow_up != 0, link, (int64_t)n * link, is_norm,
+                      div_mode, st);
+    if (rc) return rc;
     if (use_mask) {
         rc = launch_fb(flow_fwd, flow_bwd, mask_fwd, mask_bwd, nullptr, nullptr, 2, B, H, W, alpha_1, alpha_2, is_norm,
                        div_mode, st);
@@ -1101,6 +1022,16 @@ int64_t pp_fb_redo_count(int reset) {
     if (reset) {
         const unsigned long long z = 0;
         cudaMemcpyToSymbol(fbt::g_redo_pixels, &z, sizeof(z));
+    }
+    return (int64_t)v;
+}
+
+int64_t pp_chain_slow_count(int reset) {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, cup::g_slow_pixels, sizeof(v)) != cudaSuccess) return -1;
+    if (reset) {
+        const unsigned long long z = 0;
+        cudaMemcpyToSymbol(cup::g_slow_pixels, &z, sizeof(z));
     }
     return (int64_t)v;
 }

@@ -21,6 +21,7 @@ SIGNATURES = {
     "pp_last_error": (ctypes.c_char_p, []),
     "pp_launch_count": (_l, []),
     "pp_fb_redo_count": (_l, [_i]),
+    "pp_chain_slow_count": (_l, [_i]),
     "pp_profile_enable": (_i, [_i]),
     "pp_profile_num_kernels": (_i, []),
     "pp_profile_get": (_i, [_i, ctypes.c_char_p, _i, ctypes.POINTER(_l), ctypes.POINTER(_d)]),
@@ -98,6 +99,11 @@ def launch_count():
 def fb_redo_count(reset=False):
     """Pixels the TMA-staged FB-mask kernel recomputed from global memory (see pp_fb_redo_count)."""
     return int(lib().pp_fb_redo_count(int(bool(reset))))
+
+
+def chain_slow_count(reset=False):
+    """Pixel-links the fused up-sampling chain kernel evaluated on its direct (slow) path (see pp_chain_slow_count)."""
+    return int(lib().pp_chain_slow_count(int(bool(reset))))
 
 
 def profile_enable(on=True):

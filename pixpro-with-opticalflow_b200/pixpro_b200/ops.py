@@ -139,12 +139,11 @@ def forward_backward_consistency(flow_fwd, flow_bwd, alpha_1=0.01, alpha_2=0.5, 
     return c1, mask.view(torch.bool), cyc
 
 
-def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=False, use_workspace=True, out=None):
+def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=False, out=None):
     """Flow stage of contrast/util.py:175-248 (use_flow_file, not use_flow_frames), fused.
 
     lo_fwd/lo_bwd: loader layout [B,n,2,h,w].  Returns (flow_fwd, flow_bwd [B,2,H,W],
     mask_fwd, mask_bwd bool [B,H,W] or None when alpha_1/alpha_2 is None).
-    use_workspace=False forces the scratch-free chain kernel (same bits, slower for n > 1).
     out=(flow_fwd, flow_bwd, mask_fwd u8, mask_bwd u8): write into preallocated contiguous tensors
     (e.g. batch slices of larger buffers) instead of allocating."""
     f = _f32(lo_fwd, "lo_fwd")
@@ -165,7 +164,7 @@ def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=
         mf = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
         mb = torch.empty((B, H, W), device=f.device, dtype=torch.uint8) if use_mask else None
     L = _cabi.lib()
-    wsz = L.pp_flow_stage_workspace(B, n, h, w, int(flow_up)) if use_workspace else 0
+    wsz = L.pp_flow_stage_workspace(B, n, h, w, int(flow_up))  # 0: the fused chain kernel needs no scratch
     ws = torch.empty((wsz,), device=f.device, dtype=torch.uint8) if wsz else None
     with torch.cuda.device(f.device):
         _cabi.check(L.pp_flow_stage(_ptr(f), _ptr(b), B, n, h, w, int(flow_up), int(use_mask),

@@ -61,3 +61,31 @@ def features(batch, channels=256, grid=7, seed=1234):
     k1 = F.normalize(torch.randn(batch, channels, grid, grid, generator=g), dim=1)
     k2 = F.normalize(torch.randn(batch, channels, grid, grid, generator=g), dim=1)
     return feat1, feat2, k1, k2
+
+
+_MOMENTUM_TWINS = (("encoder_k.", "encoder."), ("projector_instance_k.", "projector_instance."), ("projector_k.", "projector."))
+
+
+def seeded_init_(module, seed=0):
+    """Deterministic, construction-order-independent parameter init: every parameter is drawn from a generator
+    seeded by (seed, crc32 of its state_dict name), so that two implementations with the same parameter names
+    (this package's PixPro and the reference's) hold bit-identical weights whatever order they build their layers
+    in.  Momentum-branch parameters (`*_k.`) use their online twin's name, i.e. start as copies (PixPro.py:280-287).
+    Conv / linear weights ~ N(0, 2/fan_in), norm weights ~ 1 + 0.1 N(0,1), biases ~ 0.1 N(0,1)."""
+    import zlib
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            key = name
+            for twin, online in _MOMENTUM_TWINS:
+                key = key.replace(twin, online)
+            g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7fffffff)
+            r = torch.randn(p.shape, generator=g, dtype=torch.float32)
+            if p.ndim >= 2:
+                fan_in = p[0].numel()
+                v = r * math.sqrt(2.0 / fan_in)
+            elif name.endswith("weight"):
+                v = 1.0 + 0.1 * r
+            else:
+                v = 0.1 * r
+            p.copy_(v.to(p.device))
+    return module

@@ -146,29 +146,36 @@ def test_regression_loss_golden(ops, tag):
 
 
 @pytest.mark.parametrize("tag", ["l1_p2_g7", "l0_p1_g7", "l1_p2_g14", "l0_p05_cv01", "l0_p3_g7"])
-def test_featprop_golden(ops, tag):
+@pytest.mark.parametrize("conv_impl", ["product", "cudnn"])
+def test_featprop_golden(ops, tag, conv_impl):
+    """PixPro.featprop + F.normalize against the reference module's own output and gradients.  `product`: the value
+    transform runs on this repo's conv (ops.conv1x1 — the tcgen05 3xTF32 kernel, or the PPM-fused path), i.e. the
+    reference-generated d_weight / d_bias goldens meet the product's conv; `cudnn`: torch.nn.Conv2d feeds the PPM."""
     g = load_golden("featprop_" + tag)
+    if conv_impl == "cudnn" and "weight" not in g:
+        pytest.skip("identity value transform: nothing to switch")
     feat = cu(g["feat"]).requires_grad_(True)
-    conv = None
+    w = b = None
     if "weight" in g:
-        conv = torch.nn.Conv2d(256, 256, 1).to(DEV)
-        with torch.no_grad():
-            conv.weight.copy_(cu(g["weight"]))
-            conv.bias.copy_(cu(g["bias"]))
-    # the 1x1 value transform stays on cuDNN: keep it in true fp32 for the 1e-5 comparison
+        w, b = cu(g["weight"]).requires_grad_(True), cu(g["bias"]).requires_grad_(True)
     prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False  # true fp32 for the 1e-5 comparison
     try:
-        val = conv(feat) if conv is not None else feat
+        if w is None:
+            val = feat
+        elif conv_impl == "product":
+            val = ops.conv1x1(feat, w, b)
+        else:
+            val = torch.nn.functional.conv2d(feat, w, b)
         out = ops.ppm(feat, val, float(g["gamma"]), float(g["clamp"]), final_norm=True)
         out.backward(cu(g["gout"]))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
     assert rel_err(npy(out), g["out"]) < TOL
     assert rel_err(npy(feat.grad), g["d_feat"]) < 2e-5
-    if "weight" in g:
-        assert rel_err(npy(conv.weight.grad), g["d_weight"]) < 2e-5
-        assert rel_err(npy(conv.bias.grad), g["d_bias"]) < 2e-5
+    if w is not None:
+        assert rel_err(npy(w.grad), g["d_weight"]) < 2e-5
+        assert rel_err(npy(b.grad), g["d_bias"]) < 2e-5
 
 
 # --------------------------------------------------------------------------- vs the oracle, seeded
@@ -226,9 +233,21 @@ def test_concat_flow_tma_staged_chain_vs_oracle(ops, orc, synth):
     assert_bits_equal(npy(ops.concat_flow(up)), want, "concat_flow (TMA-staged)")
 
 
-def test_fused_upsampling_chain_opt_in_vs_default(synth):
-    """PIXPRO_B200_CHAINBOX=2 (fused x8 up-sampling + chain in one launch) is opt-in; it must give the
-    same bits as the default chunked path.  Runs in a subprocess: the mode is read once per process."""
+def test_fused_upsampling_chain_equals_materialised_route(ops, synth):
+    """n > 1 with flow_up: the fused x8-up-sampling chain kernel (pp_chainup.cuh, no full-res scratch) gives the
+    bits of the reference's own route — materialise every up-sampled link (upflow8), then chain the dense links."""
+    f, b = synth.flow_fields(3, 5, seed=11)
+    f, b = f.to(DEV), b.to(DEV)
+    ff, fb, _, _ = ops.flow_stage(f, b)
+    for lo, got in ((f, ff), (b, fb)):
+        up = ops.upflow8(lo.reshape(-1, 2, 90, 160)).reshape(3, 5, 2, 720, 1280).permute(1, 0, 2, 3, 4)
+        assert torch.equal(ops.concat_flow(up), got)
+
+
+@pytest.mark.parametrize("variant", ["2", "3", "4"])
+def test_fused_upsampling_chain_tile_variants(variant):
+    """The other tile shapes of the fused chain kernel (PIXPRO_B200_CHAINUP) give the default's bits.
+    Runs in a subprocess: the variant is read once per process."""
     import subprocess
     import sys
     code = (
@@ -238,12 +257,31 @@ def test_fused_upsampling_chain_opt_in_vs_default(synth):
         "print(hashlib.sha256(b''.join(t.cpu().numpy().tobytes() for t in o)).hexdigest())\n"
     ) % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pixpro-with-opticalflow_b200")
     outs = []
-    for mode in ("1", "2"):
-        env = dict(os.environ, PIXPRO_B200_CHAINBOX=mode)
+    for mode in ("1", variant):
+        env = dict(os.environ, PIXPRO_B200_CHAINUP=mode)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1]
+
+
+def test_fused_upsampling_chain_rough_field_and_ragged_frame_vs_oracle(ops, orc, synth):
+    """(a) an incoherent link makes footprints miss the staged region: those pixels take the direct path and the
+    result is still the oracle's; (b) a frame that is no multiple of the 64x48 tile (overhanging tiles) and whose
+    flows push points out of the frame."""
+    f, b = synth.flow_fields(2, 3, seed=23)
+    g = torch.Generator().manual_seed(5)
+    f[:, 1] += torch.randn(f[:, 1].shape, generator=g) * 0.8
+    b[:, 0] += torch.randn(b[:, 0].shape, generator=g) * 2.5
+    got = ops.flow_stage(f.to(DEV), b.to(DEV))
+    want = orc.flow_stage(npy(f), npy(b))
+    for name, g_, w_ in zip(["flow_fwd", "flow_bwd", "mask_fwd", "mask_bwd"], got, want):
+        assert_bits_equal(npy(g_), w_, "rough " + name)
+    f, b = synth.flow_fields(3, 4, h=11, w=13, seed=29, coarse=(3, 4), magnitude=2.5)
+    got = ops.flow_stage(f.to(DEV), b.to(DEV))
+    want = orc.flow_stage(npy(f), npy(b))
+    for name, g_, w_ in zip(["flow_fwd", "flow_bwd", "mask_fwd", "mask_bwd"], got, want):
+        assert_bits_equal(npy(g_), w_, "ragged " + name)
 
 
 def test_flow_stage_empty_batch(ops):
@@ -476,17 +514,6 @@ def test_rcp_mode_matches_oracle_rcp_mode(ops, orc, synth):
     assert (ieee[0] != want[0]).any()   # the two modes are genuinely different arithmetic
 
 
-def test_chunked_chain_equals_scratch_free_chain(ops, synth):
-    """n > 1: the L2-chunked path (up-sample a chunk of links once, chain from the dense scratch)
-    and the scratch-free kernel (x8 up-sampling evaluated inside every tap) give the same bits."""
-    f, b = synth.flow_fields(5, 5, seed=91)
-    f, b = f.to(DEV), b.to(DEV)
-    a_ = ops.flow_stage(f, b, use_workspace=True)
-    b_ = ops.flow_stage(f, b, use_workspace=False)
-    for x, y in zip(a_, b_):
-        assert torch.equal(x, y)
-
-
 # --------------------------------------------------------------------------- SURVEY §8(f) rank 1: optimizer side
 
 def test_ema_update_kernel_golden_and_ragged(orc):
@@ -564,3 +591,34 @@ def test_lars_mirror_matches_oracle_on_a_cuda_model(orc):
                     assert rel_err(npy(p), want) <= 1e-6
                 assert rel_err(npy(opt.state[p]["momentum_buffer"]), buf) <= 1e-6
     assert set(opt.state_dict().keys()) == {"state", "param_groups"}
+
+
+def test_lars_step_with_a_moving_learning_rate_rewrites_scalars_only(orc):
+    """the reference's scheduler changes lr every iteration.  That must not rebuild or re-validate the
+    pointer table (one rebuild for the whole run while no pointer moves; the scalar columns travel through the pinned
+    staging ring), and the steps must still match the oracle applied with each step's lr."""
+    from contrast.lars import LARS, add_weight_decay
+    torch.manual_seed(7)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.ReLU(), torch.nn.Conv2d(8, 40, 3)).to(DEV)
+    opt = LARS(torch.optim.SGD(add_weight_decay(net, 1e-4), lr=0.2, momentum=0.9), eps=1e-8, trust_coef=0.001)
+    state = {}
+    steps = 6
+    for step in range(steps):
+        for grp in opt.param_groups:
+            grp["lr"] = 0.2 * (1.0 - step / 10.0)          # what a scheduler does
+        opt.zero_grad(set_to_none=False)                   # gradients keep their storage: pointers do not move
+        net(torch.randn(4, 3, 12, 12, device=DEV)).square().mean().backward()
+        before = {p: (npy(p).copy(), npy(p.grad).copy()) for grp in opt.param_groups for p in grp["params"]}
+        opt.step()
+        for grp in opt.param_groups:
+            for p in grp["params"]:
+                p0, g0 = before[p]
+                want, buf, _ = orc.lars_sgd_step(p0, g0, state.get(p), grp["weight_decay"], grp["lr"], grp["momentum"],
+                                                 grp["dampening"], lars=not grp["ignore"], first=p not in state)
+                state[p] = buf
+                assert rel_err(npy(p), want) <= 1e-6, (step, grp["lr"])
+    ts = opt._fused.ts
+    # step 0 builds the table (momentum buffers do not exist yet: null pointers), step 1 rebuilds it once they do;
+    # every later step changes lr (and nothing else) and must only rewrite the scalar columns
+    assert ts.rebuilds <= 2, ts.rebuilds
+    assert ts.scalar_updates >= steps - 2, (ts.rebuilds, ts.scalar_updates)

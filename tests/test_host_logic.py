@@ -65,15 +65,15 @@ def test_bad_transform_layer_raises(gloo1):
 def test_momentum_schedule(gloo1):
     from contrast import resnet
     from contrast.models import PixPro
+    from pixpro_b200._cabi import PixProB200Error
     m = PixPro(resnet.resnet50, pixpro_args())
-    with torch.no_grad():
-        m.projector.linear2.bias.fill_(1.0)
-        m.projector_k.linear2.bias.fill_(0.0)
     m.k, m.K = 3, 10
     mom = 1. - (1. - 0.99) * (math.cos(math.pi * 3 / 10) + 1) / 2.
-    m._momentum_update_key_encoder()
-    assert m.k == 4
-    assert torch.allclose(m.projector_k.linear2.bias, torch.full((256,), 1.0 - mom), atol=1e-7)
+    assert m._next_momentum() == pytest.approx(mom, abs=1e-15)       # PixPro.py:326
+    assert m.k == 4                                                   # PixPro.py:327
+    # the update itself is a CUDA kernel: a module kept on the host raises instead of falling back to a torch loop
+    with pytest.raises(PixProB200Error):
+        m._momentum_update_key_encoder()
 
 
 def test_unpack_coords_conventions():
@@ -302,3 +302,16 @@ def test_profiles_index_names_existing_files():
     names -= {"bench.py", "_summary.txt"}  # the repo-root script and a suffix mentioned in passing
     missing = [n for n in names if "*" not in n and not os.path.exists(os.path.join(ROOT, "profiles", n))]
     assert not missing, missing
+
+
+def test_resnet_rejects_architectures_outside_the_scope():
+    """unsupported keyword arguments of the reference's ResNet must not be swallowed."""
+    from contrast import resnet
+    resnet.resnet50(head_type='early_return', low_dim=256)           # sizes a pooled head only: accepted
+    for kw in (dict(width=2), dict(deep_stem=True), dict(avg_down=True), dict(groups=32, width_per_group=4), dict(layer4_dilation=2)):
+        with pytest.raises(NotImplementedError):
+            resnet.resnet50(**kw)
+    with pytest.raises(NotImplementedError):
+        resnet.resnet50(head_type='pass')                            # the reference pools and flattens there: not provided
+    with pytest.raises(TypeError):
+        resnet.resnet50(no_such_option=1)
