@@ -218,6 +218,21 @@ PP_API int pp_lars_sgd_step(const PpMtTensor* table_dev, int ntensors, const int
  * entry exposes the bare GEMM for numerics tests and microbenchmarks.                        */
 PP_API int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* stream);
 
+/* ---- RAFT correlation volume, pyramid and lookup ----------------------------
+ * The reference's torch CorrBlock (contrast/flow/corr.py:12-60; its CUDA twin `alt_cuda_corr` is not shipped).
+ * pp_corr_volume : CorrBlock.corr, corr.py:52-60.  fmap1, fmap2 [B, D, h, w] -> corr [B, h*w, h*w]
+ *                  (= the reference's [B,h,w,1,h,w]); <f1[:,i], f2[:,j]> / sqrt(D), tcgen05 3xTF32 for h*w >= 128.
+ * pp_corr_pool   : one pyramid step, corr.py:26-28: avg_pool2d(2, stride 2) of `planes` planes [h,w] -> [h/2,w/2].
+ * pp_corr_lookup : CorrBlock.__call__, corr.py:30-50 + bilinear_sampler (flow/utils/utils.py:64-78).
+ *                  levels: HOST array of num_levels device pointers, level l = [B*h*w, h>>l, w>>l]; coords [B,2,h,w]
+ *                  (x, y in level-0 pixels) -> out [B, num_levels*(2r+1)^2, h, w], channel = l*(2r+1)^2 + i*(2r+1) + j with
+ *                  the reference's window convention (index i shifts x, j shifts y).  div_mode: PP_DIV_* of the
+ *                  tensor / python-scalar divisions in bilinear_sampler.                                        */
+PP_API int pp_corr_volume(const float* fmap1, const float* fmap2, int64_t B, int D, int h, int w, float* corr, void* stream);
+PP_API int pp_corr_pool(const float* in, int64_t planes, int h, int w, float* out, void* stream);
+PP_API int pp_corr_lookup(const float* const* levels, int num_levels, const float* coords, int64_t B, int h, int w, int radius,
+                          int div_mode, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,3 +335,38 @@ def lars_sgd_step(p, g, buf, wd, lr, mom, damp=0.0, lars=True, first=False, trus
     rate = L.orc_lars_sgd_step(pp_, gp, bp, p.size, float(wd), float(lr), float(mom), float(damp), int(lars), int(first),
                                float(trust), float(eps))
     return p, buf, float(rate)
+
+
+# ---------------------------------------------------------------- RAFT correlation
+
+def corr_volume(fmap1, fmap2):
+    """contrast/flow/corr.py:52-60.  fmap1, fmap2 [B,D,h,w] -> [B, h*w, h*w]."""
+    f1, p1 = _f(fmap1)
+    f2, p2 = _f(fmap2)
+    B, D, h, w = f1.shape
+    out, op = _out_f((B, h * w, h * w))
+    lib().orc_corr_volume(p1, p2, _L(B), _I(D), _I(h), _I(w), op)
+    return out
+
+
+def corr_pool(corr):
+    """contrast/flow/corr.py:26-28: avg_pool2d(2, stride 2) over the last two dims."""
+    c, cp = _f(corr)
+    h, w = c.shape[-2:]
+    planes = c.size // (h * w)
+    out, op = _out_f(tuple(c.shape[:-2]) + (h // 2, w // 2))
+    lib().orc_corr_pool(cp, _L(planes), _I(h), _I(w), op)
+    return out
+
+
+def corr_lookup(pyramid, coords, radius, div_mode=0):
+    """contrast/flow/corr.py:30-50.  pyramid: list of [B*h*w, 1, h>>l, w>>l]; coords [B,2,h,w] -> [B, L*(2r+1)^2, h, w]."""
+    import ctypes
+    coords, cp = _f(coords)
+    B, _, h, w = coords.shape
+    keep = [_f(p) for p in pyramid]
+    table = (ctypes.c_void_p * len(keep))(*[ctypes.cast(pp_, ctypes.c_void_p).value for _, pp_ in keep])
+    K = 2 * radius + 1
+    out, op = _out_f((B, len(keep) * K * K, h, w))
+    lib().orc_corr_lookup(table, _I(len(keep)), cp, _L(B), _I(h), _I(w), _I(radius), _I(div_mode), op)
+    return out

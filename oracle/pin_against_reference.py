@@ -110,11 +110,16 @@ def pixpro_args(**kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--only-corr", action="store_true", help="run only the RAFT CorrBlock section (fast) and write only its fixtures")
     opt = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     rutil, rflow, rpix, rresnet = import_reference()
     rep = Report()
     gold = {}
+    if opt.only_corr:
+        pin_corr_block(rep, gold)
+        finish(rep, gold, opt)
+        return
 
     # ---------------- a1 upflow8 ----------------
     fwd, bwd = synth.flow_fields(2, 3, h=18, w=32, seed=11)
@@ -359,6 +364,8 @@ def main():
                     idx += 1
         gold[f"apply_general_{tag}"] = g
 
+    pin_corr_block(rep, gold)
+
     # ---------------- a10 / a12 / cfg 0: the whole reference model, one fwd+bwd step on CPU ----------------
     # BASELINE configs[0]: PixPro ResNet-50, n_frames=1 (no flow), batch 4, 224x224 two-view crops, 7x7 grid.  Weights come
     # from synth.seeded_init_ (a function of each parameter's NAME, so the drop-in model can rebuild them on the GPU
@@ -433,6 +440,38 @@ def main():
             lg[f"p{i}_s{step}"] = want
     gold["lars_sgd"] = lg
 
+    finish(rep, gold, opt)
+
+
+def pin_corr_block(rep, gold):
+    """the reference's torch CorrBlock (contrast/flow/corr.py, loaded by path: the package import is
+    already done, this only avoids `alt_cuda_corr`'s try/except noise) against orc_corr_volume / _pool / _lookup."""
+    import importlib
+    rcorr = importlib.import_module("contrast.flow.corr")
+    for tag, B, D, h, w, L, r, spread in [("small", 2, 32, 6, 10, 3, 2, 3.0), ("raft_small", 1, 128, 16, 24, 4, 3, 6.0),
+                                          ("oob", 1, 16, 8, 8, 2, 4, 20.0)]:
+        g = torch.Generator().manual_seed(700 + h)
+        f1 = torch.randn(B, D, h, w, generator=g)
+        f2 = torch.randn(B, D, h, w, generator=g)
+        from contrast.flow.utils.utils import coords_grid
+        coords = coords_grid(B, h, w) + spread * torch.randn(B, 2, h, w, generator=g)
+        blk = rcorr.CorrBlock(f1, f2, num_levels=L, radius=r)
+        ref_out = blk(coords).numpy()
+        ref_pyr = [p.numpy() for p in blk.corr_pyramid]
+        vol = orc.corr_volume(f1.numpy(), f2.numpy())
+        rep.close(f"f4 corr volume {tag}", vol, ref_pyr[0].reshape(B, h * w, h * w), 1e-5)
+        # pyramid / lookup from the REFERENCE's level 0 (bit-exact stages are then checked bit-exactly)
+        pyr = [ref_pyr[0]]
+        for l in range(1, L):
+            pyr.append(orc.corr_pool(pyr[-1]))
+            rep.exact(f"f4 corr pyramid {tag} level {l}", pyr[-1], ref_pyr[l])
+        out = orc.corr_lookup(pyr, coords.numpy(), r)
+        rep.exact(f"f4 corr lookup {tag} (L={L}, r={r})", out, ref_out)
+        gold[f"corr_{tag}"] = dict(fmap1=f1.numpy(), fmap2=f2.numpy(), coords=coords.numpy(), num_levels=np.int64(L), radius=np.int64(r),
+                                   level0=ref_pyr[0], out=ref_out, **{f"level{l}_sha": np.array(sha(ref_pyr[l])) for l in range(1, L)})
+
+
+def finish(rep, gold, opt):
     width = max(len(r[0]) for r in rep.rows)
     for name, res in rep.rows:
         print(f"{name:<{width}}  {res}")

@@ -921,3 +921,71 @@ ORC_API float orc_lars_sgd_step(float* p, const float* g, float* buf, long n, do
     }
     return a;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* SURVEY 8(f) rank 4 — RAFT correlation volume, pyramid, lookup                         */
+/* contrast/flow/corr.py:12-60, contrast/flow/utils/utils.py:64-78                        */
+/* ------------------------------------------------------------------------------------ */
+
+/* corr.py:52-60: corr[b,i,j] = sum_d f1[b,d,i] f2[b,d,j] / sqrt(D).  torch.matmul accumulates in fp32 in an
+ * unspecified order; the sum is formed in double here (tolerance oracle), the division is the reference's fp32
+ * tensor / tensor division. */
+ORC_API void orc_corr_volume(const float* f1, const float* f2, long B, int D, int h, int w, float* out) {
+    const long P = (long)h * w;
+    const float s = sqrtf((float)D);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (long b = 0; b < B; b++)
+        for (long i = 0; i < P; i++) {
+            const float* a = f1 + b * D * P + i;
+            const float* c = f2 + b * D * P;
+            float* o = out + (b * P + i) * P;
+            for (long j = 0; j < P; j++) {
+                double acc = 0.0;
+                for (int d = 0; d < D; d++) acc += (double)a[d * P] * (double)c[d * P + j];
+                o[j] = (float)acc / s;
+            }
+        }
+}
+
+/* corr.py:26-28: F.avg_pool2d(corr, 2, stride=2): window summed row-major, divided by 4 (exact). */
+ORC_API void orc_corr_pool(const float* in, long planes, int h, int w, float* out) {
+    const int ho = h / 2, wo = w / 2;
+#pragma omp parallel for schedule(static)
+    for (long p = 0; p < planes; p++)
+        for (int y = 0; y < ho; y++)
+            for (int x = 0; x < wo; x++) {
+                const float* q = in + (p * h + 2 * y) * (long)w + 2 * x;
+                float s = q[0] + q[1];
+                s = s + q[w];
+                s = s + q[w + 1];
+                out[(p * ho + y) * (long)wo + x] = s * 0.25f;
+            }
+}
+
+/* corr.py:30-50 + utils.py:64-78.  levels[l]: [B*P, h>>l, w>>l]; coords [B,2,h,w]; out [B, L*K*K, h, w].
+ * delta = stack(meshgrid(dy, dx), -1) is added to (x, y): window index (i, j) shifts x by d[i] and y by d[j]. */
+ORC_API void orc_corr_lookup(const float* const* levels, int L, const float* coords, long B, int h, int w, int r, int div_mode,
+                             float* out) {
+    const long P = (long)h * w;
+    const int K = 2 * r + 1;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (long b = 0; b < B; b++)
+        for (long p = 0; p < P; p++) {
+            const float cx = coords[(b * 2) * P + p], cy = coords[(b * 2 + 1) * P + p];
+            int H = h, W = w;
+            for (int l = 0; l < L; l++) {
+                const float sc = (float)(1 << l);
+                const float ccx = cx / sc, ccy = cy / sc;
+                const float* plane = levels[l] + (b * P + p) * (long)H * W;
+                for (int i = 0; i < K; i++)
+                    for (int j = 0; j < K; j++) {
+                        const float x = ccx + (float)(i - r), y = ccy + (float)(j - r);
+                        const float gx = norm_coord1(x, W, div_mode), gy = norm_coord1(y, H, div_mode);
+                        float v;
+                        grid_sample_bilinear_pt(plane, 0, 1, H, W, gx, gy, &v, 0);
+                        out[(b * (long)(L * K * K) + (long)l * K * K + i * K + j) * P + p] = v;
+                    }
+                H /= 2; W /= 2;
+            }
+        }
+}

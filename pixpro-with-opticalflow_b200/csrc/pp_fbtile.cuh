@@ -166,6 +166,10 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
     const int X0 = tx0 + lane, Y0 = ty0 + warp;
     const float* fp = ptr_at(f, Y0 * W + X0);                  // own flow, x channel, row Y0
     uint8_t* mp = (dir ? a.mask[1] : a.mask[0]) + (int64_t)b * HW + Y0 * W + X0;
+    if (OPT & 16) {  // opaque to the optimiser: kept in registers instead of being re-derived from tid / ctaid next to every use
+        asm volatile("" : "+l"(fp));
+        asm volatile("" : "+l"(mp));
+    }
     const int rstep = 8 * W;                                    // one thread-row (8 image rows)
     F2 xn2[NX];
 #pragma unroll
@@ -554,6 +558,8 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
             case 6: return launch_cfg<64, 48, 96, 72, 3, 1280, 720, 7>(a, B, st);
             case 7: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 12>(a, B, st);
             case 8: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 14>(a, B, st);
+            case 9: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 21>(a, B, st);
+            case 10: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 23>(a, B, st);
             default: return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
         }
     }

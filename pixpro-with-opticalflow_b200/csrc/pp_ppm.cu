@@ -223,22 +223,6 @@ struct EpGradS {  // gS[b,i,j] = v * A'(S[b,i,j])
 // ---- tensor-core route for large grids (tcgen05 3xTF32, pp_tc.cuh) --------------------------------
 // Specialised operand loaders for the tensor-core route (operands are pre-normalised once by
 // coldiv_kernel, so loads are plain vector / coalesced accesses without divisions).
-struct TcLdT {  // transposed: operand row = spatial index i, k = channel c; memory [C][P] (i contiguous)
-    static constexpr bool kRowMajorK = false;
-    const float* p;
-    int C, P;
-    __device__ __forceinline__ float4 load4(int64_t b, int i, int c) const {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < P) {
-            const float* q = p + (b * C + c) * (int64_t)P + i;
-            if (c < C) v.x = __ldg(q);
-            if (c + 1 < C) v.y = __ldg(q + P);
-            if (c + 2 < C) v.z = __ldg(q + 2 * (int64_t)P);
-            if (c + 3 < C) v.w = __ldg(q + 3 * (int64_t)P);
-        }
-        return v;
-    }
-};
 struct TcLdActN {  // relu^γ(S[row][k..k+3])  (S symmetric: also serves A[k][row])
     static constexpr bool kRowMajorK = true;
     const float* S;

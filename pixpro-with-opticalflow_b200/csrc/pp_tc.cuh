@@ -274,6 +274,22 @@ struct TcLdN {  // natural: memory [rows][K], k contiguous
         return ldg4_guard(p + (b * rows + row) * (int64_t)K + k, k, K);
     }
 };
+struct TcLdT {  // transposed: operand row = spatial index i, k = channel c; memory [C][P] (i contiguous)
+    static constexpr bool kRowMajorK = false;
+    const float* p;
+    int C, P;
+    __device__ __forceinline__ float4 load4(int64_t b, int i, int c) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < P) {
+            const float* q = p + (b * C + c) * (int64_t)P + i;
+            if (c < C) v.x = __ldg(q);
+            if (c + 1 < C) v.y = __ldg(q + P);
+            if (c + 2 < C) v.z = __ldg(q + 2 * (int64_t)P);
+            if (c + 3 < C) v.w = __ldg(q + 3 * (int64_t)P);
+        }
+        return v;
+    }
+};
 struct TcStN {  // out[b][m][n..n+15]
     float* out;
     int M, N;

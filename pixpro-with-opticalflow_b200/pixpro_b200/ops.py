@@ -625,3 +625,45 @@ def tc_gemm_nt(A, B):
     with torch.cuda.device(A.device):
         _cabi.check(_cabi.lib().pp_tc_gemm_nt(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, _stream()), "pp_tc_gemm_nt")
     return C
+
+
+# ---------------------------------------------------------------------- RAFT correlation --
+
+def corr_volume(fmap1, fmap2):
+    """CorrBlock.corr (contrast/flow/corr.py:52-60): fmap1, fmap2 [B,D,h,w] -> [B, h*w, h*w] = <f1_i, f2_j> / sqrt(D)."""
+    f1, f2 = _f32(fmap1, "fmap1"), _f32(fmap2, "fmap2")
+    assert f1.ndim == 4 and f1.shape == f2.shape
+    B, D, h, w = f1.shape
+    out = torch.empty((B, h * w, h * w), device=f1.device, dtype=torch.float32)
+    with torch.cuda.device(f1.device):
+        _cabi.check(_cabi.lib().pp_corr_volume(_ptr(f1), _ptr(f2), B, D, h, w, _ptr(out), _stream()), "pp_corr_volume")
+    return out
+
+
+def corr_pool(corr):
+    """One pyramid step (corr.py:26-28): avg_pool2d(2, stride=2) over the last two dims of [N,1,h,w] (or [N,h,w])."""
+    c = _f32(corr, "corr")
+    h, w = c.shape[-2:]
+    planes = c.numel() // (h * w)
+    out = torch.empty(tuple(c.shape[:-2]) + (h // 2, w // 2), device=c.device, dtype=torch.float32)
+    with torch.cuda.device(c.device):
+        _cabi.check(_cabi.lib().pp_corr_pool(_ptr(c), planes, h, w, _ptr(out), _stream()), "pp_corr_pool")
+    return out
+
+
+def corr_lookup(pyramid, coords, radius):
+    """CorrBlock.__call__ (corr.py:30-50).  pyramid: list of [B*h*w, 1, h>>l, w>>l]; coords [B,2,h,w] -> [B, L*(2r+1)^2, h, w]."""
+    import ctypes
+    coords = _f32(coords, "coords")
+    B, two, h, w = coords.shape
+    assert two == 2
+    levels = [_f32(p, "pyramid level") for p in pyramid]
+    for l, p in enumerate(levels):
+        assert p.shape[0] == B * h * w and tuple(p.shape[-2:]) == (h >> l, w >> l), "pyramid level %d has shape %s" % (l, tuple(p.shape))
+    K = 2 * radius + 1
+    out = torch.empty((B, len(levels) * K * K, h, w), device=coords.device, dtype=torch.float32)
+    table = (ctypes.c_void_p * len(levels))(*[p.data_ptr() for p in levels])
+    with torch.cuda.device(coords.device):
+        _cabi.check(_cabi.lib().pp_corr_lookup(ctypes.cast(table, ctypes.c_void_p), len(levels), _ptr(coords), B, h, w, int(radius),
+                                               _div_mode, _ptr(out), _stream()), "pp_corr_lookup")
+    return out

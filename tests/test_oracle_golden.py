@@ -191,3 +191,21 @@ def test_sparse_corr_equals_sampling_the_dense_stage(orc, n, h, w, flow_up, size
         assert_bits_equal(wp[0], ox.reshape(B, -1), "warped x")
         assert_bits_equal(wp[1], oy.reshape(B, -1), "warped y")
         assert_bits_equal(wp[2] != 0, mg.reshape(B, -1), "mask bit")
+
+
+CORR_TAGS = ["small", "raft_small", "oob"]
+
+
+@pytest.mark.parametrize("tag", CORR_TAGS)
+def test_corr_block(orc, tag):
+    """the RAFT CorrBlock restatement against the reference's torch CorrBlock
+    (contrast/flow/corr.py:12-60): volume within 1e-5, pyramid and windowed lookup bit-exact."""
+    g = load_golden("corr_" + tag)
+    L, r = int(g["num_levels"]), int(g["radius"])
+    B, D, h, w = g["fmap1"].shape
+    assert rel_err(orc.corr_volume(g["fmap1"], g["fmap2"]), g["level0"].reshape(B, h * w, h * w)) < TOL
+    pyr = [g["level0"]]
+    for l in range(1, L):
+        pyr.append(orc.corr_pool(pyr[-1]))
+        assert sha(pyr[-1]) == str(g[f"level{l}_sha"]), f"pyramid level {l}"
+    assert_bits_equal(orc.corr_lookup(pyr, g["coords"], r), g["out"], "lookup")
