@@ -217,6 +217,11 @@ PP_API int pp_lars_sgd_step(const PpMtTensor* table_dev, int ntensors, const int
  * The PPM / loss contractions at large grids run on the same kernel with fused loaders; this
  * entry exposes the bare GEMM for numerics tests and microbenchmarks.                        */
 PP_API int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* stream);
+/* The same product through the TMA-fed, warp-specialised kernel (csrc/pp_tc2.cuh): operands are split once into hi / lo
+ * planes in `workspace` (pp_tc_gemm_nt_workspace bytes, 16-byte aligned) and streamed by TMA in the 128-byte-swizzled UMMA
+ * layout; 128 x 256 CTA tiles.  K % 4 != 0 or PIXPRO_B200_TC2=0 falls back to the kernel above.                  */
+PP_API int64_t pp_tc_gemm_nt_workspace(int64_t batch, int M, int N, int K);
+PP_API int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* workspace, void* stream);
 
 /* ---- RAFT correlation volume, pyramid and lookup ----------------------------
  * The reference's torch CorrBlock (contrast/flow/corr.py:12-60; its CUDA twin `alt_cuda_corr` is not shipped).

@@ -2,6 +2,7 @@
 // C[b] = A[b] * B[b]^T in fp32 accuracy (3xTF32), A [batch,M,K], B [batch,N,K], C [batch,M,N].
 #include "pp_common.cuh"
 #include "pp_tc.cuh"
+#include "pp_tc2.cuh"
 
 namespace pp {
 namespace tc {
@@ -49,4 +50,29 @@ extern "C" int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t b
     PP_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "pp_tc_gemm_nt: bad shape");
     return launch_tc("tc_gemm_nt", batch, M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N},
                      (cudaStream_t)stream);
+}
+
+// The same product through the TMA-fed kernel (pp_tc2.cuh): the operands are split once into hi / lo planes in `workspace`
+// (pp_tc_gemm_nt_workspace bytes), then streamed by TMA.  Falls back to the kernel above when K % 4 != 0.
+extern "C" int64_t pp_tc_gemm_nt_workspace(int64_t batch, int M, int N, int K) {
+    return 2 * batch * ((int64_t)M + N) * K * (int64_t)sizeof(float);
+}
+
+extern "C" int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* workspace, void* stream) {
+    PP_REQUIRE(A && B && C && workspace, "pp_tc_gemm_nt_ws: null pointer");
+    PP_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "pp_tc_gemm_nt_ws: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* a_hi = (float*)workspace;
+    float* a_lo = a_hi + batch * (int64_t)M * K;
+    float* b_hi = a_lo + batch * (int64_t)M * K;
+    float* b_lo = b_hi + batch * (int64_t)N * K;
+    if (tc2::applicable(K, A, B, workspace, C)) {
+        int rc = tc2::launch_split(A, batch * (int64_t)M * K, a_hi, a_lo, st);
+        if (rc) return rc;
+        rc = tc2::launch_split(B, batch * (int64_t)N * K, b_hi, b_lo, st);
+        if (rc) return rc;
+        rc = tc2::launch_tc2("tc2_gemm_nt", batch, M, N, K, a_hi, a_lo, b_hi, b_lo, tc::StoreC{C, M, N}, st);
+        if (rc >= 0) return rc;
+    }
+    return launch_tc("tc_gemm_nt", batch, M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N}, st);
 }

@@ -55,6 +55,8 @@ SIGNATURES = {
     "pp_conv1x1_bwd_workspace": (_l, [_l, _i, _i, _i]),
     "pp_conv1x1_bwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pp_tc_gemm_nt": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp]),
+    "pp_tc_gemm_nt_workspace": (_l, [_l, _i, _i, _i]),
+    "pp_tc_gemm_nt_ws": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp]),
     "pp_corr_volume": (_i, [_vp, _vp, _l, _i, _i, _i, _vp, _vp]),
     "pp_corr_pool": (_i, [_vp, _l, _i, _i, _vp, _vp]),
     "pp_corr_lookup": (_i, [_vp, _i, _vp, _l, _i, _i, _i, _i, _vp, _vp]),

@@ -613,9 +613,10 @@ def conv1x1(x, weight, bias=None):
 
 # ---------------------------------------------------------------------------- tensor cores --
 
-def tc_gemm_nt(A, B):
+def tc_gemm_nt(A, B, tma=True, workspace=None):
     """C[b] = A[b] @ B[b].T on the tcgen05 tensor cores with 3xTF32 (fp32-accurate).
-    A [batch,M,K], B [batch,N,K] -> [batch,M,N]."""
+    A [batch,M,K], B [batch,N,K] -> [batch,M,N].  tma=True: the TMA-fed warp-specialised kernel (csrc/pp_tc2.cuh; the
+    operands are split into hi / lo planes in a workspace first); tma=False: the thread-staged kernel (csrc/pp_tc.cuh)."""
     A = _f32(A, "A")
     B = _f32(B, "B")
     assert A.ndim == 3 and B.ndim == 3 and A.shape[0] == B.shape[0] and A.shape[2] == B.shape[2]
@@ -623,7 +624,14 @@ def tc_gemm_nt(A, B):
     N = B.shape[1]
     C = torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
     with torch.cuda.device(A.device):
-        _cabi.check(_cabi.lib().pp_tc_gemm_nt(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, _stream()), "pp_tc_gemm_nt")
+        if tma:
+            nbytes = _cabi.lib().pp_tc_gemm_nt_workspace(batch, M, N, K)
+            if workspace is None or workspace.numel() < nbytes:
+                workspace = torch.empty(nbytes, device=A.device, dtype=torch.uint8)
+            _cabi.check(_cabi.lib().pp_tc_gemm_nt_ws(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, _ptr(workspace), _stream()),
+                        "pp_tc_gemm_nt_ws")
+        else:
+            _cabi.check(_cabi.lib().pp_tc_gemm_nt(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, _stream()), "pp_tc_gemm_nt")
     return C
 
 

@@ -7,14 +7,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.mark.parametrize("tma", [False, True], ids=["staged", "tma"])
 @pytest.mark.parametrize("batch,M,N,K", [(1, 128, 128, 32), (2, 128, 128, 256), (3, 196, 196, 256), (2, 256, 784, 784),
-                                         (1, 50, 70, 36), (2, 300, 130, 100)])
-def test_tc_gemm_nt_matches_fp64(batch, M, N, K):
+                                         (1, 50, 70, 36), (2, 300, 130, 100), (2, 784, 784, 256), (1, 130, 530, 72)])
+def test_tc_gemm_nt_matches_fp64(batch, M, N, K, tma):
+    """tma=True: the TMA-fed warp-specialised kernel (csrc/pp_tc2.cuh; 128 x 256 tiles, ragged M / N / K tails are TMA
+    zero fill); tma=False: the thread-staged kernel (csrc/pp_tc.cuh)."""
     from pixpro_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
     A = torch.randn(batch, M, K, generator=g).to(DEV)
     B = torch.randn(batch, N, K, generator=g).to(DEV)
-    C = ops.tc_gemm_nt(A, B)
+    C = ops.tc_gemm_nt(A, B, tma=tma)
     ref = torch.bmm(A.double(), B.double().transpose(1, 2))
     err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-5, err
@@ -22,14 +25,15 @@ def test_tc_gemm_nt_matches_fp64(batch, M, N, K):
     assert err < 5e-6
 
 
-def test_tc_gemm_exact_on_small_integers():
+@pytest.mark.parametrize("tma", [False, True], ids=["staged", "tma"])
+def test_tc_gemm_exact_on_small_integers(tma):
     """Integer-valued operands below 2^10 are exact in TF32 and sums below 2^24 are exact in
     fp32: the tensor-core result must equal the integer matmul bit for bit."""
     from pixpro_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(5)
     A = torch.randint(-8, 9, (2, 200, 64), generator=g).float().to(DEV)
     B = torch.randint(-8, 9, (2, 136, 64), generator=g).float().to(DEV)
-    C = ops.tc_gemm_nt(A, B)
+    C = ops.tc_gemm_nt(A, B, tma=tma)
     ref = torch.bmm(A.double(), B.double().transpose(1, 2)).float()
     assert torch.equal(C, ref)
 
