@@ -115,8 +115,8 @@ PP_API int pp_add_optical_flow(const float* flow, int64_t B, int Hin, int Win, c
  * Outputs: loss[1]; pos_num[B]; pos_mean[B]; dq [B,C,P] = d loss/d q (the backward of the
  * reference's autograd graph for upstream gradient 1; NULL to skip); optional debug/parity
  * outputs pos_mask u8 [B,P,P] and centres [4,B,P] = (warped q x, warped q y, k x, k y).
- * workspace: pp_regression_loss_workspace(B,G) bytes of device scratch.                   */
-PP_API int64_t pp_regression_loss_workspace(int64_t B, int G);
+ * workspace: pp_regression_loss_workspace(B,C,G) bytes of device scratch.                 */
+PP_API int64_t pp_regression_loss_workspace(int64_t B, int C, int G);
 PP_API int pp_regression_loss(const float* q, const float* k, int64_t B, int C, int G, const float* coord_q, const float* coord_k,
                        const float* flow, int Hin, int Win, const uint8_t* mask, int H_orig, int W_orig, double pos_ratio,
                        int div_mode, float* loss, float* pos_num, float* pos_mean, float* dq, uint8_t* pos_mask,
@@ -125,7 +125,7 @@ PP_API int pp_regression_loss(const float* q, const float* k, int64_t B, int C, 
 /* Both loss directions of PixPro.forward (contrast/models/PixPro.py:429-430) in ONE launch:
  * every argument that differs between the two regression_loss calls is a table of two
  * pointers (entries of flow[] / mask[] may be NULL).  Same results as two pp_regression_loss
- * calls; workspace[i] each pp_regression_loss_workspace(B,G) bytes.                         */
+ * calls; workspace[i] each pp_regression_loss_workspace(B,C,G) bytes.                       */
 PP_API int pp_regression_loss_pair(const float* const* q, const float* const* k, int64_t B, int C, int G,
                                    const float* const* coord_q, const float* const* coord_k, const float* const* flow,
                                    int Hin, int Win, const uint8_t* const* mask, int H_orig, int W_orig, double pos_ratio,

@@ -448,7 +448,7 @@ def pin_corr_block(rep, gold):
     already done, this only avoids `alt_cuda_corr`'s try/except noise) against orc_corr_volume / _pool / _lookup."""
     import importlib
     rcorr = importlib.import_module("contrast.flow.corr")
-    for tag, B, D, h, w, L, r, spread in [("small", 2, 32, 6, 10, 3, 2, 3.0), ("raft_small", 1, 128, 16, 24, 4, 3, 6.0),
+    for tag, B, D, h, w, L, r, spread in [("small", 2, 32, 8, 12, 3, 2, 3.0), ("raft_small", 1, 128, 16, 24, 4, 3, 6.0),
                                           ("oob", 1, 16, 8, 8, 2, 4, 20.0)]:
         g = torch.Generator().manual_seed(700 + h)
         f1 = torch.randn(B, D, h, w, generator=g)

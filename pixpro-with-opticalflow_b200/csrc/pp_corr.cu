@@ -17,10 +17,14 @@
 
 namespace pp {
 
-struct TcStDiv {  // out[b][m][n..n+15] = v / s  (tensor / tensor true division of the reference: IEEE on every device)
+struct TcStDiv {
+    static constexpr bool kAux = false;  // out[b][m][n..n+15] = v / s  (tensor / tensor true division of the reference: IEEE on every device)
     float* out;
     int M, N;
     float s;
+    __device__ __forceinline__ void store4(int64_t b, int m, int n, float4 v) const {
+        st4_guard(out + (b * M + m) * (int64_t)N + n, n, N, make_float4(__fdiv_rn(v.x, s), __fdiv_rn(v.y, s), __fdiv_rn(v.z, s), __fdiv_rn(v.w, s)));
+    }
     __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
         float* q = out + (b * M + m) * (int64_t)N + n;
         if (n + 15 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {

@@ -16,6 +16,7 @@
 #include "pp_common.cuh"
 #include "pp_small.cuh"
 #include "pp_tc.cuh"
+#include "pp_tc2.cuh"
 #include "pp_warp.cuh"
 
 namespace pp {
@@ -339,7 +340,8 @@ __global__ void __launch_bounds__(256) loss_centres_kernel(PrepArgs a) {
 }
 
 // grid (ceil(P/8), B); warp w of the block owns query cell i = 8*blockIdx.x + w
-__global__ void __launch_bounds__(256) loss_pos_kernel(LossWs ws, int P, float pr, uint8_t* posb) {
+// posf (optional): the same matrix as 0/1 floats — the B operand plane the TMA-fed contraction streams (exact in TF32)
+__global__ void __launch_bounds__(256) loss_pos_kernel(LossWs ws, int P, float pr, uint8_t* posb, float* posf) {
     const int64_t b = blockIdx.y;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= P) return;
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(256) loss_pos_kernel(LossWs ws, int P, float p
     for (int j = lane; j < P; j += 32) {
         bool pos = mg && pair_pos(qx, qy, kx[j], ky[j], md, pr);
         row[j] = pos ? 1 : 0;
+        if (posf) posf[(b * P + i) * (int64_t)P + j] = pos ? 1.0f : 0.0f;
         cnt += pos;
     }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -398,10 +401,15 @@ struct TcLdPos {  // B operand: row = query cell i, k = key cell j; bytes -> 0/1
     }
 };
 struct TcStDq {  // dq[b][c][i..i+15] = M * (-2 / (B den_b))
+    static constexpr bool kAux = false;
     float* dq;
     const float* den;
     float scale;
     int C, P;
+    __device__ __forceinline__ void store4(int64_t b, int c, int i, float4 v) const {
+        const float s = scale / __ldg(den + b);
+        st4_guard(dq + (b * C + c) * (int64_t)P + i, i, P, make_float4(v.x * s, v.y * s, v.z * s, v.w * s));
+    }
     __device__ __forceinline__ void store16(int64_t b, int c, int i, const float v[16]) const {
         const float s = scale / __ldg(den + b);
         float* q = dq + (b * C + c) * (int64_t)P + i;
@@ -575,10 +583,17 @@ int pp_add_optical_flow(const float* flow, int64_t B, int Hin, int Win, const fl
     return check_launch("add_flow_kernel");
 }
 
-int64_t pp_regression_loss_workspace(int64_t B, int G) {
+// The TMA-fed contraction (pp_tc2.cuh) streams planes with 16-byte row strides: C % 4 == 0 and P % 4 == 0.
+static bool loss_tc2(int C, int P) {
+    static const int off = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
+    return !off && use_tensor_cores(P) && P > PMAX && C % 4 == 0 && P % 4 == 0;
+}
+
+int64_t pp_regression_loss_workspace(int64_t B, int C, int G) {
     int64_t P = (int64_t)G * G;
     int64_t bytes = (5 * B * P + 2 * B + B * loss_ntile((int)P)) * (int64_t)sizeof(float);
     if (P > PMAX) bytes += B * P * (int64_t)sizeof(int) + B * P * P;  // row counts + byte matrix of positives
+    if (loss_tc2(C, (int)P)) bytes += 16 + (B * P * P + 2 * B * (int64_t)C * P) * (int64_t)sizeof(float);  // (16-byte aligned) 0/1 float plane, hi / lo planes of k
     return bytes;
 }
 
@@ -642,12 +657,23 @@ static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int
         for (int c = 0; c < ncall; c++) {
             uint8_t* posb = calls[c].pos_mask ? calls[c].pos_mask : pa[c].ws.posb;
             PP_LAUNCH("loss_centres", st, loss_centres_kernel<<<(unsigned)B, 256, 0, st>>>(pa[c]));
-            PP_LAUNCH("loss_pos", st, loss_pos_kernel<<<dim3((P + 7) / 8, (unsigned)B), 256, 0, st>>>(pa[c].ws, P, pa[c].pr, posb));
+            const bool tma = loss_tc2(C, P);
+            float* posf = tma ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(pa[c].ws.posb + B * (int64_t)P * P) + 15) & ~(uintptr_t)15) : nullptr;
+            float *k_hi = posf + B * (int64_t)P * P, *k_lo = k_hi + B * (int64_t)C * P;
+            PP_LAUNCH("loss_pos", st, loss_pos_kernel<<<dim3((P + 7) / 8, (unsigned)B), 256, 0, st>>>(pa[c].ws, P, pa[c].pr, posb, posf));
             PP_LAUNCH("loss_cnt", st, loss_cnt_kernel<<<(unsigned)B, 256, 0, st>>>(pa[c].ws, P, pa[c].pos_num, pa[c].pos_mean));
             rc = check_launch("loss prep (large grid)");
             if (rc) return rc;
-            rc = launch_tc("loss M=K*pos^T (tcgen05)", B, C, P, P, TcLdN{calls[c].k, C, P}, TcLdPos{posb, P},
-                           TcStDq{calls[c].dq, pa[c].ws.den, scale, C, P}, st);
+            rc = -1;
+            if (tma) {
+                rc = tc2::launch_split(calls[c].k, B * (int64_t)C * P, k_hi, k_lo, st);
+                if (rc) return rc;
+                rc = tc2::launch_tc2<false>("loss M=K*pos^T (tcgen05)", B, C, P, P, k_hi, k_lo, posf, posf,
+                                            TcStDq{calls[c].dq, pa[c].ws.den, scale, C, P}, st);
+            }
+            if (rc < 0)
+                rc = launch_tc("loss M=K*pos^T (tcgen05)", B, C, P, P, TcLdN{calls[c].k, C, P}, TcLdPos{posb, P},
+                               TcStDq{calls[c].dq, pa[c].ws.den, scale, C, P}, st);
             if (rc) return rc;
             PP_LAUNCH("loss_dot", st, loss_dot_kernel<<<dim3(kDotSplit, (unsigned)B), 256, 0, st>>>(calls[c].q, calls[c].dq, pa[c].ws, (int64_t)C * P, scale));
             rc = check_launch("loss_dot_kernel");

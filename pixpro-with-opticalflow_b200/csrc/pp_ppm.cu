@@ -20,6 +20,7 @@
 #include "pp_common.cuh"
 #include "pp_ppm.cuh"
 #include "pp_tc.cuh"
+#include "pp_tc2.cuh"
 
 namespace pp {
 
@@ -266,6 +267,152 @@ struct TcStGradS {  // gS[b][i][j] = v * A'(S[b][i][j])
     }
 };
 
+// ---- TMA-fed tensor-core route (pp_tc2.cuh): operands as pre-split hi / lo planes -----------------------------------------
+// One pass over a [B,C,P] tensor u (optionally divided by a column norm) that writes whatever the contractions need of it:
+//   out        u / n as plain fp32 [B,C,P]                      (kept for the normalisation backward)
+//   hi, lo     the same values split, [B,C,P]   (K = spatial index: the A operand of Y / gv / gx)
+//   thi, tlo   the same values split and TRANSPOSED, [B,P,C]    (K = channel: both operands of S and gS)
+// grid (ceil(P/32), ceil(C/32), B), block (32, 8); the transpose goes through a padded 32 x 32 shared-memory tile.
+__global__ void __launch_bounds__(256) planes_kernel(const float* __restrict__ u, const float* __restrict__ nrm, int C, int P,
+                                                      float* __restrict__ out, float* __restrict__ hi, float* __restrict__ lo,
+                                                      float* __restrict__ thi, float* __restrict__ tlo) {
+    __shared__ float t[32][33];
+    const int64_t b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int p = p0 + threadIdx.x;
+    const float n = (nrm && p < P) ? __ldg(nrm + b * P + p) : 1.0f;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int c = c0 + r;
+        float v = 0.0f;
+        if (c < C && p < P) {
+            const int64_t o = (b * C + c) * (int64_t)P + p;
+            v = __ldg(u + o);
+            if (nrm) v = v / n;
+            if (out) out[o] = v;
+            if (hi) {
+                float h, l;
+                tc2::split1(v, h, l);
+                hi[o] = h;
+                lo[o] = l;
+            }
+        }
+        t[r][threadIdx.x] = v;
+    }
+    if (!thi) return;
+    __syncthreads();
+    const int c = c0 + threadIdx.x;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int pp_ = p0 + r;
+        if (c < C && pp_ < P) {
+            float h, l;
+            tc2::split1(t[threadIdx.x][r], h, l);
+            const int64_t o = (b * P + pp_) * (int64_t)C + c;
+            thi[o] = h;
+            tlo[o] = l;
+        }
+    }
+}
+// (gS + gS^T) split into planes [B,P,P].  grid (ceil(P/32), ceil(P/32), B), block (32, 8).
+__global__ void __launch_bounds__(256) sym_planes_kernel(const float* __restrict__ gS, int P, float* __restrict__ hi, float* __restrict__ lo) {
+    __shared__ float t[32][33];
+    const float* g = gS + (int64_t)blockIdx.z * P * P;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {  // tile (J, I) read row-wise: t[r][x] = gS[j0 + r][i0 + x]
+        const int jj = j0 + r, ii = i0 + threadIdx.x;
+        t[r][threadIdx.x] = (jj < P && ii < P) ? __ldg(g + jj * (int64_t)P + ii) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = i0 + r, j = j0 + threadIdx.x;
+        if (i < P && j < P) {
+            const int64_t o = (int64_t)blockIdx.z * P * P + i * (int64_t)P + j;
+            float h, l;
+            tc2::split1(__ldg(g + i * (int64_t)P + j) + t[threadIdx.x][r], h, l);
+            hi[o] = h;
+            lo[o] = l;
+        }
+    }
+}
+// Epilogue of the similarity contraction: S itself (kept for the backward) and relu^gamma(S) already split into the planes the
+// propagation contractions stream — the activation pass over S is gone.  Requires P % 4 == 0 (the TMA route does).
+struct TcStSAct {
+    static constexpr bool kAux = false;
+    float *S, *hi, *lo;
+    int P;
+    Act act;
+    __device__ __forceinline__ void store4(int64_t b, int i, int j, float4 v) const {  // P % 4 == 0: j + 3 < P, 16-byte aligned
+        const int64_t o = (b * P + i) * (int64_t)P + j;
+        float4 h, l;
+        tc2::split1(act.f(v.x), h.x, l.x);
+        tc2::split1(act.f(v.y), h.y, l.y);
+        tc2::split1(act.f(v.z), h.z, l.z);
+        tc2::split1(act.f(v.w), h.w, l.w);
+        *reinterpret_cast<float4*>(S + o) = v;
+        *reinterpret_cast<float4*>(hi + o) = h;
+        *reinterpret_cast<float4*>(lo + o) = l;
+    }
+    __device__ __forceinline__ void store16(int64_t b, int i, int j, const float v[16]) const {
+        const int64_t o = (b * P + i) * (int64_t)P + j;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j + 4 * q < P) {
+                float4 h, l;
+                tc2::split1(act.f(v[4 * q]), h.x, l.x);
+                tc2::split1(act.f(v[4 * q + 1]), h.y, l.y);
+                tc2::split1(act.f(v[4 * q + 2]), h.z, l.z);
+                tc2::split1(act.f(v[4 * q + 3]), h.w, l.w);
+                *reinterpret_cast<float4*>(S + o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                *reinterpret_cast<float4*>(hi + o + 4 * q) = h;
+                *reinterpret_cast<float4*>(lo + o + 4 * q) = l;
+            }
+        }
+    }
+};
+struct TcStGradS4 {  // gS[b][i][j] = v * A'(S[b][i][j]), 16-byte accesses (P % 4 == 0)
+    float* gS;
+    const float* S;
+    int P;
+    Act act;
+    static constexpr bool kAux = true;  // S[b][i][j..j+3], loaded ahead of the accumulator read
+    __device__ __forceinline__ float4 aux4(int64_t b, int i, int j, int M, int N) const {
+        if (i >= P || j >= P) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return __ldg(reinterpret_cast<const float4*>(S + (b * P + i) * (int64_t)P + j));
+    }
+    __device__ __forceinline__ void prefetch_line(int64_t b, int i, int j) const {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S + (b * P + i) * (int64_t)P + j));
+    }
+    __device__ __forceinline__ void store4(int64_t b, int i, int j, float4 v, float4 s) const {
+        const int64_t o = (b * P + i) * (int64_t)P + j;
+        *reinterpret_cast<float4*>(gS + o) = make_float4(v.x * act.df(s.x), v.y * act.df(s.y), v.z * act.df(s.z), v.w * act.df(s.w));
+    }
+    __device__ __forceinline__ void store16(int64_t b, int i, int j, const float v[16]) const {
+        const int64_t o = (b * P + i) * (int64_t)P + j;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j + 4 * q < P) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(S + o + 4 * q));
+                *reinterpret_cast<float4*>(gS + o + 4 * q) = make_float4(v[4 * q] * act.df(s.x), v[4 * q + 1] * act.df(s.y),
+                                                                         v[4 * q + 2] * act.df(s.z), v[4 * q + 3] * act.df(s.w));
+            }
+        }
+    }
+};
+// The TMA route needs 16-byte row strides in every plane: C % 4 == 0 and P % 4 == 0 (PIXPRO_B200_TC2=0 disables it).
+static inline bool ppm_tc2(int C, int P) {
+    static const int off = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
+    return !off && use_tensor_cores(P) && C % 4 == 0 && P % 4 == 0;
+}
+static int launch_planes(const float* u, const float* nrm, int64_t B, int C, int P, float* out, float* hi, float* lo, float* thi,
+                         float* tlo, cudaStream_t st) {
+    dim3 grid((P + 31) / 32, (C + 31) / 32, (unsigned)B), block(32, 8);
+    PP_LAUNCH("ppm planes", st, planes_kernel<<<grid, block, 0, st>>>(u, nrm, C, P, out, hi, lo, thi, tlo));
+    return check_launch("ppm planes");
+}
+
 template <class LA, class LB, class EP>
 static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (unsigned)B);
@@ -275,6 +422,8 @@ static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la,
 
 struct Saved {
     float *nx, *nv, *ny, *S, *xh, *vh;  // xh, vh: normalised operands (generic path only)
+    // TMA route only (ppm_tc2): hi / lo planes.  a: relu^gamma(S) [B,P,P]; x, v: [B,C,P]; xt, vt: transposed [B,P,C]
+    float *a_hi, *a_lo, *x_hi, *x_lo, *xt_hi, *xt_lo, *v_hi, *v_lo, *vt_hi, *vt_lo;
 };
 static Saved carve_saved(void* p, int64_t B, int C, int P) {
     Saved s;
@@ -284,7 +433,12 @@ static Saved carve_saved(void* p, int64_t B, int C, int P) {
     s.ny = f; f += B * P;
     s.S = f; f += B * (int64_t)P * P;
     s.xh = f; f += B * (int64_t)C * P;
-    s.vh = f;
+    s.vh = f; f += B * (int64_t)C * P;
+    const int64_t pp2 = B * (int64_t)P * P, cp = B * (int64_t)C * P;
+    s.a_hi = f; f += pp2;
+    s.a_lo = f; f += pp2;
+    float** q[8] = {&s.x_hi, &s.x_lo, &s.xt_hi, &s.xt_lo, &s.v_hi, &s.v_lo, &s.vt_hi, &s.vt_lo};
+    for (int i = 0; i < 8; i++) { *q[i] = f; f += cp; }
     return s;
 }
 
@@ -296,13 +450,18 @@ extern "C" {
 
 int64_t pp_ppm_saved_bytes(int64_t B, int C, int P) {
     int64_t f = 3 * B * P + B * (int64_t)P * P;
-    if (!ppm_small_supported(C, P)) f += 2 * B * (int64_t)C * P;  // normalised operands kept for the backward contractions
+    if (!ppm_small_supported(C, P)) {
+        f += 2 * B * (int64_t)C * P;  // normalised operands kept for the backward contractions
+        if (ppm_tc2(C, P)) f += 2 * B * (int64_t)P * P + 8 * B * (int64_t)C * P;  // hi / lo planes (see Saved)
+    }
     return f * (int64_t)sizeof(float);
 }
 
 int64_t pp_ppm_bwd_workspace(int64_t B, int C, int P) {
     // gy [B,C,P] + gS [B,P,P] + gvh [B,C,P] + gxh [B,C,P]
-    return (3 * B * (int64_t)C * P + B * (int64_t)P * P) * (int64_t)sizeof(float);
+    int64_t f = 3 * B * (int64_t)C * P + B * (int64_t)P * P;
+    if (!ppm_small_supported(C, P) && ppm_tc2(C, P)) f += 4 * B * (int64_t)C * P + 2 * B * (int64_t)P * P;  // gy, gy^T and (gS+gS^T) planes
+    return f * (int64_t)sizeof(float);
 }
 
 int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, double gamma, double clamp_value, int final_norm,
@@ -321,7 +480,23 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
     if (rc) return rc;
     // S[i][j] = Σ_c x̂[c][i] x̂[c][j]
     const int64_t total = B * (int64_t)C * P;
-    if (use_tensor_cores(P)) {
+    if (ppm_tc2(C, P)) {
+        // TMA route: one pass per operand writes the normalised tensor and every plane the five contractions stream
+        rc = launch_planes(feat, sv.nx, B, C, P, sv.xh, sv.x_hi, sv.x_lo, sv.xt_hi, sv.xt_lo, st);
+        if (rc) return rc;
+        rc = launch_planes(val, sv.nv, B, C, P, sv.vh, sv.v_hi, sv.v_lo, sv.vt_hi, sv.vt_lo, st);
+        if (rc) return rc;
+        rc = tc2::launch_tc2("ppm S (tcgen05)", B, P, P, C, sv.xt_hi, sv.xt_lo, sv.xt_hi, sv.xt_lo, TcStSAct{sv.S, sv.a_hi, sv.a_lo, P, act}, st);
+        if (rc > 0) return rc;
+        if (rc == 0) rc = tc2::launch_tc2("ppm Y (tcgen05)", B, C, P, P, sv.v_hi, sv.v_lo, sv.a_hi, sv.a_lo, TcStN{out, C, P}, st);
+        if (rc > 0) return rc;
+        if (rc < 0) {  // tensor maps could not be encoded: the thread-staged kernels read the same normalised tensors
+            rc = launch_tc("ppm S (tcgen05)", B, P, P, C, TcLdT{sv.xh, C, P}, TcLdT{sv.xh, C, P}, TcStSAct{sv.S, sv.a_hi, sv.a_lo, P, act}, st);
+            if (rc) return rc;
+            rc = launch_tc("ppm Y (tcgen05)", B, C, P, P, TcLdN{sv.vh, C, P}, TcLdActN{sv.S, P, act}, TcStN{out, C, P}, st);
+            if (rc) return rc;
+        }
+    } else if (use_tensor_cores(P)) {
         // normalise once (x̂, v̂ kept for backward), then the two contractions on the tensor cores
         PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, sv.nx, C, P, total, sv.xh));
         PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(val, sv.nv, C, P, total, sv.vh));
@@ -368,6 +543,36 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
         rc = check_launch("ppm normbwd(out)");
         if (rc) return rc;
         gyp = gy;
+    }
+    if (ppm_tc2(C, P)) {
+        float* f = gxh + B * (int64_t)C * P;
+        const int64_t cp = B * (int64_t)C * P, pp2 = B * (int64_t)P * P;
+        float *gy_hi = f, *gy_lo = f + cp, *gyt_hi = f + 2 * cp, *gyt_lo = f + 3 * cp, *sym_hi = f + 4 * cp, *sym_lo = sym_hi + pp2;
+        rc = launch_planes(gyp, nullptr, B, C, P, nullptr, gy_hi, gy_lo, gyt_hi, gyt_lo, st);
+        if (rc) return rc;
+        rc = tc2::launch_tc2("ppm gS (tcgen05)", B, P, P, C, gyt_hi, gyt_lo, sv.vt_hi, sv.vt_lo, TcStGradS4{gS, sv.S, P, act}, st);
+        if (rc > 0) return rc;
+        if (rc == 0) {
+            // gv̂[c][j] = Σ_i gy[c][i] A[i][j]; A is symmetric, so the B operand row j is row j of the saved relu^γ(S) planes
+            rc = tc2::launch_tc2("ppm gvh (tcgen05)", B, C, P, P, gy_hi, gy_lo, sv.a_hi, sv.a_lo, TcStN{gvh, C, P}, st);
+            if (rc) return rc < 0 ? PP_ERR_CUDA : rc;
+            dim3 sg((P + 31) / 32, (P + 31) / 32, (unsigned)B), sb(32, 8);
+            PP_LAUNCH("ppm sym planes", st, sym_planes_kernel<<<sg, sb, 0, st>>>(gS, P, sym_hi, sym_lo));
+            rc = check_launch("ppm sym planes");
+            if (rc) return rc;
+            rc = tc2::launch_tc2("ppm gxh (tcgen05)", B, C, P, P, sv.x_hi, sv.x_lo, sym_hi, sym_lo, TcStN{gxh, C, P}, st);
+            if (rc) return rc < 0 ? PP_ERR_CUDA : rc;
+        } else {
+            rc = launch_tc("ppm gS (tcgen05)", B, P, P, C, TcLdT{gyp, C, P}, TcLdT{sv.vh, C, P}, TcStGradS{gS, sv.S, P, act}, st);
+            if (rc) return rc;
+            rc = launch_tc("ppm gvh (tcgen05)", B, C, P, P, TcLdN{gyp, C, P}, TcLdActN{sv.S, P, act}, TcStN{gvh, C, P}, st);
+            if (rc) return rc;
+            rc = launch_tc("ppm gxh (tcgen05)", B, C, P, P, TcLdN{sv.xh, C, P}, TcLdSymN{gS, P}, TcStN{gxh, C, P}, st);
+            if (rc) return rc;
+        }
+        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gxh, sv.xh, nullptr, sv.nx, C, P, d_feat_sim));
+        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gvh, sv.vh, nullptr, sv.nv, C, P, d_val));
+        return check_launch("ppm normbwd(in)");
     }
     // gS[i][j] = (Σ_c gy[c][i] v̂[c][j]) A'(S[i][j])
     if (use_tensor_cores(P)) {

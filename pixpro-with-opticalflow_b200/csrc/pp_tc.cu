@@ -25,8 +25,10 @@ struct LoadRowK {  // row-major [rows, K], k contiguous
 };
 
 struct StoreC {
+    static constexpr bool kAux = false;
     float* c;
     int M, N;
+    __device__ __forceinline__ void store4(int64_t b, int m, int n, float4 v) const { st4_guard(c + (b * M + m) * (int64_t)N + n, n, N, v); }
     __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
         float* q = c + (b * M + m) * (int64_t)N + n;
         if (n + 15 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {

@@ -290,9 +290,22 @@ struct TcLdT {  // transposed: operand row = spatial index i, k = channel c; mem
         return v;
     }
 };
+// 4 consecutive columns n..n+3 of row m (the TMA-fed kernel's epilogue, pp_tc2.cuh): one 16-byte store when aligned
+__device__ __forceinline__ void st4_guard(float* q, int n, int N, float4 v) {
+    if (n + 3 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+        *reinterpret_cast<float4*>(q) = v;
+    } else {
+        q[0] = v.x;
+        if (n + 1 < N) q[1] = v.y;
+        if (n + 2 < N) q[2] = v.z;
+        if (n + 3 < N) q[3] = v.w;
+    }
+}
 struct TcStN {  // out[b][m][n..n+15]
+    static constexpr bool kAux = false;
     float* out;
     int M, N;
+    __device__ __forceinline__ void store4(int64_t b, int m, int n, float4 v) const { st4_guard(out + (b * M + m) * (int64_t)N + n, n, N, v); }
     __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
         float* q = out + (b * M + m) * (int64_t)N + n;
         if (n + 15 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {

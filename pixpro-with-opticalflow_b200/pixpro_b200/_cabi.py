@@ -37,7 +37,7 @@ SIGNATURES = {
     "pp_flow_stage": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _l, _vp]),
     "pp_calc_mask_ratio": (_i, [_vp, _l, _i, _i, _vp, _vp]),
     "pp_add_optical_flow": (_i, [_vp, _l, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
-    "pp_regression_loss_workspace": (_l, [_l, _i]),
+    "pp_regression_loss_workspace": (_l, [_l, _i, _i]),
     "pp_regression_loss": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _d, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pp_regression_loss_pair": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _d, _i,

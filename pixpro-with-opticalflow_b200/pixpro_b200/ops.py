@@ -329,7 +329,7 @@ class _RegressionLoss(torch.autograd.Function):
         m = _mask_u8(mask, "mask") if mask is not None else None
         H_orig, W_orig = size
         L = _cabi.lib()
-        ws = torch.empty((L.pp_regression_loss_workspace(B, G),), device=dev, dtype=torch.uint8)
+        ws = torch.empty((L.pp_regression_loss_workspace(B, C, G),), device=dev, dtype=torch.uint8)
         loss = torch.empty((), device=dev, dtype=torch.float32)
         pos_num = torch.empty((B,), device=dev, dtype=torch.float32)
         pos_mean = torch.empty((B,), device=dev, dtype=torch.float32)
@@ -409,7 +409,7 @@ class _RegressionLossPair(torch.autograd.Function):
                 Hin, Win = f.shape[-2:]
         H_orig, W_orig = size
         L = _cabi.lib()
-        wsz = L.pp_regression_loss_workspace(B, G)
+        wsz = L.pp_regression_loss_workspace(B, C, G)
         ws = [torch.empty((wsz,), device=dev, dtype=torch.uint8) for _ in range(2)]
         loss = torch.empty((2,), device=dev, dtype=torch.float32)
         pos_num = torch.empty((2, B), device=dev, dtype=torch.float32)

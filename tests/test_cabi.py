@@ -52,7 +52,7 @@ def test_abi_version_and_size_queries():
     from pixpro_b200 import _cabi
     L = _cabi.lib()
     assert L.pp_abi_version() == 1
-    assert L.pp_regression_loss_workspace(64, 7) == (5 * 64 * 49 + 2 * 64 + 64 * 7) * 4
+    assert L.pp_regression_loss_workspace(64, 256, 7) == (5 * 64 * 49 + 2 * 64 + 64 * 7) * 4
     assert L.pp_ppm_saved_bytes(2, 256, 49) == (3 * 2 * 49 + 2 * 49 * 49) * 4
     assert L.pp_ppm_bwd_workspace(2, 256, 49) == (3 * 2 * 256 * 49 + 2 * 49 * 49) * 4
 

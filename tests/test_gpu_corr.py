@@ -82,6 +82,14 @@ def test_corr_vs_oracle(orc, B, D, h, w, L, r):
 def test_corr_empty_batch_and_errors():
     from pixpro_b200 import ops
     from pixpro_b200._cabi import PixProB200Error
+    # a pyramid level with a single row or column: the reference divides by (size - 1) = 0 there (utils.py:68-69) and
+    # samples NaN coordinates; the kernel refuses instead of reproducing that
+    f = torch.randn(1, 16, 6, 10, device=DEV)
+    pyr = [ops.corr_volume(f, f).view(60, 1, 6, 10)]
+    for _ in range(2):
+        pyr.append(ops.corr_pool(pyr[-1]))
+    with pytest.raises(PixProB200Error):
+        ops.corr_lookup(pyr, torch.zeros(1, 2, 6, 10, device=DEV), 2)
     z = torch.zeros(0, 16, 8, 8, device=DEV)
     assert tuple(ops.corr_volume(z, z).shape) == (0, 64, 64)
     with pytest.raises((PixProB200Error, AssertionError)):
