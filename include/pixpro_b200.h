@@ -177,10 +177,13 @@ PP_API int pp_ppm_bwd(const float* feat, const float* val, const float* out, con
 
 /* ---- value transform of the PPM: 1x1 convolution (contrast/models/PixPro.py:21-23,300,343) ---
  * x [B,Cin,P], w [Cout,Cin], bias [Cout] or NULL -> y [B,Cout,P]; backward: dy -> dx (NULL to
- * skip), dw, db (NULL to skip).  One tcgen05 3xTF32 GEMM each over the joint (sample,pixel) index;
- * workspace: pp_conv1x1_bwd_workspace() bytes (split-K partials of dw).                       */
+ * skip), dw, db (NULL to skip).  One tcgen05 3xTF32 GEMM each: per sample through the TMA-fed kernel
+ * (csrc/pp_tc2.cuh) over hi / lo planes written into the workspace when P >= 128 and Cin, Cout, P are multiples of 4,
+ * else over the joint (sample,pixel) index.  workspace: pp_conv1x1_fwd_workspace() bytes for the forward (may be 0 -> NULL),
+ * pp_conv1x1_bwd_workspace() bytes for the backward (operand planes, per-sample / split-K partials of dw).        */
+PP_API int64_t pp_conv1x1_fwd_workspace(int64_t B, int Cin, int Cout, int P);
 PP_API int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B, int Cin, int Cout, int P, float* y,
-                          void* stream);
+                          void* workspace, void* stream);
 PP_API int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P);
 PP_API int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
                           float* dw, float* db, void* workspace, void* stream);

@@ -13,6 +13,7 @@
 // fp32-accurate (3xTF32, ~1e-6 relative), checked against torch in tests/test_gpu_tc.py.
 #include "pp_common.cuh"
 #include "pp_tc.cuh"
+#include "pp_tc2.cuh"
 
 namespace pp {
 
@@ -159,24 +160,116 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __rest
 
 constexpr int kWgradSplitK = 128;  // joint indices per split
 
+// ---- TMA-fed route (pp_tc2.cuh): per-sample contractions over pre-split hi / lo planes ------------------------------------
+//     y [b][o][p] = Σ_c W[o][c] x^T[b][p][c] + bias[o]       A = W planes (shared by every sample), B = transposed planes of x
+//     dx[b][c][p] = Σ_o W^T[c][o] dy^T[b][p][o]              A = W^T planes,                        B = transposed planes of dy
+//     dW[o][c]    = Σ_b Σ_p dy[b][o][p] x[b][c][p]           per sample: A = dy planes, B = x planes; deterministic sum over b
+// One pass per activation tensor writes its planes (act_planes_kernel); the weight planes are a 256 x 256 transpose / split.
+static inline bool conv_tc2(int Cin, int Cout, int P) {
+    static const int off = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
+    return !off && use_tensor_cores(P) && Cin % 4 == 0 && Cout % 4 == 0 && P % 4 == 0;
+}
+// u [B,C,P] -> split planes [B,C,P] (hi, lo; optional) and transposed split planes [B,P,C] (thi, tlo; optional).
+// grid (ceil(P/32), ceil(C/32), B), block (32, 8).
+__global__ void __launch_bounds__(256) act_planes_kernel(const float* __restrict__ u, int C, int P, float* __restrict__ hi,
+                                                          float* __restrict__ lo, float* __restrict__ thi, float* __restrict__ tlo) {
+    __shared__ float t[32][33];
+    const int64_t b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int p = p0 + threadIdx.x;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int c = c0 + r;
+        float v = 0.0f;
+        if (c < C && p < P) {
+            const int64_t o = (b * C + c) * (int64_t)P + p;
+            v = __ldg(u + o);
+            if (hi) {
+                float h, l;
+                tc2::split1(v, h, l);
+                hi[o] = h;
+                lo[o] = l;
+            }
+        }
+        t[r][threadIdx.x] = v;
+    }
+    if (!thi) return;
+    __syncthreads();
+    const int c = c0 + threadIdx.x;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int q = p0 + r;
+        if (c < C && q < P) {
+            float h, l;
+            tc2::split1(t[threadIdx.x][r], h, l);
+            const int64_t o = (b * P + q) * (int64_t)C + c;
+            thi[o] = h;
+            tlo[o] = l;
+        }
+    }
+}
+static int launch_act_planes(const float* u, int64_t B, int C, int P, float* hi, float* lo, float* thi, float* tlo, cudaStream_t st) {
+    dim3 grid((P + 31) / 32, (C + 31) / 32, (unsigned)B), block(32, 8);
+    PP_LAUNCH("conv1x1 planes", st, act_planes_kernel<<<grid, block, 0, st>>>(u, C, P, hi, lo, thi, tlo));
+    return check_launch("conv1x1 planes");
+}
+struct TcStBias {  // out[b][m][n..n+3] = v + bias[m]
+    static constexpr bool kAux = false;
+    float* out;
+    const float* bias;  // may be null
+    int M, N;
+    __device__ __forceinline__ void store4(int64_t b, int m, int n, float4 v) const {
+        const float bv = bias ? __ldg(bias + m) : 0.0f;
+        st4_guard(out + (b * M + m) * (int64_t)N + n, n, N, make_float4(v.x + bv, v.y + bv, v.z + bv, v.w + bv));
+    }
+    __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
+        const float bv = bias ? __ldg(bias + m) : 0.0f;
+        float* q = out + (b * M + m) * (int64_t)N + n;
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+            if (n + u < N) q[u] = v[u] + bv;
+    }
+};
+
 }  // namespace pp
 
 using namespace pp;
 
 extern "C" {
 
+int64_t pp_conv1x1_fwd_workspace(int64_t B, int Cin, int Cout, int P) {
+    if (!conv_tc2(Cin, Cout, P)) return 0;
+    return (2 * B * (int64_t)P * Cin + 2 * (int64_t)Cout * Cin) * (int64_t)sizeof(float);  // transposed planes of x, planes of W
+}
+
 int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B, int Cin, int Cout, int P, float* y,
-                   void* stream) {
+                   void* workspace, void* stream) {
     PP_REQUIRE(x && w && y, "pp_conv1x1_fwd: null pointer");
     PP_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && P > 0 && B * P < (1 << 24), "pp_conv1x1_fwd: bad shape");
     const int NP = (int)(B * P);
+    if (conv_tc2(Cin, Cout, P) && workspace) {
+        cudaStream_t st = (cudaStream_t)stream;
+        float* xt_hi = (float*)workspace;
+        float* xt_lo = xt_hi + B * (int64_t)P * Cin;
+        float* w_hi = xt_lo + B * (int64_t)P * Cin;
+        float* w_lo = w_hi + (int64_t)Cout * Cin;
+        int rc = launch_act_planes(x, B, Cin, P, nullptr, nullptr, xt_hi, xt_lo, st);
+        if (rc) return rc;
+        rc = tc2::launch_split(w, (int64_t)Cout * Cin, w_hi, w_lo, st);
+        if (rc) return rc;
+        rc = tc2::launch_tc2("conv1x1 fwd (tcgen05)", B, Cout, P, Cin, w_hi, w_lo, xt_hi, xt_lo, TcStBias{y, bias, Cout, P}, st, true);
+        if (rc >= 0) return rc;
+    }
     return launch_tc("conv1x1 fwd (tcgen05)", 1, Cout, NP, Cin, LdW{w, Cout, Cin}, LdNC{x, Cin, NP, make_divp(P)},
                      StCN{y, bias, Cout, NP, make_divp(P)}, (cudaStream_t)stream);
 }
 
 int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P) {
     const int64_t splits = (B * P + kWgradSplitK - 1) / kWgradSplitK;
-    return (splits * Cin * Cout + B * Cout) * (int64_t)sizeof(float);  // split-K partials of dW, then the row sums of db
+    int64_t f = splits * Cin * Cout + B * Cout;  // split-K partials of dW, then the row sums of db
+    if (conv_tc2(Cin, Cout, P))  // dgrad: transposed planes of dy, planes of W^T; wgrad: planes of dy and x, per-sample partials of dW
+        f += 2 * B * (int64_t)P * Cout + 2 * (int64_t)Cin * Cout + 2 * B * (int64_t)Cout * P + 2 * B * (int64_t)Cin * P + B * (int64_t)Cout * Cin;
+    return f * (int64_t)sizeof(float);
 }
 
 int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
@@ -186,6 +279,36 @@ int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, i
     cudaStream_t st = (cudaStream_t)stream;
     const int NP = (int)(B * P);
     int rc;
+    const int64_t base_f = (int64_t)((NP + kWgradSplitK - 1) / kWgradSplitK) * Cin * Cout + B * Cout;
+    const bool tma = conv_tc2(Cin, Cout, P);
+    float* f = (float*)workspace + base_f;  // TMA-route regions, disjoint per gradient (they may run on different streams)
+    float *dyt_hi = f, *dyt_lo = dyt_hi + B * (int64_t)P * Cout, *wt_hi = dyt_lo + B * (int64_t)P * Cout, *wt_lo = wt_hi + (int64_t)Cin * Cout;
+    float *dy_hi = wt_lo + (int64_t)Cin * Cout, *dy_lo = dy_hi + B * (int64_t)Cout * P, *x_hi = dy_lo + B * (int64_t)Cout * P,
+          *x_lo = x_hi + B * (int64_t)Cin * P, *part_b = x_lo + B * (int64_t)Cin * P;
+    if (dx && tma) {
+        rc = launch_act_planes(dy, B, Cout, P, nullptr, nullptr, dyt_hi, dyt_lo, st);
+        if (rc) return rc;
+        rc = launch_act_planes(w, 1, Cout, Cin, nullptr, nullptr, wt_hi, wt_lo, st);  // W [Cout][Cin] -> W^T planes [Cin][Cout]
+        if (rc) return rc;
+        rc = tc2::launch_tc2("conv1x1 dgrad (tcgen05)", B, Cin, P, Cout, wt_hi, wt_lo, dyt_hi, dyt_lo, TcStBias{dx, nullptr, Cin, P}, st, true);
+        if (rc > 0) return rc;
+        if (rc == 0) dx = nullptr;  // done
+    }
+    if (dw && tma) {
+        rc = launch_act_planes(dy, B, Cout, P, dy_hi, dy_lo, nullptr, nullptr, st);
+        if (rc) return rc;
+        rc = launch_act_planes(x, B, Cin, P, x_hi, x_lo, nullptr, nullptr, st);
+        if (rc) return rc;
+        rc = tc2::launch_tc2("conv1x1 wgrad (tcgen05)", B, Cout, Cin, P, dy_hi, dy_lo, x_hi, x_lo, TcStN{part_b, Cout, Cin}, st);
+        if (rc > 0) return rc;
+        if (rc == 0) {
+            const int total = Cout * Cin;
+            PP_LAUNCH("conv1x1 wgrad reduce", st, conv_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(part_b, (int)B, total, dw));
+            rc = check_launch("conv_wgrad_reduce_kernel");
+            if (rc) return rc;
+            dw = nullptr;  // done
+        }
+    }
     if (dx) {
         rc = launch_tc("conv1x1 dgrad (tcgen05)", 1, Cin, NP, Cout, LdWT{w, Cout, Cin}, LdNC{dy, Cout, NP, make_divp(P)},
                        StCN{dx, nullptr, Cin, NP, make_divp(P)}, st);

@@ -120,7 +120,7 @@ struct EpNoAux {
 // accumulators the ring already holds the next tile's first chunks; barriers: full/empty per stage, acc_full/acc_empty.
 // BLO = false: the B operand is exact in TF32 (e.g. a 0/1 mask) — its lo plane is neither loaded nor multiplied.
 template <int TK, bool BLO, class EP>
-__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int batch, EP ep) {
+__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int batch, int a_bcast, EP ep) {
     using C = Cfg<TK>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t tc2_smem_raw[];
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
                     if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage have completed
                     const uint32_t st = base + s * C::kStageBytes;
                     mbar_arrive_expect_tx(&full[s], BLO ? C::kStageBytes : C::kStageBytes - C::kBTile);
-                    tma_load_3d(st, &maps.a_hi, c * TK, mt * TM, b, &full[s]);
-                    tma_load_3d(st + C::kATile, &maps.a_lo, c * TK, mt * TM, b, &full[s]);
+                    tma_load_3d(st, &maps.a_hi, c * TK, mt * TM, a_bcast ? 0 : b, &full[s]);
+                    tma_load_3d(st + C::kATile, &maps.a_lo, c * TK, mt * TM, a_bcast ? 0 : b, &full[s]);
                     tma_load_3d(st + 2 * C::kATile, &maps.b_hi, c * TK, nt * TN, b, &full[s]);
                     if (BLO) tma_load_3d(st + 2 * C::kATile + C::kBTile, &maps.b_lo, c * TK, nt * TN, b, &full[s]);
                 }
@@ -328,7 +328,7 @@ static inline bool applicable(int K, const void* a, const void* b, const void* c
 }
 
 template <int TK, bool BLO, class EP>
-static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int M, int N, int K, EP ep, cudaStream_t st) {
+static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int M, int N, int K, int a_bcast, EP ep, cudaStream_t st) {
     auto kern = tc2_gemm_kernel<TK, BLO, EP>;
     static unsigned long long opted = 0;  // per template instantiation, one bit per device
     if (smem_opt_in(kern, (int)SMEM_BYTES, opted) != cudaSuccess) {
@@ -337,25 +337,28 @@ static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, 
     }
     const int64_t ntiles = batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN);
     const unsigned grid = (unsigned)(ntiles < num_sms() ? ntiles : num_sms());
-    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, (int)batch, ep));
+    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, (int)batch, a_bcast, ep));
     return check_launch(what);
 }
 
-// Planes: A_hi/A_lo [batch][M][K], B_hi/B_lo [batch][N][K].  Returns -1 when not applicable (caller uses pp_tc.cuh's kernel).
+// Planes: A_hi/A_lo [batch][M][K] (or [M][K] shared by every batch entry: a_bcast), B_hi/B_lo [batch][N][K].
+// Returns -1 when not applicable (caller uses pp_tc.cuh's kernel).
 // PIXPRO_B200_TC2: 0 = off, 1 (default) = 64-byte chunks x 4 stages, 2 = 128-byte chunks x 2 stages (A/B switch).
 template <bool BLO = true, class EP>
 static inline int launch_tc2(const char* what, int64_t batch, int M, int N, int K, const float* a_hi, const float* a_lo, const float* b_hi,
-                             const float* b_lo, EP ep, cudaStream_t st) {
+                             const float* b_lo, EP ep, cudaStream_t st, bool a_bcast = false) {
     if (!applicable(K, a_hi, a_lo, b_hi, b_lo) || batch > 65535) return -1;
     if (batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN) >= (1ll << 31)) return -1;
     static const int mode = [] { const char* e = getenv("PIXPRO_B200_TC2"); return e ? atoi(e) : 1; }();
     const int tk = mode == 2 ? 32 : 16;
     Maps maps;
     memset(&maps, 0, sizeof(maps));
-    if (!make_plane_map(&maps.a_hi, a_hi, batch, M, K, TM, tk) || !make_plane_map(&maps.a_lo, a_lo, batch, M, K, TM, tk) ||
+    const int64_t abatch = a_bcast ? 1 : batch;
+    if (!make_plane_map(&maps.a_hi, a_hi, abatch, M, K, TM, tk) || !make_plane_map(&maps.a_lo, a_lo, abatch, M, K, TM, tk) ||
         !make_plane_map(&maps.b_hi, b_hi, batch, N, K, TN, tk) || !make_plane_map(&maps.b_lo, BLO ? b_lo : b_hi, batch, N, K, TN, tk))
         return -1;
-    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, M, N, K, ep, st) : launch_cfg<16, BLO>(what, maps, batch, M, N, K, ep, st);
+    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, M, N, K, a_bcast ? 1 : 0, ep, st)
+                    : launch_cfg<16, BLO>(what, maps, batch, M, N, K, a_bcast ? 1 : 0, ep, st);
 }
 
 static inline int launch_split(const float* x, int64_t n, float* hi, float* lo, cudaStream_t st) {

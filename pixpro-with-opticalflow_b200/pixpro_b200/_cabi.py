@@ -51,7 +51,8 @@ SIGNATURES = {
     "pp_ppm_fwd": (_i, [_vp, _vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _vp]),
     "pp_ppm_bwd_workspace": (_l, [_l, _i, _i]),
     "pp_ppm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
-    "pp_conv1x1_fwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp]),
+    "pp_conv1x1_fwd_workspace": (_l, [_l, _i, _i, _i]),
+    "pp_conv1x1_fwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp]),
     "pp_conv1x1_bwd_workspace": (_l, [_l, _i, _i, _i]),
     "pp_conv1x1_bwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pp_tc_gemm_nt": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp]),

@@ -556,8 +556,10 @@ class _Conv1x1(torch.autograd.Function):
         Cout = w2.shape[0]
         assert w2.shape[1] == Cin
         y = torch.empty((B, Cout) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32)
+        nws = _cabi.lib().pp_conv1x1_fwd_workspace(B, Cin, Cout, P)
+        ws = torch.empty((nws,), device=x.device, dtype=torch.uint8) if nws else None
         with torch.cuda.device(x.device):
-            _cabi.check(_cabi.lib().pp_conv1x1_fwd(_ptr(x), _ptr(w2), _ptr(b), B, Cin, Cout, P, _ptr(y), _stream()),
+            _cabi.check(_cabi.lib().pp_conv1x1_fwd(_ptr(x), _ptr(w2), _ptr(b), B, Cin, Cout, P, _ptr(y), _ptr(ws), _stream()),
                         "pp_conv1x1_fwd")
         ctx.save_for_backward(x, w2)
         ctx.has_bias = bias is not None
