@@ -582,6 +582,17 @@ def run_b200(a):
             except Exception as e:  # a failing side configuration must not take the headline down with it
                 extra[name] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
+    # the whole DDP pre-training step (BASELINE configs[2]) beside the pixel path, so that the driver's 1/2/4/8-GPU scaling
+    # runs carry it: every rank takes part (NCCL gradient all-reduce), a few steps only
+    pre = None
+    if not a.no_extra and default_workload:
+        try:
+            pre = measure_pretrain(ctx, steps=6, warmup=3)
+            for k in ("higher_is_better", "scaling", "vs_baseline", "data"):
+                pre.pop(k, None)
+        except Exception as e:
+            pre = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
     tgb = None
     if not a.no_extra and ctx.rank == 0:
         try:
@@ -591,7 +602,7 @@ def run_b200(a):
     if ctx.world > 1:
         dist.barrier()
     if ctx.rank != 0:
-        if ctx.world > 1:
+        if dist.is_initialized():
             dist.destroy_process_group()
         return
     line = {
@@ -621,21 +632,23 @@ def run_b200(a):
         line["config"]["flow_stage"] = "sparse correspondence (pp_sparse_corr): evaluated at the loss's grid centres only"
     if extra:
         line["configs"] = extra
+    if pre is not None:
+        line["pretrain_ddp"] = pre
     if tgb is not None:
         line["torch_gpu_baseline"] = tgb
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_arm(a.batch, a.n_frames, a.grid, steps=8, warmup=1, budget_s=25.0, sample=a.cpu_sample)
     emit(line)
-    if ctx.world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------ the DDP pre-training step
 
-def run_pretrain(ctx):
-    """`--pretrain`: the whole pre-training step of main_pretrain.py (drop-in contrast.models.PixPro around an eager
-    PyTorch ResNet-50 + DDP gradient all-reduce over NCCL + LARS + this repo's flow stage), synthetic data,
-    BASELINE configs[2] shape.  metric = frames/s = B * world * n_frames / step time (max over ranks)."""
+def measure_pretrain(ctx, steps, warmup):
+    """The whole pre-training step of main_pretrain.py (drop-in contrast.models.PixPro around an eager PyTorch ResNet-50 +
+    DDP gradient all-reduce over NCCL + LARS + this repo's flow stage), synthetic data, BASELINE configs[2] shape.
+    Collective: every rank calls it.  frames/s = B * world * n_frames / step time (max over ranks); rank 0 gets the record."""
     import torch
     import torch.distributed as dist
     import main_pretrain as MP
@@ -646,7 +659,8 @@ def run_pretrain(ctx):
         dist.init_process_group("nccl", rank=0, world_size=1, device_id=ctx.dev)
     opt = MP.synthetic_options(batch_size=a.pretrain_batch, n_frames=a.pretrain_frames, amp="bf16")
     trainer = MP.SyntheticTrainer(opt, ctx.dev)
-    for _ in range(max(3, a.warmup)):
+    warmup = max(3, warmup)
+    for _ in range(warmup):
         trainer.step()
     sampler = ClockSampler(ctx.local)
     ctx.barrier()
@@ -654,23 +668,33 @@ def run_pretrain(ctx):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         trainer.step()
     e1.record()
     ctx.barrier()
     clocks = sampler.stop() if ctx.rank == 0 else None
-    ms = max_over_ranks(e0.elapsed_time(e1), ctx.world, ctx.dev) / a.steps
+    ms = max_over_ranks(e0.elapsed_time(e1), ctx.world, ctx.dev) / steps
+    fps = a.pretrain_batch * ctx.world * a.pretrain_frames / (ms * 1e-3)
+    rec = {"metric": "PixPro+OF pretrain frames/sec (whole DDP step: ResNet-50 + projector on cuDNN/PyTorch, pixel path + "
+                     "EMA + LARS on this repo's kernels, NCCL gradient all-reduce)",
+           "value": fps, "unit": "frames/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": f"main_pretrain.py --synthetic: PixPro+OF ResNet-50, n_frames={a.pretrain_frames}, "
+                                  f"batch {a.pretrain_batch}/GPU, 224^2 crops, 7x7 grid, bf16 autocast, DDP (BASELINE.json configs[2])",
+                      "per_gpu_batch": a.pretrain_batch, "n_frames": a.pretrain_frames, "flow_stage": trainer.flow_mode},
+           "samples_per_s": fps / a.pretrain_frames, "clocks": clocks, "gpu_launches": trainer.launches(),
+           "step_breakdown_ms": trainer.breakdown()}
+    del trainer
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_pretrain(ctx):
+    """`--pretrain`: the DDP pre-training step as the headline line."""
+    import torch.distributed as dist
+    rec = measure_pretrain(ctx, ctx.a.steps, ctx.a.warmup)
     if ctx.rank == 0:
-        fps = a.pretrain_batch * ctx.world * a.pretrain_frames / (ms * 1e-3)
-        emit({"metric": "PixPro+OF pretrain frames/sec (whole DDP step: ResNet-50 + projector on cuDNN/PyTorch, pixel path + "
-                        "EMA + LARS on this repo's kernels, NCCL gradient all-reduce)",
-              "value": fps, "unit": "frames/s", "n_gpus": ctx.world, "steps": a.steps, "warmup": max(3, a.warmup),
-              "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-              "config": {"workload": f"main_pretrain.py --synthetic: PixPro+OF ResNet-50, n_frames={a.pretrain_frames}, "
-                                     f"batch {a.pretrain_batch}/GPU, 224^2 crops, 7x7 grid, bf16 autocast, DDP (BASELINE.json configs[2])",
-                         "per_gpu_batch": a.pretrain_batch, "n_frames": a.pretrain_frames, "flow_stage": trainer.flow_mode},
-              "samples_per_s": fps / a.pretrain_frames, "clocks": clocks, "gpu_launches": trainer.launches(),
-              "step_breakdown_ms": trainer.breakdown()})
+        emit(rec)
     if dist.is_initialized():
         dist.destroy_process_group()
 

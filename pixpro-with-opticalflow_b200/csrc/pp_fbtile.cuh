@@ -549,20 +549,10 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
     a.dw2 = make_div<DM_FAST>((float)(W - 1) / 2.0f); a.dh2 = make_div<DM_FAST>((float)(H - 1) / 2.0f);
     static const int variant = [] { const char* e = getenv("PIXPRO_B200_FBTILE"); return e ? atoi(e) : 1; }();
     if (variant == 0) return -1;  // disabled: gather kernels
-    if (W == 1280 && H == 720) {  // the published frame size
-        switch (variant) {
-            case 2: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 1>(a, B, st);
-            case 3: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 5>(a, B, st);
-            case 4: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 7>(a, B, st);
-            case 5: return launch_cfg<64, 48, 96, 72, 3, 1280, 720, 5>(a, B, st);
-            case 6: return launch_cfg<64, 48, 96, 72, 3, 1280, 720, 7>(a, B, st);
-            case 7: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 12>(a, B, st);
-            case 8: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 14>(a, B, st);
-            case 9: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 21>(a, B, st);
-            case 10: return launch_cfg<64, 48, 96, 72, 4, 1280, 720, 23>(a, B, st);
-            default: return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
-        }
-    }
+    // the published frame size.  The OPT switches of fbbox_kernel (immediate-offset addressing, magic-number floor, lazy tap
+    // origin, rolled row loop, opaque row pointers) were built, verified bit-exact and measured within +-1.5 % of each other
+    // (profiles/r02_a_fb_variants.txt, gpurun_out/r02_g_fb.txt: 355-364 us at B=64): only the plain kernel is instantiated.
+    if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
     if (H % 48 == 0) return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
     if (H % 32 == 0) return launch_cfg<64, 32, 96, 56, 4>(a, B, st);
     return -1;
