@@ -226,6 +226,35 @@ PP_API int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t batch
 PP_API int64_t pp_tc_gemm_nt_workspace(int64_t batch, int M, int N, int K);
 PP_API int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* workspace, void* stream);
 
+/* ---- synchronised batch normalisation in three launches per direction (csrc/pp_syncbn.cu) ----------------------------
+ * The reference converts every BatchNorm of encoder / projector to torch.nn.SyncBatchNorm (contrast/models/PixPro.py:289-292,
+ * 315-317) and trains under DDP (main_pretrain.py:78); torch issues ~10 launches + one all_gather per layer and direction.
+ * x, y, dy, dx: logical [N, C, HW] in `layout` (PP_LAYOUT_NCHW contiguous, or PP_LAYOUT_NHWC = torch.channels_last memory),
+ * element type `dtype` (PP_DTYPE_F32 / PP_DTYPE_BF16); every statistic is fp32.  workspace: pp_bn_workspace(C) bytes, ZEROED
+ * once by the caller (holds a completion ticket that every launch leaves at 0), one per stream in flight.
+ *   pp_bn_stats     -> stats[0..C) = local mean, [C..2C) = local M2 = sum (x - mean)^2, [2C] = local count; the caller
+ *                      all-gathers this ONE vector across ranks (nranks rows of 2C+1)
+ *   pp_bn_apply     global mean / invstd from the gathered rows (parallel-variance combination); running = (1-momentum)
+ *                   running + momentum stat (unbiased variance); y = (x - mean) invstd weight + bias; save_mean [C] and
+ *                   save_invstd [C+1] (its last element = the total count) for the backward
+ *   pp_bn_bwd_stats -> sums[0..C) = sum dy, [C..2C) = sum dy (x - mean) (the caller all-reduces); grad_weight / grad_bias [C]
+ *                      from the LOCAL sums (DDP reduces parameter gradients itself), either may be NULL
+ *   pp_bn_bwd_apply dx = (dy - mean(dy) - (x - mean) invstd^2 mean(dy (x - mean))) invstd weight; total_count: DEVICE pointer
+ *                   to the total element count (= save_invstd[C] of the forward)                                           */
+#define PP_LAYOUT_NCHW 0
+#define PP_LAYOUT_NHWC 1
+#define PP_DTYPE_F32 0
+#define PP_DTYPE_BF16 1
+PP_API int64_t pp_bn_workspace(int C);
+PP_API int pp_bn_stats(const void* x, int64_t N, int C, int HW, int layout, int dtype, void* workspace, float* stats, void* stream);
+PP_API int pp_bn_apply(const void* x, void* y, int64_t N, int C, int HW, int layout, int dtype, const float* stats, int nranks, const float* weight,
+                       const float* bias, float* running_mean, float* running_var, double eps, double momentum, float* save_mean,
+                       float* save_invstd, void* stream);
+PP_API int pp_bn_bwd_stats(const void* dy, const void* x, int64_t N, int C, int HW, int layout, int dtype, const float* save_mean,
+                           const float* save_invstd, void* workspace, float* sums, float* grad_weight, float* grad_bias, void* stream);
+PP_API int pp_bn_bwd_apply(const void* dy, const void* x, void* dx, int64_t N, int C, int HW, int layout, int dtype, const float* save_mean,
+                           const float* save_invstd, const float* weight, const float* sums, const float* total_count, void* stream);
+
 /* ---- RAFT correlation volume, pyramid and lookup ----------------------------
  * The reference's torch CorrBlock (contrast/flow/corr.py:12-60; its CUDA twin `alt_cuda_corr` is not shipped).
  * pp_corr_volume : CorrBlock.corr, corr.py:52-60.  fmap1, fmap2 [B, D, h, w] -> corr [B, h*w, h*w]

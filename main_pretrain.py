@@ -51,7 +51,7 @@ def synthetic_options(**kw):
         pixpro_p=2.0, pixpro_momentum=0.99, pixpro_pos_ratio=0.7, pixpro_clamp_value=0.0, pixpro_transform_layer=1,
         pixpro_ins_loss_weight=0.0, feature_dim=256, head_type="early_return", output_dir="/tmp", num_instances=70000,
         use_flow=True, use_flow_file=True, use_flow_frames=False, flow_up=True, flow_cat_norm=False, alpha1=0.01, alpha2=0.5,
-        flow_sparse=False, graph_momentum_branch=True, channels_last=True, debug=False, print_freq=100, local_rank=0,
+        flow_sparse=False, graph_momentum_branch=True, fast_sync_bn=True, channels_last=True, debug=False, print_freq=100, local_rank=0,
         frame_hw=(720, 1280), flow_hw=(90, 160), steps_per_epoch=500)
     a.__dict__.update(kw)
     a.use_flow = a.use_flow and a.n_frames > 1
@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--flow-sparse", action="store_true")
     ap.add_argument("--no-graph-momentum-branch", action="store_true")
+    ap.add_argument("--no-fast-syncbn", action="store_true", help="torch.nn.SyncBatchNorm instead of pixpro_b200.syncbn.FastSyncBatchNorm")
     ap.add_argument("--print-freq", type=int, default=10)
     a = ap.parse_args()
     if not a.synthetic:
@@ -228,7 +229,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     args = synthetic_options(batch_size=a.batch_size, n_frames=a.n_frames, amp=a.amp, flow_sparse=a.flow_sparse,
-                             graph_momentum_branch=not a.no_graph_momentum_branch, print_freq=a.print_freq, local_rank=local)
+                             graph_momentum_branch=not a.no_graph_momentum_branch, fast_sync_bn=not a.no_fast_syncbn,
+                             print_freq=a.print_freq, local_rank=local)
     tr = SyntheticTrainer(args, dev)
     for _ in range(a.warmup):
         tr.step()

@@ -8,6 +8,8 @@ PixPro.featprop; module-level regression_loss / add_optical_flow; state_dict key
 encoder.* projector.* encoder_k.* projector_k.* value_transform.* (checkpoint-compatible).
 The backbone, projector and value_transform stay on cuDNN/cuBLAS through PyTorch.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -123,8 +125,11 @@ class PixPro(BaseModel):
         self.projector_k = Proj_Head()
         self._init_momentum_pair(self.encoder, self.encoder_k)
         self._init_momentum_pair(self.projector, self.projector_k)
+        # opt-in (args.fast_sync_bn / PIXPRO_B200_FAST_SYNCBN=1): the same layers on pixpro_b200.syncbn.FastSyncBatchNorm
+        # (three launches and one all-reduce per layer and direction instead of torch's ~10 launches and an all_gather)
+        self.fast_sync_bn = bool(getattr(args, "fast_sync_bn", False)) or os.environ.get("PIXPRO_B200_FAST_SYNCBN", "0") == "1"
         for m in (self.encoder, self.encoder_k, self.projector, self.projector_k):
-            nn.SyncBatchNorm.convert_sync_batchnorm(m)
+            self._sync_bn(m)
 
         # momentum schedule counters (PixPro.py:294-295)
         self.K = int(args.num_instances * 1. / get_world_size() / args.batch_size * args.epochs)
@@ -146,8 +151,15 @@ class PixPro(BaseModel):
             self.predictor = Pred_Head()
             self._init_momentum_pair(self.projector_instance, self.projector_instance_k)
             for m in (self.projector_instance, self.projector_instance_k, self.predictor):
-                nn.SyncBatchNorm.convert_sync_batchnorm(m)
+                self._sync_bn(m)
             self.avgpool = nn.AvgPool2d(7, stride=1)
+
+    def _sync_bn(self, m):
+        """PixPro.py:289-292, 315-317 (in place: every module passed is a container)."""
+        nn.SyncBatchNorm.convert_sync_batchnorm(m)
+        if self.fast_sync_bn:
+            from pixpro_b200.syncbn import convert_fast_sync_batchnorm
+            convert_fast_sync_batchnorm(m)
 
     @staticmethod
     def _init_momentum_pair(online, momentum):

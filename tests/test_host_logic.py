@@ -315,3 +315,94 @@ def test_resnet_rejects_architectures_outside_the_scope():
         resnet.resnet50(head_type='pass')                            # the reference pools and flattens there: not provided
     with pytest.raises(TypeError):
         resnet.resnet50(no_such_option=1)
+
+
+# ---- FastSyncBatchNorm: the collective wiring on two gloo ranks, kernels restated in torch ------------------------------
+
+def _torch_bn_kernels(syncbn):
+    """torch restatements of the four C-ABI calls of pixpro_b200.syncbn (same argument / return conventions)."""
+    def view(x, N, C):
+        return x.reshape(N, C, -1).float()
+
+    def bn_stats(x, layout, N, C, HW, ws):
+        v = view(x, N, C)
+        m = v.mean((0, 2))
+        return torch.cat([m, ((v - m[None, :, None]) ** 2).sum((0, 2)), torch.tensor([float(N * HW)])])
+
+    def bn_apply(x, layout, N, C, HW, stats, nranks, weight, bias, running_mean, running_var, eps, momentum):
+        st = stats.reshape(nranks, 2 * C + 1)
+        n = st[:, 2 * C]
+        cnt = n.sum()
+        mean = (n[:, None] * st[:, :C]).sum(0) / cnt
+        var = (st[:, C:2 * C] + n[:, None] * (st[:, :C] - mean[None]) ** 2).sum(0) / cnt
+        invstd = (var + eps).rsqrt()
+        if running_mean is not None:
+            running_mean.mul_(1 - momentum).add_(momentum * mean)
+            running_var.mul_(1 - momentum).add_(momentum * var * cnt / (cnt - 1))
+        y = (view(x, N, C) - mean[None, :, None]) * invstd[None, :, None]
+        if weight is not None:
+            y = y * weight[None, :, None] + bias[None, :, None]
+        return y.reshape(x.shape).to(x.dtype), torch.cat([mean, invstd, cnt.reshape(1)])
+
+    def bn_bwd_stats(dy, x, layout, N, C, HW, save, ws, need_w, need_b):
+        g, xm = view(dy, N, C), view(x, N, C) - save[:C][None, :, None]
+        s0, s1 = g.sum((0, 2)), (g * xm).sum((0, 2))
+        return torch.cat([s0, s1]), (s1 * save[C:2 * C] if need_w else None), (s0.clone() if need_b else None)
+
+    def bn_bwd_apply(dy, x, layout, N, C, HW, save, weight, sums):
+        mean, invstd, count = save[:C][None, :, None], save[C:2 * C][None, :, None], save[2 * C]
+        mdy = (sums[:C] / count)[None, :, None]
+        k = (sums[C:] / count)[None, :, None] * invstd * invstd
+        w = 1.0 if weight is None else weight[None, :, None]
+        return ((view(dy, N, C) - mdy - (view(x, N, C) - mean) * k) * invstd * w).reshape(x.shape).to(x.dtype)
+
+    syncbn.bn_stats, syncbn.bn_apply, syncbn.bn_bwd_stats, syncbn.bn_bwd_apply = bn_stats, bn_apply, bn_bwd_stats, bn_bwd_apply
+
+
+def _syncbn_rank_main(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "pixpro-with-opticalflow_b200"))
+    from pixpro_b200 import syncbn
+    _torch_bn_kernels(syncbn)
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn(6, 8, 5, 5, generator=g) * 2 + 1      # the global batch; rank r owns samples [3r, 3r+3)
+    dfull = torch.randn(6, 8, 5, 5, generator=g)
+    w, b = torch.rand(8, generator=g) + 0.5, torch.randn(8, generator=g)
+    x = full[3 * rank:3 * rank + 3].clone().requires_grad_(True)
+    wl, bl = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    rm, rv = torch.zeros(8), torch.ones(8)
+    y = syncbn._SyncBNFunction.apply(x, wl, bl, rm, rv, 1e-5, 0.1, None, None)
+    y.backward(dfull[3 * rank:3 * rank + 3])
+    # the single-process batch norm over the GLOBAL batch is what synchronised batch norm computes
+    xr = full.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(8), torch.ones(8)
+    yr = torch.nn.functional.batch_norm(xr, rm2, rv2, wr, br, True, 0.1, 1e-5)
+    yr.backward(dfull)
+    sl = slice(3 * rank, 3 * rank + 3)
+    ok = (torch.allclose(y, yr[sl], atol=1e-5) and torch.allclose(x.grad, xr.grad[sl], atol=1e-5) and
+          torch.allclose(rm, rm2, atol=1e-6) and torch.allclose(rv, rv2, atol=1e-5))
+    # parameter gradients are LOCAL sums (DDP reduces them): their sum over ranks is the global gradient
+    gw, gb = wl.grad.clone(), bl.grad.clone()
+    dist.all_reduce(gw); dist.all_reduce(gb)
+    ok = ok and torch.allclose(gw, wr.grad, atol=1e-4) and torch.allclose(gb, br.grad, atol=1e-4)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fast_sync_batch_norm_two_ranks_equal_global_batch_norm():
+    """world_size-2 gloo: one all-gather of the [2C+1] statistics forward and one all-reduce of the [2C] sums backward make the two
+    ranks' halves equal to batch norm over the whole batch (values, input gradients, running statistics)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_syncbn_rank_main, args=(r, 2, 29551, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
