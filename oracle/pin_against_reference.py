@@ -118,6 +118,7 @@ def main():
     gold = {}
     if opt.only_corr:
         pin_corr_block(rep, gold)
+        pin_raft(rep, gold, rflow)
         finish(rep, gold, opt)
         return
 
@@ -365,6 +366,7 @@ def main():
         gold[f"apply_general_{tag}"] = g
 
     pin_corr_block(rep, gold)
+    pin_raft(rep, gold, rflow)
 
     # ---------------- a10 / a12 / cfg 0: the whole reference model, one fwd+bwd step on CPU ----------------
     # BASELINE configs[0]: PixPro ResNet-50, n_frames=1 (no flow), batch 4, 224x224 two-view crops, 7x7 grid.  Weights come
@@ -469,6 +471,32 @@ def pin_corr_block(rep, gold):
         rep.exact(f"f4 corr lookup {tag} (L={L}, r={r})", out, ref_out)
         gold[f"corr_{tag}"] = dict(fmap1=f1.numpy(), fmap2=f2.numpy(), coords=coords.numpy(), num_levels=np.int64(L), radius=np.int64(r),
                                    level0=ref_pyr[0], out=ref_out, **{f"level{l}_sha": np.array(sha(ref_pyr[l])) for l in range(1, L)})
+
+
+def pin_raft(rep, gold, rflow):
+    """SURVEY 8(f) rank 4, the caller side: the reference's RAFT estimator (contrast/flow/raft.py:26-162, small and basic
+    variants) run on CPU with name-seeded weights (synth.seeded_init_) in eval mode; the drop-in contrast.flow.RAFT rebuilds
+    the same weights on the GPU box and must reproduce the flows (tests/test_gpu_corr.py).  The stored key list pins the
+    state_dict layout (checkpoint compatibility) on the CPU side."""
+    for tag, small, B, H, W, iters in [("small", True, 2, 128, 160, 4), ("basic", False, 1, 128, 192, 2)]:
+        args = argparse.Namespace(small=small, mixed_precision=False)
+        m = rflow.RAFT(args)
+        synth.seeded_init_(m, 300)
+        m.eval()
+        g = torch.Generator().manual_seed(310 + int(small))
+        base = torch.rand(B, 3, H, W, generator=g) * 255.0
+        # stored as float16: rounded BEFORE the reference sees them, so that the fixture holds exactly what it was given
+        im1 = base.half().float()
+        im2 = (torch.roll(base, shifts=(2, -3), dims=(2, 3)) + 4.0 * torch.rand(B, 3, H, W, generator=g)).half().float()
+        with torch.no_grad():
+            low, up = m(im1, im2, iters=iters, upsample=False, test_mode=True)
+        sd = m.state_dict()
+        rep.rows.append((f"f4 reference RAFT ({tag}, {iters} iterations, {H}x{W})",
+                         f"{len(sd)} state_dict entries, |flow| max {float(low.abs().max()):.3f} low-res px"))
+        gold[f"raft_{tag}"] = dict(small=np.bool_(small), iters=np.int64(iters), seed=np.int64(300), image1=im1.numpy().astype(np.float16),
+                                   image2=im2.numpy().astype(np.float16), flow_low=low.numpy(), flow_up_sha=np.array(sha(up.numpy())),
+                                   flow_up_absmax=np.float64(up.abs().max()), keys=np.array(list(sd.keys())),
+                                   shapes=np.array([",".join(map(str, v.shape)) for v in sd.values()]))
 
 
 def finish(rep, gold, opt):

@@ -95,6 +95,58 @@ def forward_backward_consistency(flow_fwd, flow_bwd, coords0=None, alpha_1=0.01,
 
 
 @torch.no_grad()
+def calc_optical_flow(imgs, flow_model, up=False, verbose=False):
+    """contrast/util.py:76-103: one estimate per consecutive frame pair, forward in time and backward in time (the backward
+    links listed from the last frame to the first) -> two [num_img-1, nb, 2, h, w] tensors.  `up`: the model's up-sampled
+    prediction instead of its 1/8-resolution one."""
+    assert len(imgs) >= 2
+    flow_model.eval()
+    pick = 1 if up else 0
+    rev = list(imgs)[::-1]
+    fwd = torch.stack([flow_model(a, b, upsample=False, test_mode=True)[pick] for a, b in zip(imgs[:-1], imgs[1:])])
+    bwd = torch.stack([flow_model(a, b, upsample=False, test_mode=True)[pick] for a, b in zip(rev[:-1], rev[1:])])
+    if verbose:
+        print("calc_optical_flow: flow_fwds %s flow_bwds %s" % (tuple(fwd.shape), tuple(bwd.shape)))
+    return fwd.cuda(), bwd.cuda()
+
+
+def _estimate_links(orig_imgs, flow_model, args):
+    """Links of the whole batch in the loader's layout [B, n, 2, h, w], estimated `flow_bs` samples at a time like
+    mem_reduce_calc_optical_flow (util.py:128-171; per-sample results do not depend on the chunking).  Returns
+    (fwd, bwd, flow_up): the 1/8-resolution links and flow_up=args.flow_up when the model up-samples bilinearly (RAFT-small:
+    the x8 up-sampling is then fused into the chain kernels), the model's own full-resolution prediction and flow_up=False
+    when it up-samples by learned convex combination (RAFT-basic)."""
+    core = flow_model.module if hasattr(flow_model, 'module') else flow_model
+    convex = bool(args.flow_up) and getattr(getattr(core, 'update_block', None), 'mask', None) is not None
+    bs = orig_imgs[0].shape[0]
+    flow_bs = getattr(args, 'flow_bs', None) or 8
+    fs, bs_ = [], []
+    for i0 in range(0, bs, flow_bs):
+        chunk = [im[i0:i0 + flow_bs].cuda() for im in orig_imgs]
+        f, b = calc_optical_flow(chunk, flow_model, up=convex, verbose=bool(getattr(args, 'verbose', False)))
+        fs.append(f), bs_.append(b)
+    fwd = torch.cat(fs, dim=1).permute(1, 0, 2, 3, 4).contiguous()
+    bwd = torch.cat(bs_, dim=1).permute(1, 0, 2, 3, 4).contiguous()
+    return fwd, bwd, bool(args.flow_up) and not convex
+
+
+@torch.no_grad()
+def mem_reduce_calc_optical_flow(orig_imgs, flow_model, args):
+    """contrast/util.py:128-171 -> chained (flow_fwd, flow_bwd), each [k, nb, 2, H, W] (k = 1, or every sub-chain with
+    use_flow_frames)."""
+    fwd, bwd, flow_up = _estimate_links(orig_imgs, flow_model, args)
+    fwd, bwd = fwd.permute(1, 0, 2, 3, 4), bwd.permute(1, 0, 2, 3, 4)
+    if flow_up:
+        num, nb, c, h, w = fwd.shape
+        fwd = upflow8(fwd.reshape(-1, c, h, w)).reshape(num, nb, c, 8 * h, 8 * w)
+        bwd = upflow8(bwd.reshape(-1, c, h, w)).reshape(num, nb, c, 8 * h, 8 * w)
+    ff, fb = all_concat_flow(fwd, bwd, is_norm=args.flow_cat_norm, use_flow_frames=args.use_flow_frames and len(orig_imgs) > 2)
+    if ff.ndim == 4:
+        ff, fb = ff.unsqueeze(0), fb.unsqueeze(0)
+    return ff, fb
+
+
+@torch.no_grad()
 def apply_optical_flow(data, flow_model, args):
     """contrast/util.py:175-248.  data follows the loader layout (contrast/data/dataset.py:503):
     data[5] = [target, flow_fwd [B,n,2,h,w], flow_bwd [B,n,2,h,w]], data[6] = [size [B,2], num_img [B,1], ...].
@@ -103,10 +155,13 @@ def apply_optical_flow(data, flow_model, args):
     size, num_img = orig_imgs_tmp[0][0], int(orig_imgs_tmp[1][0].item())
     is_mask_flow = args.alpha1 is not None and args.alpha2 is not None
     is_use_flow_frames = args.use_flow_frames and num_img > 2
-    if not args.use_flow_file:
-        raise NotImplementedError("on-the-fly RAFT estimation is out of scope (SURVEY.md §2.1 row 6): "
-                                  "precompute flows and pass --use_flow_file")
-    _, flow_fwds, flow_bwds = data[5]
+    if args.use_flow_file:
+        _, flow_fwds, flow_bwds = data[5]
+        flow_up = args.flow_up
+    else:
+        # util.py:201-204: links estimated on the fly by the RAFT model (contrast.flow.RAFT: correlation kernels of
+        # csrc/pp_corr.cu), then the same stage as for precomputed links
+        flow_fwds, flow_bwds, flow_up = _estimate_links(orig_imgs_tmp[2:], flow_model, args)
     debug = bool(getattr(args, 'debug', False))
     sparse = bool(getattr(args, 'flow_sparse', False)) or os.environ.get("PIXPRO_B200_SPARSE", "0") == "1"
     if sparse and not is_use_flow_frames and not debug and not args.flow_cat_norm:
@@ -114,14 +169,14 @@ def apply_optical_flow(data, flow_model, args):
         # objects carry the low-res links; regression_loss evaluates the chain and the FB test only at its
         # G*G grid centres (bit-identical to sampling the dense tensors), and `.dense()` / calc_mask_ratio
         # materialise the dense tensors on demand through the fused path below.
-        pair = _ops.LazyFlowPair(flow_fwds.cuda(), flow_bwds.cuda(), flow_up=args.flow_up,
+        pair = _ops.LazyFlowPair(flow_fwds.cuda(), flow_bwds.cuda(), flow_up=flow_up,
                                  alpha_1=args.alpha1 if is_mask_flow else None, alpha_2=args.alpha2 if is_mask_flow else None)
         return [pair.flow[0], size, pair.mask[0]], [pair.flow[1], size, pair.mask[1]]
     if not is_use_flow_frames and not debug:
         # fused path: x8 up-sampling, chaining and both FB masks in two launches, nothing else
         # materialised (util.py:185-244 in one pass)
         flow_fwd, flow_bwd, mask_fwd, mask_bwd = _ops.flow_stage(
-            flow_fwds.cuda(), flow_bwds.cuda(), flow_up=args.flow_up,
+            flow_fwds.cuda(), flow_bwds.cuda(), flow_up=flow_up,
             alpha_1=args.alpha1 if is_mask_flow else None, alpha_2=args.alpha2 if is_mask_flow else None,
             is_norm=args.flow_cat_norm)
         return [flow_fwd, size, mask_fwd], [flow_bwd, size, mask_bwd]
@@ -129,7 +184,7 @@ def apply_optical_flow(data, flow_model, args):
     # general path (use_flow_frames / debug), composed from the same kernels step by step
     flow_fwds = flow_fwds.cuda().permute(1, 0, 2, 3, 4)
     flow_bwds = flow_bwds.cuda().permute(1, 0, 2, 3, 4)
-    if args.flow_up:
+    if flow_up:
         num, nb, c, h, w = flow_fwds.shape
         flow_fwds = upflow8(flow_fwds.reshape(-1, c, h, w)).reshape(num, nb, c, 8 * h, 8 * w)
         flow_bwds = upflow8(flow_bwds.reshape(-1, c, h, w)).reshape(num, nb, c, 8 * h, 8 * w)

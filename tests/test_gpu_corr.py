@@ -94,3 +94,62 @@ def test_corr_empty_batch_and_errors():
     assert tuple(ops.corr_volume(z, z).shape) == (0, 64, 64)
     with pytest.raises((PixProB200Error, AssertionError)):
         ops.corr_volume(torch.zeros(1, 16, 8, 8), torch.zeros(1, 16, 8, 8))  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("tag", ["small", "basic"])
+def test_raft_estimator_matches_the_reference(tag):
+    """The drop-in contrast.flow.RAFT (cuDNN convolutions + this package's correlation volume / pyramid / lookup / x8
+    up-sampling kernels) against the reference's RAFT run on CPU with the same name-seeded weights.  Tolerance: 2e-3 of the
+    flow's scale — cuDNN and CPU convolutions differ in summation order and the GRU iterations feed back on themselves."""
+    import types
+    from contrast.flow import RAFT
+    from pixpro_b200 import synth
+    g = load_golden("raft_" + tag)
+    m = RAFT(types.SimpleNamespace(small=bool(g["small"]), mixed_precision=False))
+    synth.seeded_init_(m, int(g["seed"]))
+    m = m.to(DEV).eval()
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            low, up = m(cu(g["image1"].astype(np.float32)), cu(g["image2"].astype(np.float32)), iters=int(g["iters"]), upsample=False,
+                        test_mode=True)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    assert tuple(low.shape) == g["flow_low"].shape and tuple(up.shape) == (low.shape[0], 2, 8 * low.shape[2], 8 * low.shape[3])
+    scale = float(np.abs(g["flow_low"]).max())
+    assert np.abs(npy(low) - g["flow_low"]).max() < 2e-3 * scale
+    assert abs(float(up.abs().max()) - float(g["flow_up_absmax"])) < 2e-3 * float(g["flow_up_absmax"])
+
+
+def test_apply_optical_flow_estimates_links_with_the_raft_model():
+    """The non-file path of apply_optical_flow (contrast/util.py:201-204, 76-103, 128-171): links come from the flow model
+    (here a name-seeded RAFT-small on three 128x160 frames), `flow_bs` chunks do not change them, and the stage that
+    follows is the precomputed-links stage applied to those links."""
+    import types
+    from contrast import util
+    from contrast.flow import RAFT
+    from pixpro_b200 import ops, synth
+    m = RAFT(types.SimpleNamespace(small=True, mixed_precision=False))
+    synth.seeded_init_(m, 300)
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(3)
+    B = 3
+    frames = [torch.rand(B, 3, 128, 160, generator=g) * 255.0 for _ in range(3)]
+    size = torch.tensor([[128, 160]] * B)
+    data = [None] * 5 + [None, [size, torch.tensor([[3]] * B)] + frames]
+    args = types.SimpleNamespace(alpha1=0.01, alpha2=0.5, use_flow_frames=False, use_flow_file=False, flow_up=True, flow_cat_norm=False,
+                                 debug=False, flow_bs=2, verbose=False)
+    (ff, sz, mf), (fb, _, mb) = util.apply_optical_flow(data, m, args)
+    assert tuple(ff.shape) == (B, 2, 128, 160) and tuple(mf.shape) == (B, 128, 160) and sz is size[0]
+    # the same links estimated in one chunk, then the fused stage
+    with torch.no_grad():
+        fr = [f.to(DEV) for f in frames]
+        lo_f = torch.stack([m(a, b, upsample=False, test_mode=True)[0] for a, b in zip(fr[:-1], fr[1:])], dim=1)
+        lo_b = torch.stack([m(a, b, upsample=False, test_mode=True)[0] for a, b in zip(fr[::-1][:-1], fr[::-1][1:])], dim=1)
+    want = ops.flow_stage(lo_f, lo_b, flow_up=True, alpha_1=0.01, alpha_2=0.5)
+    # chunks of 2 vs the whole batch: cuDNN may pick another algorithm per batch size, so compare to a tolerance
+    assert torch.allclose(ff, want[0], atol=2e-3) and torch.allclose(fb, want[1], atol=2e-3)
+    assert (mf != want[2]).float().mean().item() < 1e-3
+    cf, cb = util.mem_reduce_calc_optical_flow(frames, m, args)
+    assert tuple(cf.shape) == (1, B, 2, 128, 160) and torch.equal(cf[0], ff) and torch.equal(cb[0], fb)

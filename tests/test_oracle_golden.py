@@ -209,3 +209,16 @@ def test_corr_block(orc, tag):
         pyr.append(orc.corr_pool(pyr[-1]))
         assert sha(pyr[-1]) == str(g[f"level{l}_sha"]), f"pyramid level {l}"
     assert_bits_equal(orc.corr_lookup(pyr, g["coords"], r), g["out"], "lookup")
+
+
+@pytest.mark.parametrize("tag", ["small", "basic"])
+def test_raft_state_dict_layout_matches_the_reference(tag):
+    """Checkpoint compatibility of the drop-in estimator (contrast/flow/raft.py:26-162 + extractor.py + update.py): same
+    state_dict keys, in the same order, with the same shapes as the reference's RAFT (recorded by the pin script)."""
+    import types
+    from contrast.flow import RAFT
+    g = load_golden("raft_" + tag)
+    m = RAFT(types.SimpleNamespace(small=bool(g["small"]), mixed_precision=False))
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == [str(s) for s in g["shapes"]]
