@@ -71,8 +71,9 @@ def build_model(args, device):
     else:
         raise NotImplementedError
     if args.use_flow and not args.use_flow_file:
-        raise NotImplementedError("RAFT estimation inside the training loop is not part of this entry: precompute flows "
-                                  "(--use_flow_file) or call contrast.flow.raft_small yourself")
+        raise NotImplementedError("this synthetic entry feeds precomputed links (--use_flow_file); for on-the-fly estimation build "
+                                  "contrast.flow.RAFT, load the reference's checkpoint and pass it to util.apply_optical_flow "
+                                  "as flow_model (main_pretrain.py:44-58 of the reference)")
     ddp = DistributedDataParallel(model, device_ids=[device.index], broadcast_buffers=False)
     return ddp, optimizer
 

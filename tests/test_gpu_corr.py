@@ -132,6 +132,9 @@ def test_apply_optical_flow_estimates_links_with_the_raft_model():
     from pixpro_b200 import ops, synth
     m = RAFT(types.SimpleNamespace(small=True, mixed_precision=False))
     synth.seeded_init_(m, 300)
+    with torch.no_grad():  # a randomly initialised RAFT iterated 12 times is chaotic: damp its updates so that runs are comparable
+        m.update_block.flow_head.conv2.weight.mul_(0.02)
+        m.update_block.flow_head.conv2.bias.mul_(0.02)
     m = m.to(DEV).eval()
     g = torch.Generator().manual_seed(3)
     B = 3
@@ -139,17 +142,24 @@ def test_apply_optical_flow_estimates_links_with_the_raft_model():
     size = torch.tensor([[128, 160]] * B)
     data = [None] * 5 + [None, [size, torch.tensor([[3]] * B)] + frames]
     args = types.SimpleNamespace(alpha1=0.01, alpha2=0.5, use_flow_frames=False, use_flow_file=False, flow_up=True, flow_cat_norm=False,
-                                 debug=False, flow_bs=2, verbose=False)
+                                 debug=False, flow_bs=B, verbose=False)
     (ff, sz, mf), (fb, _, mb) = util.apply_optical_flow(data, m, args)
-    assert tuple(ff.shape) == (B, 2, 128, 160) and tuple(mf.shape) == (B, 128, 160) and sz is size[0]
+    assert tuple(ff.shape) == (B, 2, 128, 160) and tuple(mf.shape) == (B, 128, 160) and torch.equal(sz, size[0])
     # the same links estimated in one chunk, then the fused stage
     with torch.no_grad():
         fr = [f.to(DEV) for f in frames]
         lo_f = torch.stack([m(a, b, upsample=False, test_mode=True)[0] for a, b in zip(fr[:-1], fr[1:])], dim=1)
         lo_b = torch.stack([m(a, b, upsample=False, test_mode=True)[0] for a, b in zip(fr[::-1][:-1], fr[::-1][1:])], dim=1)
     want = ops.flow_stage(lo_f, lo_b, flow_up=True, alpha_1=0.01, alpha_2=0.5)
-    # chunks of 2 vs the whole batch: cuDNN may pick another algorithm per batch size, so compare to a tolerance
-    assert torch.allclose(ff, want[0], atol=2e-3) and torch.allclose(fb, want[1], atol=2e-3)
+    scale = want[0].abs().max().item()
+    assert (ff - want[0]).abs().max().item() < 1e-4 * scale and (fb - want[1]).abs().max().item() < 1e-4 * scale
     assert (mf != want[2]).float().mean().item() < 1e-3
     cf, cb = util.mem_reduce_calc_optical_flow(frames, m, args)
-    assert tuple(cf.shape) == (1, B, 2, 128, 160) and torch.equal(cf[0], ff) and torch.equal(cb[0], fb)
+    assert tuple(cf.shape) == (1, B, 2, 128, 160)
+    assert (cf[0] - ff).abs().max().item() < 1e-4 * scale and (cb[0] - fb).abs().max().item() < 1e-4 * scale
+    # estimating flow_bs = 2 samples at a time: same layout; values agree up to what a randomly initialised, iterated
+    # network makes of cuDNN choosing another algorithm for another batch size
+    args.flow_bs = 2
+    (ff2, _, mf2), _ = util.apply_optical_flow(data, m, args)
+    assert tuple(ff2.shape) == tuple(ff.shape) and tuple(mf2.shape) == tuple(mf.shape)
+    assert (ff2 - ff).abs().max().item() < 1e-2 * scale
