@@ -88,9 +88,10 @@ PP_API int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int 
 
 /* ---- a6 (a1+a3+a5 fused): flow stage of apply_optical_flow — contrast/util.py:175-248 ---
  * (use_flow_file, not use_flow_frames).  lo_fwd/lo_bwd in the loader layout [B,n,2,h,w]
- * (contrast/data/dataset.py:485-495).  flow_up: links are x8-upsampled on the fly (n == 1) or
- * chunk-wise into `workspace` (n > 1: pp_flow_stage_workspace() bytes of device scratch, up to
- * 640 MB; NULL selects the scratch-free path).  Outputs flow_fwd/flow_bwd [B,2,H,W]
+ * (contrast/data/dataset.py:485-495).  flow_up: links are x8-upsampled on the fly, fused into the
+ * chain kernels for every n (csrc/pp_chainup.cuh for n > 1): no device scratch is needed any more —
+ * pp_flow_stage_workspace() returns 0 and `workspace` may be NULL (both kept for ABI stability).
+ * Outputs flow_fwd/flow_bwd [B,2,H,W]
  * (H,W = 8h,8w if flow_up), and, when use_mask, mask_fwd/mask_bwd u8 [B,H,W].  is_norm restates
  * --flow_cat_norm.                                                                          */
 PP_API int64_t pp_flow_stage_workspace(int64_t B, int n, int h, int w, int flow_up);
