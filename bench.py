@@ -587,7 +587,7 @@ def run_b200(a):
     pre = None
     if not a.no_extra and default_workload:
         try:
-            pre = measure_pretrain(ctx, steps=6, warmup=3)
+            pre = measure_pretrain(ctx, steps=8, warmup=6)   # warm-up covers the momentum branch's graph capture (after 3 eager steps)
             for k in ("higher_is_better", "scaling", "vs_baseline", "data"):
                 pre.pop(k, None)
         except Exception as e:
