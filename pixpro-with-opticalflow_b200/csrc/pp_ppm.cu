@@ -314,29 +314,6 @@ __global__ void __launch_bounds__(256) planes_kernel(const float* __restrict__ u
         }
     }
 }
-// (gS + gS^T) split into planes [B,P,P].  grid (ceil(P/32), ceil(P/32), B), block (32, 8).
-__global__ void __launch_bounds__(256) sym_planes_kernel(const float* __restrict__ gS, int P, float* __restrict__ hi, float* __restrict__ lo) {
-    __shared__ float t[32][33];
-    const float* g = gS + (int64_t)blockIdx.z * P * P;
-    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-#pragma unroll
-    for (int r = threadIdx.y; r < 32; r += 8) {  // tile (J, I) read row-wise: t[r][x] = gS[j0 + r][i0 + x]
-        const int jj = j0 + r, ii = i0 + threadIdx.x;
-        t[r][threadIdx.x] = (jj < P && ii < P) ? __ldg(g + jj * (int64_t)P + ii) : 0.0f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int i = i0 + r, j = j0 + threadIdx.x;
-        if (i < P && j < P) {
-            const int64_t o = (int64_t)blockIdx.z * P * P + i * (int64_t)P + j;
-            float h, l;
-            tc2::split1(__ldg(g + i * (int64_t)P + j) + t[threadIdx.x][r], h, l);
-            hi[o] = h;
-            lo[o] = l;
-        }
-    }
-}
 // Epilogue of the similarity contraction: S itself (kept for the backward) and relu^gamma(S) already split into the planes the
 // propagation contractions stream — the activation pass over S is gone.  Requires P % 4 == 0 (the TMA route does).
 struct TcStSAct {
@@ -372,8 +349,10 @@ struct TcStSAct {
         }
     }
 };
-struct TcStGradS4 {  // gS[b][i][j] = v * A'(S[b][i][j]), 16-byte accesses (P % 4 == 0)
-    float* gS;
+// Epilogue of the backward's similarity-gradient contraction.  The accumulator holds G + G^T (two products, see below); with S
+// (hence A'(S)) symmetric, (G + G^T) o A'(S) IS gS + gS^T — written straight as the hi / lo planes the gx contraction streams.
+struct TcStSymPlanes {
+    float *hi, *lo;
     const float* S;
     int P;
     Act act;
@@ -387,18 +366,13 @@ struct TcStGradS4 {  // gS[b][i][j] = v * A'(S[b][i][j]), 16-byte accesses (P % 
     }
     __device__ __forceinline__ void store4(int64_t b, int i, int j, float4 v, float4 s) const {
         const int64_t o = (b * P + i) * (int64_t)P + j;
-        *reinterpret_cast<float4*>(gS + o) = make_float4(v.x * act.df(s.x), v.y * act.df(s.y), v.z * act.df(s.z), v.w * act.df(s.w));
-    }
-    __device__ __forceinline__ void store16(int64_t b, int i, int j, const float v[16]) const {
-        const int64_t o = (b * P + i) * (int64_t)P + j;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (j + 4 * q < P) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(S + o + 4 * q));
-                *reinterpret_cast<float4*>(gS + o + 4 * q) = make_float4(v[4 * q] * act.df(s.x), v[4 * q + 1] * act.df(s.y),
-                                                                         v[4 * q + 2] * act.df(s.z), v[4 * q + 3] * act.df(s.w));
-            }
-        }
+        float4 h, l;
+        tc2::split1(v.x * act.df(s.x), h.x, l.x);
+        tc2::split1(v.y * act.df(s.y), h.y, l.y);
+        tc2::split1(v.z * act.df(s.z), h.z, l.z);
+        tc2::split1(v.w * act.df(s.w), h.w, l.w);
+        *reinterpret_cast<float4*>(hi + o) = h;
+        *reinterpret_cast<float4*>(lo + o) = l;
     }
 };
 // The TMA route needs 16-byte row strides in every plane: C % 4 == 0 and P % 4 == 0 (PIXPRO_B200_TC2=0 disables it).
@@ -550,16 +524,16 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
         float *gy_hi = f, *gy_lo = f + cp, *gyt_hi = f + 2 * cp, *gyt_lo = f + 3 * cp, *sym_hi = f + 4 * cp, *sym_lo = sym_hi + pp2;
         rc = launch_planes(gyp, nullptr, B, C, P, nullptr, gy_hi, gy_lo, gyt_hi, gyt_lo, st);
         if (rc) return rc;
-        rc = tc2::launch_tc2("ppm gS (tcgen05)", B, P, P, C, gyt_hi, gyt_lo, sv.vt_hi, sv.vt_lo, TcStGradS4{gS, sv.S, P, act}, st);
+        // (gS + gS^T)[i][j] = (G + G^T)[i][j] A'(S[i][j]) with G = gy^T v̂: ONE contraction with two operand sets accumulates
+        // gy^T v̂ and v̂^T gy into the same tile (K = 2C), and its epilogue writes the symmetrised gradient directly as the planes
+        // the gx contraction streams — gS itself, its store, and the transposing symmetrisation pass never exist.
+        const tc2::Operands sets[2] = {{gyt_hi, gyt_lo, sv.vt_hi, sv.vt_lo, C}, {sv.vt_hi, sv.vt_lo, gyt_hi, gyt_lo, C}};
+        rc = tc2::launch_tc2_sets("ppm gS (tcgen05)", B, P, P, sets, 2, TcStSymPlanes{sym_hi, sym_lo, sv.S, P, act}, st, false);
         if (rc > 0) return rc;
         if (rc == 0) {
             // gv̂[c][j] = Σ_i gy[c][i] A[i][j]; A is symmetric, so the B operand row j is row j of the saved relu^γ(S) planes
             rc = tc2::launch_tc2("ppm gvh (tcgen05)", B, C, P, P, gy_hi, gy_lo, sv.a_hi, sv.a_lo, TcStN{gvh, C, P}, st);
             if (rc) return rc < 0 ? PP_ERR_CUDA : rc;
-            dim3 sg((P + 31) / 32, (P + 31) / 32, (unsigned)B), sb(32, 8);
-            PP_LAUNCH("ppm sym planes", st, sym_planes_kernel<<<sg, sb, 0, st>>>(gS, P, sym_hi, sym_lo));
-            rc = check_launch("ppm sym planes");
-            if (rc) return rc;
             rc = tc2::launch_tc2("ppm gxh (tcgen05)", B, C, P, P, sv.x_hi, sv.x_lo, sym_hi, sym_lo, TcStN{gxh, C, P}, st);
             if (rc) return rc < 0 ? PP_ERR_CUDA : rc;
         } else {

@@ -101,8 +101,10 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t addr_a, uint32_t addr_b, fl
     for (int i = 0; i < 16; i++) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(r[16 + i]); }
 }
 
+// Two operand sets: the K loop runs over set 0 (K chunks [0, nchunk0)) and then, optionally, over set 1 — a second product
+// accumulated into the same tile (C = A0 B0^T + A1 B1^T: how the PPM backward forms G + G^T without ever writing G).
 struct Maps {
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2];
 };
 __device__ __forceinline__ bool m_in_range(int m, int M) { return m < M; }
 // Base of epilogue functors: store4(b, m, n, float4) for 4 consecutive columns of one row; functors with kAux = true also
@@ -111,7 +113,11 @@ struct EpNoAux {
     static constexpr bool kAux = false;
 };
 
-// Persistent: grid = min(#tiles, #SMs) CTAs, each walking the tile list (n fastest, so neighbouring CTAs share A rows in L2);
+// Persistent: grid = min(#tiles, #SMs) CTAs, each walking the tile list t = blockIdx.x + i gridDim.x with n fastest, then m, then
+// batch: the 28 tiles of a 784 x 784 sample run side by side on 28 SMs and request the same operand lines at the same time, which
+// the L2 merges.  (Measured alternative: n slowest — balances the narrow tail tiles of N over all CTAs, 25 % fewer full tiles per
+// busy CTA — is 5-15 % SLOWER: the kernel is bound by the chip-wide L2 request rate, not by per-SM work, so operand sharing in
+// time beats load balance.)
 // block 384; dynamic smem SMEM_BYTES; one CTA per SM (all 512 TMEM columns: columns [0,256) accumulate hi*hi, [256,512) the
 // 2^-11-smaller correction products — the tensor core truncates addends to the accumulator's exponent at every accumulate
 // step, so folding the 2 K/8 correction steps into the large accumulator triples its truncation bias: measured 3.0e-6 vs
@@ -120,7 +126,7 @@ struct EpNoAux {
 // accumulators the ring already holds the next tile's first chunks; barriers: full/empty per stage, acc_full/acc_empty.
 // BLO = false: the B operand is exact in TF32 (e.g. a 0/1 mask) — its lo plane is neither loaded nor multiplied.
 template <int TK, bool BLO, class EP>
-__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int batch, int a_bcast, EP ep) {
+__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int K1, int batch, int a_bcast, EP ep) {
     using C = Cfg<TK>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t tc2_smem_raw[];
@@ -131,14 +137,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MT = (M + TM - 1) / TM, NT = (N + TN - 1) / TN;
     const int ntiles = batch * MT * NT;
-    const int nchunk = (K + TK - 1) / TK;
+    const int nchunk0 = (K + TK - 1) / TK;
+    const int nchunk = nchunk0 + (K1 + TK - 1) / TK;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(&acc_full, 1);
         tc::mbar_init(&acc_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0 && lane == 0) { prefetch_map(&maps.a_hi); prefetch_map(&maps.a_lo); prefetch_map(&maps.b_hi); prefetch_map(&maps.b_lo); }
+    if (warp == 0 && lane == 0) { prefetch_map(&maps.a_hi[0]); prefetch_map(&maps.a_lo[0]); prefetch_map(&maps.b_hi[0]); prefetch_map(&maps.b_lo[0]); }
     if (warp == 2) tc::tmem_alloc(&tmem_slot, 512);
     tc::fence_before_sync();
     __syncthreads();
@@ -155,11 +162,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
                     const int s = g % STAGES, round = g / STAGES;
                     if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage have completed
                     const uint32_t st = base + s * C::kStageBytes;
+                    const int set = c >= nchunk0 ? 1 : 0;
+                    const int k0 = (set ? c - nchunk0 : c) * TK;
                     mbar_arrive_expect_tx(&full[s], BLO ? C::kStageBytes : C::kStageBytes - C::kBTile);
-                    tma_load_3d(st, &maps.a_hi, c * TK, mt * TM, a_bcast ? 0 : b, &full[s]);
-                    tma_load_3d(st + C::kATile, &maps.a_lo, c * TK, mt * TM, a_bcast ? 0 : b, &full[s]);
-                    tma_load_3d(st + 2 * C::kATile, &maps.b_hi, c * TK, nt * TN, b, &full[s]);
-                    if (BLO) tma_load_3d(st + 2 * C::kATile + C::kBTile, &maps.b_lo, c * TK, nt * TN, b, &full[s]);
+                    tma_load_3d(st, &maps.a_hi[set], k0, mt * TM, a_bcast ? 0 : b, &full[s]);
+                    tma_load_3d(st + C::kATile, &maps.a_lo[set], k0, mt * TM, a_bcast ? 0 : b, &full[s]);
+                    tma_load_3d(st + 2 * C::kATile, &maps.b_hi[set], k0, nt * TN, b, &full[s]);
+                    if (BLO) tma_load_3d(st + 2 * C::kATile + C::kBTile, &maps.b_lo[set], k0, nt * TN, b, &full[s]);
                 }
             }
         }
@@ -328,7 +337,7 @@ static inline bool applicable(int K, const void* a, const void* b, const void* c
 }
 
 template <int TK, bool BLO, class EP>
-static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int M, int N, int K, int a_bcast, EP ep, cudaStream_t st) {
+static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int M, int N, int K, int K1, int a_bcast, EP ep, cudaStream_t st) {
     auto kern = tc2_gemm_kernel<TK, BLO, EP>;
     static unsigned long long opted = 0;  // per template instantiation, one bit per device
     if (smem_opt_in(kern, (int)SMEM_BYTES, opted) != cudaSuccess) {
@@ -337,8 +346,38 @@ static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, 
     }
     const int64_t ntiles = batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN);
     const unsigned grid = (unsigned)(ntiles < num_sms() ? ntiles : num_sms());
-    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, (int)batch, a_bcast, ep));
+    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, K1, (int)batch, a_bcast, ep));
     return check_launch(what);
+}
+
+// Planes: A_hi/A_lo [batch][M][K] (or [M][K] shared by every batch entry: a_bcast), B_hi/B_lo [batch][N][K].
+// Returns -1 when not applicable (caller uses pp_tc.cuh's kernel).
+// PIXPRO_B200_TC2: 0 = off, 1 (default) = 64-byte chunks x 4 stages, 2 = 128-byte chunks x 2 stages (A/B switch).
+struct Operands {  // hi / lo planes of one product: A [batch][M][K] (or [M][K] with a_bcast), B [batch][N][K]
+    const float *a_hi, *a_lo, *b_hi, *b_lo;
+    int K;
+};
+template <bool BLO = true, class EP>
+static inline int launch_tc2_sets(const char* what, int64_t batch, int M, int N, const Operands* sets, int nsets, EP ep, cudaStream_t st,
+                                  bool a_bcast) {
+    if (batch > 65535 || nsets < 1 || nsets > 2) return -1;
+    for (int i = 0; i < nsets; i++)
+        if (!applicable(sets[i].K, sets[i].a_hi, sets[i].a_lo, sets[i].b_hi, sets[i].b_lo)) return -1;
+    if (batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN) >= (1ll << 31)) return -1;
+    static const int mode = [] { const char* e = getenv("PIXPRO_B200_TC2"); return e ? atoi(e) : 1; }();
+    const int tk = mode == 2 ? 32 : 16;
+    Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    const int64_t abatch = a_bcast ? 1 : batch;
+    for (int i = 0; i < 2; i++) {
+        const Operands& o = sets[i < nsets ? i : 0];
+        if (!make_plane_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, TM, tk) || !make_plane_map(&maps.a_lo[i], o.a_lo, abatch, M, o.K, TM, tk) ||
+            !make_plane_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, TN, tk) || !make_plane_map(&maps.b_lo[i], BLO ? o.b_lo : o.b_hi, batch, N, o.K, TN, tk))
+            return -1;
+    }
+    const int K0 = sets[0].K, K1 = nsets > 1 ? sets[1].K : 0;
+    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, ep, st)
+                    : launch_cfg<16, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, ep, st);
 }
 
 // Planes: A_hi/A_lo [batch][M][K] (or [M][K] shared by every batch entry: a_bcast), B_hi/B_lo [batch][N][K].
@@ -347,18 +386,8 @@ static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, 
 template <bool BLO = true, class EP>
 static inline int launch_tc2(const char* what, int64_t batch, int M, int N, int K, const float* a_hi, const float* a_lo, const float* b_hi,
                              const float* b_lo, EP ep, cudaStream_t st, bool a_bcast = false) {
-    if (!applicable(K, a_hi, a_lo, b_hi, b_lo) || batch > 65535) return -1;
-    if (batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN) >= (1ll << 31)) return -1;
-    static const int mode = [] { const char* e = getenv("PIXPRO_B200_TC2"); return e ? atoi(e) : 1; }();
-    const int tk = mode == 2 ? 32 : 16;
-    Maps maps;
-    memset(&maps, 0, sizeof(maps));
-    const int64_t abatch = a_bcast ? 1 : batch;
-    if (!make_plane_map(&maps.a_hi, a_hi, abatch, M, K, TM, tk) || !make_plane_map(&maps.a_lo, a_lo, abatch, M, K, TM, tk) ||
-        !make_plane_map(&maps.b_hi, b_hi, batch, N, K, TN, tk) || !make_plane_map(&maps.b_lo, BLO ? b_lo : b_hi, batch, N, K, TN, tk))
-        return -1;
-    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, M, N, K, a_bcast ? 1 : 0, ep, st)
-                    : launch_cfg<16, BLO>(what, maps, batch, M, N, K, a_bcast ? 1 : 0, ep, st);
+    const Operands o{a_hi, a_lo, b_hi, b_lo, K};
+    return launch_tc2_sets<BLO>(what, batch, M, N, &o, 1, ep, st, a_bcast);
 }
 
 static inline int launch_split(const float* x, int64_t n, float* hi, float* lo, cudaStream_t st) {
