@@ -197,12 +197,6 @@ __device__ __forceinline__ F2 add2(F2 a, F2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
     return r;
 }
-// round-down add (FADD2.RM): see the packed floor of fbbox_kernel
-__device__ __forceinline__ F2 add2_rm(F2 a, F2 b) {
-    F2 r;
-    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
 __device__ __forceinline__ F2 sub2(F2 a, F2 b) {
     F2 r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));

@@ -89,12 +89,12 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, i
 // grid = (W / TW, H / TH, planes); block = 256.  Requires W % TW == 0 and H % TH == 0.
 // WC/HC > 0: the frame size is a compile-time constant (the 1280x720 frames of the published BDD100K runs): every
 // derived constant and row offset folds into instruction immediates (no per-pixel constant-bank loads).
-// OPT (A/B switches, all value-preserving): 1 = own-flow loads and mask stores address with immediate offsets off one
-// per-thread pointer (compile-time frame size only); 2 = floor by a round-down add of 1.5*2^23 on packed pairs
-// (FADD2.RM: the integer sits in the low mantissa bits, the float floor is one exact subtraction) instead of
-// F2I.FLOOR + I2FP per coordinate; 4 = the rare global-memory path re-derives its tap origin instead of every pixel
-// packing one.
-template <int TW, int TH, int BW, int BH, int MINB, int WC, int HC, int OPT>
+// Five value-preserving instruction-diet switches of this kernel (immediate-offset addressing off one per-thread pointer; floor by
+// a round-down add of 1.5*2^23 on packed pairs instead of F2I.FLOOR + I2FP; lazily re-derived tap origin on the rare global path;
+// a rolled row loop; opaque row pointers) were built, verified bit-exact and measured within +-1.5 % of this plain form
+// (profiles/r02_a_fb_variants.txt, profiles/r02_g_fb_variants.txt: 355-364 us at B=64) — the L1 data pipe is as full as the issue
+// port, so shaving glue instructions does not move it — and were removed again.
+template <int TW, int TH, int BW, int BH, int MINB, int WC, int HC>
 __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant__ CUtensorMap tm0,
                                                           const __grid_constant__ CUtensorMap tm1,
                                                           const __grid_constant__ CUtensorMap tp0,
@@ -166,10 +166,6 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
     const int X0 = tx0 + lane, Y0 = ty0 + warp;
     const float* fp = ptr_at(f, Y0 * W + X0);                  // own flow, x channel, row Y0
     uint8_t* mp = (dir ? a.mask[1] : a.mask[0]) + (int64_t)b * HW + Y0 * W + X0;
-    if (OPT & 16) {  // opaque to the optimiser: kept in registers instead of being re-derived from tid / ctaid next to every use
-        asm volatile("" : "+l"(fp));
-        asm volatile("" : "+l"(mp));
-    }
     const int rstep = 8 * W;                                    // one thread-row (8 image rows)
     F2 xn2[NX];
 #pragma unroll
@@ -180,14 +176,9 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
         for (int c = 0; c < NX; c++)
 #pragma unroll
             for (int p = 0; p < 2; p++) {
-                if ((OPT & 1) && WC) {
-                    nfx[c][p] = __ldg(fp + ((kp + p) * 8 * WC + 32 * c));
-                    nfy[c][p] = __ldg(fp + (WC * HC + (kp + p) * 8 * WC + 32 * c));
-                } else {
-                    const float* q = ptr_at(fp, (kp + p) * rstep + 32 * c);
-                    nfx[c][p] = __ldg(q);
-                    nfy[c][p] = __ldg(ptr_at(q, HW));
-                }
+                const float* q = ptr_at(fp, (kp + p) * rstep + 32 * c);
+                nfx[c][p] = __ldg(q);
+                nfy[c][p] = __ldg(ptr_at(q, HW));
             }
     };
     prefetch(0);
@@ -196,7 +187,7 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
     const float* sp = reinterpret_cast<const float*>(fbt_smem);
     int nglobal = 0;  // pixels of this thread whose footprint was outside the staged box
     const float* g = (dir ? a.flow[0] : a.flow[1]) + (int64_t)b * 2 * HW;
-#pragma unroll(OPT & 8 ? 1 : NR / 2)
+#pragma unroll(NR / 2)
     for (int kp = 0; kp < NR; kp += 2) {
         float fxs[NX][2], fys[NX][2];
 #pragma unroll
@@ -217,32 +208,15 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
             bool inb[2], outside[2];
             int gofs[2];
             float t[2][8], xws[2], yws[2];
-            if (OPT & 2) {
-                // x + 1.5*2^23 rounded DOWN = 1.5*2^23 + floor(x) exactly for |x| < 2^22 (ulp is 1 there); the bits are
-                // 0x4B400000 + floor(x).  Garbage (NaN / huge) only occurs for pixels outside the frame, whose tap
-                // address is clamped below and whose mask bit is 0 whatever they read.
-                const F2 mg = pk1(12582912.0f);
-                const F2 tx = add2_rm(ix, mg), ty = add2_rm(iy, mg);
-                unpk(sub2(tx, mg), xws[0], xws[1]);
-                unpk(sub2(ty, mg), yws[0], yws[1]);
-                unpk(tx, ixs[0], ixs[1]);  // reuse as bit carriers
-                unpk(ty, iys[0], iys[1]);
-            }
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);                       // :276
-                int x0, y0;
-                if (OPT & 2) {
-                    x0 = __float_as_int(ixs[p]) - 0x4B400000; y0 = __float_as_int(iys[p]) - 0x4B400000;
-                } else {
-                    x0 = __float2int_rd(ixs[p]); y0 = __float2int_rd(iys[p]);
-                    xws[p] = __int2float_rn(x0);
-                    yws[p] = __int2float_rn(y0);
-                }
+                const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
+                xws[p] = __int2float_rn(x0);
+                yws[p] = __int2float_rn(y0);
                 const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
                 outside[p] = inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
-                if (OPT & 4) gofs[p] = 0;
-                else gofs[p] = (y0 << 16) | (x0 & 0xffff);  // only read for in-frame pixels (launcher: W, H < 32768)
+                gofs[p] = (y0 << 16) | (x0 & 0xffff);  // only read for in-frame pixels (launcher: W, H < 32768)
                 // clamp: a pixel outside the box or the frame still addresses the staged box
                 const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
                 t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
@@ -254,10 +228,7 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
 #pragma unroll
                 for (int p = 0; p < 2; p++)
                     if (outside[p]) {
-                        int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
-                        if (OPT & 4) {  // in-frame pixel: xws / yws are exact small non-negative integers
-                            x0 = (int)xws[p]; y0 = (int)yws[p];
-                        }
+                        const int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
                         const float* q = ptr_at(g, y0 * W + x0);
                         const bool xin = x0 < W - 1, yin = y0 < H - 1;
                         t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
@@ -284,8 +255,7 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 const uint8_t bit = (inb[p] && (ds[p] <= 0.0f)) ? 1 : 0;                             // :296
-                if ((OPT & 1) && WC) mp[(kp + p) * 8 * WC + 32 * c] = bit;
-                else *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = bit;
+                *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = bit;
             }
         }
     }
@@ -506,9 +476,9 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t planes, int H, 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int TW, int TH, int BW, int BH, int MINB, int WC = 0, int HC = 0, int OPT = 0>
+template <int TW, int TH, int BW, int BH, int MINB, int WC = 0, int HC = 0>
 static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
-    auto kern = fbbox_kernel<TW, TH, BW, BH, MINB, WC, HC, OPT>;
+    auto kern = fbbox_kernel<TW, TH, BW, BH, MINB, WC, HC>;
     constexpr int smem = 2 * BW * BH * 4;
     static unsigned long long opted = 0;  // one bit per device
     static const bool dbg = getenv("PIXPRO_B200_FBDBG") != nullptr;
@@ -549,9 +519,7 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
     a.dw2 = make_div<DM_FAST>((float)(W - 1) / 2.0f); a.dh2 = make_div<DM_FAST>((float)(H - 1) / 2.0f);
     static const int variant = [] { const char* e = getenv("PIXPRO_B200_FBTILE"); return e ? atoi(e) : 1; }();
     if (variant == 0) return -1;  // disabled: gather kernels
-    // the published frame size.  The OPT switches of fbbox_kernel (immediate-offset addressing, magic-number floor, lazy tap
-    // origin, rolled row loop, opaque row pointers) were built, verified bit-exact and measured within +-1.5 % of each other
-    // (profiles/r02_a_fb_variants.txt, gpurun_out/r02_g_fb.txt: 355-364 us at B=64): only the plain kernel is instantiated.
+    // the published frame size: every derived constant folds into instruction immediates
     if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
     if (H % 48 == 0) return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
     if (H % 32 == 0) return launch_cfg<64, 32, 96, 56, 4>(a, B, st);

@@ -117,7 +117,8 @@ struct EpNoAux {
 // batch: the 28 tiles of a 784 x 784 sample run side by side on 28 SMs and request the same operand lines at the same time, which
 // the L2 merges.  (Measured alternative: n slowest — balances the narrow tail tiles of N over all CTAs, 25 % fewer full tiles per
 // busy CTA — is 5-15 % SLOWER: the kernel is bound by the chip-wide L2 request rate, not by per-SM work, so operand sharing in
-// time beats load balance.)
+// time beats load balance.  Starting every second group of 28 CTAs 3-10 us late, so that their store-bound epilogues would meet the
+// others' L2-bound main loops, changed nothing either: profiles/r02_s_stagger.txt.)
 // block 384; dynamic smem SMEM_BYTES; one CTA per SM (all 512 TMEM columns: columns [0,256) accumulate hi*hi, [256,512) the
 // 2^-11-smaller correction products — the tensor core truncates addends to the accumulator's exponent at every accumulate
 // step, so folding the 2 K/8 correction steps into the large accumulator triples its truncation bias: measured 3.0e-6 vs
