@@ -221,3 +221,53 @@ def test_graphed_momentum_branch_matches_eager(group):
     finally:
         m2._kgraph = None
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_flow_store_to_host_step_end_to_end(tmp_path):
+    """SURVEY 8(f) rank 2 end to end on the GPU: per-video `.flw` stores (pixpro_b200.flowstore.write_flw) -> the drop-in
+    load_flows (sliced mmap reads, contrast/data/dataset.py:341-369) -> PinnedFlowStager (pinned [B,n,2,h,w] batches) ->
+    HostPixelStep (copies, flow stage, PPM, loss, backward, results back in pinned memory): loss, positive counts and feature
+    gradients equal the device-resident ops fed with the same links taken straight from the tensors the stores were written
+    from."""
+    from pixpro_b200 import flowstore as fs
+    from pixpro_b200 import ops, synth
+    from pixpro_b200.host_step import HostPixelStep
+    B, C, G, n = 6, 256, 7, 2
+    vids = []
+    for v in range(3):   # three "videos" of 12 frames at the published 90x160 flow size
+        f, b = synth.flow_fields(1, 11, seed=40 + v)
+        pf, pb = str(tmp_path / f"v{v}_fwd.flw"), str(tmp_path / f"v{v}_bwd.flw")
+        fs.write_flw(pf, f[0])
+        fs.write_flw(pb, b[0])
+        vids.append((f[0], b[0], pf, pb))
+    picks = [(0, 0), (0, 7), (1, 3), (1, 9), (2, 1), (2, 5)]   # (video, first link) per sample
+    samples, want_f, want_b = [], [], []
+    for v, s in picks:
+        f, b, pf, pb = vids[v]
+        bs, bn = fs.calc_bwd_idx(s, s + n, f.shape[0])
+        samples.append(fs.load_flows((pf, s, s + n), (pb, s, s + n)))
+        want_f.append(f[s:s + n])
+        want_b.append(b[bs:bn])
+    stager = fs.PinnedFlowStager(B, n, 90, 160, buffers=1)
+    lo_f, lo_b = stager.collate(samples)
+    assert lo_f.is_pinned() and torch.equal(lo_f, torch.stack(want_f)) and torch.equal(lo_b, torch.stack(want_b))
+    f1, f2, k1, k2 = synth.features(B, C, G, seed=46)
+    c1, c2 = synth.crop_coords(B, seed=47), synth.crop_coords(B, seed=48)
+    gen = torch.Generator().manual_seed(49)
+    w = (torch.randn(C, C, 1, 1, generator=gen) / 16).to(DEV)
+    bias = torch.zeros(C, device=DEV)
+    host = {k: v.pin_memory() for k, v in dict(feat1=f1, feat2=f2, k1=k1, k2=k2, c1=c1, c2=c2).items()}
+    host["lo_f"], host["lo_b"] = lo_f, lo_b
+    step = HostPixelStep(DEV, B, C, G, use_graph=True)
+    for _ in range(4):
+        out, _ = step(host, w, bias)
+    ff, fb, mf, mb = ops.flow_stage(torch.stack(want_f).to(DEV), torch.stack(want_b).to(DEV))
+    x = torch.cat([f1, f2]).to(DEV).requires_grad_(True)
+    p1, p2 = ops.ppm(x, ops.conv1x1(x, w, bias), 2.0, 0.0, True).chunk(2)
+    l12, pn, _ = ops.regression_loss_pair(p1, k2.to(DEV), c1.to(DEV), c2.to(DEV), p2, k1.to(DEV), c2.to(DEV), c1.to(DEV), 0.7,
+                                          flow1=ff, flow2=fb, size=(720, 1280), mask1=mf, mask2=mb)
+    (l12[0] + l12[1]).backward()
+    assert torch.equal(out["pos_num"].to(DEV), pn)
+    assert abs(out["loss"].item() - (l12[0] + l12[1]).item()) <= 1e-6 * max(1e-3, abs(out["loss"].item()))
+    ref = x.grad.view(2, B, C, G, G).cpu()
+    assert (out["d_feat"] - ref).abs().max().item() <= 1e-6 * ref.abs().max().item() + 1e-12
