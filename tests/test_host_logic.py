@@ -117,14 +117,48 @@ def test_all_concat_flow_subchains(monkeypatch):
     assert calls == [[float(v) for v in w] for w in want]
 
 
-def test_apply_optical_flow_rejects_on_the_fly_raft():
+def test_apply_optical_flow_estimates_links_with_the_flow_model(monkeypatch):
+    """The non-file branch (contrast/util.py:76-103, 128-171, 201-204) on CPU with a stand-in flow model: frame pairs go to the
+    model forward in time and backward in time (backward links listed from the last frame), `flow_bs` samples at a time, the
+    links reach the fused stage in the loader layout [B,n,2,h,w], and the x8 up-sampling is fused only when the model up-samples
+    bilinearly (no `update_block.mask`)."""
     import contrast.util as util
-    args = types.SimpleNamespace(alpha1=0.01, alpha2=0.5, use_flow_frames=False, use_flow_file=False, flow_up=True,
-                                 flow_cat_norm=False, debug=False)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    seen = []
+
+    class FakeRaft(torch.nn.Module):
+        def __init__(self, convex):
+            super().__init__()
+            self.update_block = types.SimpleNamespace(mask=(object() if convex else None))
+
+        def forward(self, a, b, upsample=False, test_mode=True):
+            seen.append((float(a[0, 0, 0, 0]), float(b[0, 0, 0, 0]), a.shape[0]))
+            low = (b[:, :2, ::8, ::8] - a[:, :2, ::8, ::8]).clone()      # "flow" = frame id difference, 1/8 resolution
+            return low, torch.nn.functional.interpolate(low, scale_factor=8.0) * 8
+
+    B = 5
+    frames = [torch.full((B, 3, 16, 24), float(t)) + torch.arange(B).view(B, 1, 1, 1) * 10 for t in range(3)]   # frame ids 0, 1, 2
     data = [None] * 7
-    data[6] = [torch.tensor([[720, 1280]]), torch.tensor([[2]])]
-    with pytest.raises(NotImplementedError):
-        util.apply_optical_flow(data, None, args)
+    data[6] = [torch.tensor([[16, 24]] * B), torch.tensor([[3]] * B)] + frames
+    got = {}
+
+    def fake_stage(lo_f, lo_b, flow_up=True, alpha_1=None, alpha_2=None, is_norm=False):
+        got.update(lo_f=lo_f, lo_b=lo_b, flow_up=flow_up)
+        z = torch.zeros(1)
+        return z, z, z, z
+
+    monkeypatch.setattr(util._ops, "flow_stage", fake_stage)
+    args = types.SimpleNamespace(alpha1=0.01, alpha2=0.5, use_flow_frames=False, use_flow_file=False, flow_up=True,
+                                 flow_cat_norm=False, debug=False, flow_bs=2, verbose=False)
+    util.apply_optical_flow(data, FakeRaft(convex=False), args)
+    assert got["flow_up"] is True and tuple(got["lo_f"].shape) == (B, 2, 2, 2, 3)
+    assert torch.all(got["lo_f"] == 1.0) and torch.all(got["lo_b"] == -1.0)      # every forward link +1 frame, every backward link -1
+    # chunks of flow_bs = 2 samples (2, 2, 1); per chunk forward pairs (0,1), (1,2) then backward pairs (2,1), (1,0)
+    assert [s[2] for s in seen] == [2] * 4 + [2] * 4 + [1] * 4
+    assert [(s[0] % 10, s[1] % 10) for s in seen[:4]] == [(0.0, 1.0), (1.0, 2.0), (2.0, 1.0), (1.0, 0.0)]
+    # a model with a learned (convex) up-sampler: its full-resolution prediction is chained, nothing is up-sampled again
+    util.apply_optical_flow(data, FakeRaft(convex=True), args)
+    assert got["flow_up"] is False and tuple(got["lo_f"].shape) == (B, 2, 2, 16, 24)
 
 
 def test_regression_loss_debug_tuple_is_rejected():
