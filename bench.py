@@ -109,7 +109,7 @@ def kernel_work(kernel, B, n, G):
         "ppm_bwd_small": (2 * 6 * cp, 2 * 3 * gemm),      # F4 backward: read feat, val, out, g, write d_feat, d_val
         "ppm S (tcgen05)": (2 * (cp + pp), 2 * gemm),
         "ppm Y (tcgen05)": (2 * (2 * cp + pp), 2 * gemm),
-        "ppm gS (tcgen05)": (2 * (2 * cp + 2 * pp), 2 * gemm),
+        "ppm gS (tcgen05)": (2 * (2 * cp + 3 * pp), 2 * gemm),   # useful flops: G once (the TMA route also accumulates G^T: K = 2C)
         "ppm gvh (tcgen05)": (2 * (2 * cp + pp), 2 * gemm),
         "ppm gxh (tcgen05)": (2 * (2 * cp + pp), 2 * gemm),
         "loss M=K*pos^T (tcgen05)": (2 * (2 * cp + P * 8), 2 * gemm),
@@ -128,6 +128,10 @@ def kernel_work(kernel, B, n, G):
         "loss_prep": (2 * 5 * P * 4, 0),
         "loss_cnt": (2 * P * 4, 0),
         "loss_final": (0, 0),
+        # plane passes of the TMA-fed route (bytes actually moved per step: what each pass must read and write)
+        "ppm planes": (2 * (2 * (1 + 5) + (1 + 4)) * cp, 0),      # feat, val: read 1, write out + 4 planes; gy: read 1, write 4 planes
+        "conv1x1 planes": (2 * ((1 + 2) * 4) * cp + 3 * ww, 0),   # x (fwd, wgrad), dy (dgrad, wgrad): read 1, write 2 planes each; W^T
+        "tc split": (2 * 3 * cp + 3 * ww, 0),                     # k planes of the two loss directions; W planes
     }
     by, fl = per_sample.get(kernel, (0, 0))
     return by * B, fl * B
