@@ -226,6 +226,10 @@ PP_API int pp_tc_gemm_nt(const float* A, const float* B, float* C, int64_t batch
  * layout; 128 x 256 CTA tiles.  K % 4 != 0 or PIXPRO_B200_TC2=0 falls back to the kernel above.                  */
 PP_API int64_t pp_tc_gemm_nt_workspace(int64_t batch, int M, int N, int K);
 PP_API int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, void* workspace, void* stream);
+/* General operand layouts through the same kernel: a_mn / b_mn != 0 = that operand is stored MN-major (A as [batch][K][M], B as
+ * [batch][K][N]) and read in place by TMA boxes + MN-major UMMA descriptors; fp32 operands are split into hi / lo by the kernel's
+ * converter warps (no workspace).  PP_ERR_INVALID when a shape is not streamable (no fallback).                     */
+PP_API int pp_tc_gemm_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, int a_mn, int b_mn, void* stream);
 
 /* ---- synchronised batch normalisation in three launches per direction (csrc/pp_syncbn.cu) ----------------------------
  * The reference converts every BatchNorm of encoder / projector to torch.nn.SyncBatchNorm (contrast/models/PixPro.py:289-292,

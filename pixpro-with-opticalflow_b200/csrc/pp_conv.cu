@@ -160,58 +160,14 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __rest
 
 constexpr int kWgradSplitK = 128;  // joint indices per split
 
-// ---- TMA-fed route (pp_tc2.cuh): per-sample contractions over pre-split hi / lo planes ------------------------------------
-//     y [b][o][p] = Σ_c W[o][c] x^T[b][p][c] + bias[o]       A = W planes (shared by every sample), B = transposed planes of x
-//     dx[b][c][p] = Σ_o W^T[c][o] dy^T[b][p][o]              A = W^T planes,                        B = transposed planes of dy
-//     dW[o][c]    = Σ_b Σ_p dy[b][o][p] x[b][c][p]           per sample: A = dy planes, B = x planes; deterministic sum over b
-// One pass per activation tensor writes its planes (act_planes_kernel); the weight planes are a 256 x 256 transpose / split.
+// ---- TMA-fed route (pp_tc2.cuh): per-sample contractions, every operand streamed by TMA in place and split by the kernel --------
+//     y [b][o][p] = Σ_c W[o][c] x[b][c][p] + bias[o]     A = W (K-major, shared by every sample),   B = x[b]  read MN-major
+//     dx[b][c][p] = Σ_o W[o][c] dy[b][o][p]               A = W read MN-major (rows c, K lines o),   B = dy[b] read MN-major
+//     dW[o][c]    = Σ_b Σ_p dy[b][o][p] x[b][c][p]        per sample: A = dy[b], B = x[b], both K-major; deterministic sum over b
+// No transposes, no plane passes, no workspace beyond the per-sample partials of dW.
 static inline bool conv_tc2(int Cin, int Cout, int P) {
     static const int off = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
     return !off && use_tensor_cores(P) && Cin % 4 == 0 && Cout % 4 == 0 && P % 4 == 0;
-}
-// u [B,C,P] -> split planes [B,C,P] (hi, lo; optional) and transposed split planes [B,P,C] (thi, tlo; optional).
-// grid (ceil(P/32), ceil(C/32), B), block (32, 8).
-__global__ void __launch_bounds__(256) act_planes_kernel(const float* __restrict__ u, int C, int P, float* __restrict__ hi,
-                                                          float* __restrict__ lo, float* __restrict__ thi, float* __restrict__ tlo) {
-    __shared__ float t[32][33];
-    const int64_t b = blockIdx.z;
-    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-    const int p = p0 + threadIdx.x;
-#pragma unroll
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int c = c0 + r;
-        float v = 0.0f;
-        if (c < C && p < P) {
-            const int64_t o = (b * C + c) * (int64_t)P + p;
-            v = __ldg(u + o);
-            if (hi) {
-                float h, l;
-                tc2::split1(v, h, l);
-                hi[o] = h;
-                lo[o] = l;
-            }
-        }
-        t[r][threadIdx.x] = v;
-    }
-    if (!thi) return;
-    __syncthreads();
-    const int c = c0 + threadIdx.x;
-#pragma unroll
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int q = p0 + r;
-        if (c < C && q < P) {
-            float h, l;
-            tc2::split1(t[threadIdx.x][r], h, l);
-            const int64_t o = (b * P + q) * (int64_t)C + c;
-            thi[o] = h;
-            tlo[o] = l;
-        }
-    }
-}
-static int launch_act_planes(const float* u, int64_t B, int C, int P, float* hi, float* lo, float* thi, float* tlo, cudaStream_t st) {
-    dim3 grid((P + 31) / 32, (C + 31) / 32, (unsigned)B), block(32, 8);
-    PP_LAUNCH("conv1x1 planes", st, act_planes_kernel<<<grid, block, 0, st>>>(u, C, P, hi, lo, thi, tlo));
-    return check_launch("conv1x1 planes");
 }
 struct TcStBias {  // out[b][m][n..n+3] = v + bias[m]
     static constexpr bool kAux = false;
@@ -238,8 +194,8 @@ using namespace pp;
 extern "C" {
 
 int64_t pp_conv1x1_fwd_workspace(int64_t B, int Cin, int Cout, int P) {
-    if (!conv_tc2(Cin, Cout, P)) return 0;
-    return (2 * B * (int64_t)P * Cin + 2 * (int64_t)Cout * Cin) * (int64_t)sizeof(float);  // transposed planes of x, planes of W
+    (void)B; (void)Cin; (void)Cout; (void)P;
+    return 0;  // the TMA route streams x and W in place (kept in the ABI: earlier builds staged planes here)
 }
 
 int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B, int Cin, int Cout, int P, float* y,
@@ -247,17 +203,11 @@ int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B,
     PP_REQUIRE(x && w && y, "pp_conv1x1_fwd: null pointer");
     PP_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && P > 0 && B * P < (1 << 24), "pp_conv1x1_fwd: bad shape");
     const int NP = (int)(B * P);
-    if (conv_tc2(Cin, Cout, P) && workspace) {
-        cudaStream_t st = (cudaStream_t)stream;
-        float* xt_hi = (float*)workspace;
-        float* xt_lo = xt_hi + B * (int64_t)P * Cin;
-        float* w_hi = xt_lo + B * (int64_t)P * Cin;
-        float* w_lo = w_hi + (int64_t)Cout * Cin;
-        int rc = launch_act_planes(x, B, Cin, P, nullptr, nullptr, xt_hi, xt_lo, st);
-        if (rc) return rc;
-        rc = tc2::launch_split(w, (int64_t)Cout * Cin, w_hi, w_lo, st);
-        if (rc) return rc;
-        rc = tc2::launch_tc2("conv1x1 fwd (tcgen05)", B, Cout, P, Cin, w_hi, w_lo, xt_hi, xt_lo, TcStBias{y, bias, Cout, P}, st, true);
+    (void)workspace;
+    if (conv_tc2(Cin, Cout, P)) {
+        tc2::Operands o{w, nullptr, x, nullptr, Cin};
+        o.b_mn = true;
+        const int rc = tc2::launch_tc2_sets("conv1x1 fwd (tcgen05)", B, Cout, P, &o, 1, TcStBias{y, bias, Cout, P}, (cudaStream_t)stream, true);
         if (rc >= 0) return rc;
     }
     return launch_tc("conv1x1 fwd (tcgen05)", 1, Cout, NP, Cin, LdW{w, Cout, Cin}, LdNC{x, Cin, NP, make_divp(P)},
@@ -267,8 +217,7 @@ int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B,
 int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P) {
     const int64_t splits = (B * P + kWgradSplitK - 1) / kWgradSplitK;
     int64_t f = splits * Cin * Cout + B * Cout;  // split-K partials of dW, then the row sums of db
-    if (conv_tc2(Cin, Cout, P))  // dgrad: transposed planes of dy, planes of W^T; wgrad: planes of dy and x, per-sample partials of dW
-        f += 2 * B * (int64_t)P * Cout + 2 * (int64_t)Cin * Cout + 2 * B * (int64_t)Cout * P + 2 * B * (int64_t)Cin * P + B * (int64_t)Cout * Cin;
+    if (conv_tc2(Cin, Cout, P)) f += B * (int64_t)Cout * Cin;  // wgrad: per-sample partials of dW
     return f * (int64_t)sizeof(float);
 }
 
@@ -281,25 +230,17 @@ int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, i
     int rc;
     const int64_t base_f = (int64_t)((NP + kWgradSplitK - 1) / kWgradSplitK) * Cin * Cout + B * Cout;
     const bool tma = conv_tc2(Cin, Cout, P);
-    float* f = (float*)workspace + base_f;  // TMA-route regions, disjoint per gradient (they may run on different streams)
-    float *dyt_hi = f, *dyt_lo = dyt_hi + B * (int64_t)P * Cout, *wt_hi = dyt_lo + B * (int64_t)P * Cout, *wt_lo = wt_hi + (int64_t)Cin * Cout;
-    float *dy_hi = wt_lo + (int64_t)Cin * Cout, *dy_lo = dy_hi + B * (int64_t)Cout * P, *x_hi = dy_lo + B * (int64_t)Cout * P,
-          *x_lo = x_hi + B * (int64_t)Cin * P, *part_b = x_lo + B * (int64_t)Cin * P;
+    float* part_b = (float*)workspace + base_f;  // per-sample partials of dW (TMA route)
     if (dx && tma) {
-        rc = launch_act_planes(dy, B, Cout, P, nullptr, nullptr, dyt_hi, dyt_lo, st);
-        if (rc) return rc;
-        rc = launch_act_planes(w, 1, Cout, Cin, nullptr, nullptr, wt_hi, wt_lo, st);  // W [Cout][Cin] -> W^T planes [Cin][Cout]
-        if (rc) return rc;
-        rc = tc2::launch_tc2("conv1x1 dgrad (tcgen05)", B, Cin, P, Cout, wt_hi, wt_lo, dyt_hi, dyt_lo, TcStBias{dx, nullptr, Cin, P}, st, true);
+        tc2::Operands o{w, nullptr, dy, nullptr, Cout};
+        o.a_mn = o.b_mn = true;
+        rc = tc2::launch_tc2_sets("conv1x1 dgrad (tcgen05)", B, Cin, P, &o, 1, TcStBias{dx, nullptr, Cin, P}, st, true);
         if (rc > 0) return rc;
         if (rc == 0) dx = nullptr;  // done
     }
     if (dw && tma) {
-        rc = launch_act_planes(dy, B, Cout, P, dy_hi, dy_lo, nullptr, nullptr, st);
-        if (rc) return rc;
-        rc = launch_act_planes(x, B, Cin, P, x_hi, x_lo, nullptr, nullptr, st);
-        if (rc) return rc;
-        rc = tc2::launch_tc2("conv1x1 wgrad (tcgen05)", B, Cout, Cin, P, dy_hi, dy_lo, x_hi, x_lo, TcStN{part_b, Cout, Cin}, st);
+        // both operands as they are ([B,C,P]: K = the pixel index is contiguous), split by the kernel's converter warps
+        rc = tc2::launch_tc2("conv1x1 wgrad (tcgen05)", B, Cout, Cin, P, dy, nullptr, x, nullptr, TcStN{part_b, Cout, Cin}, st);
         if (rc > 0) return rc;
         if (rc == 0) {
             const int total = Cout * Cin;

@@ -14,6 +14,7 @@
 
 #include "pp_common.cuh"
 #include "pp_tc.cuh"
+#include "pp_tc2.cuh"
 
 namespace pp {
 
@@ -154,6 +155,13 @@ int pp_corr_volume(const float* fmap1, const float* fmap2, int64_t B, int D, int
     const int P = h * w;
     const float s = sqrtf((float)D);  // torch.sqrt(torch.tensor(dim).float())
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_tensor_cores(P)) {
+        // both feature maps read in place, MN-major ([D][h*w]: the channel index is the K line), by the TMA-fed kernel
+        tc2::Operands o{fmap1, nullptr, fmap2, nullptr, D};
+        o.a_mn = o.b_mn = true;
+        const int rc = tc2::launch_tc2_sets("corr volume (tcgen05)", B, P, P, &o, 1, TcStDiv{corr, P, P, s}, st, false);
+        if (rc >= 0) return rc;
+    }
     if (use_tensor_cores(P))
         return launch_tc("corr volume (tcgen05)", B, P, P, D, TcLdT{fmap1, D, P}, TcLdT{fmap2, D, P}, TcStDiv{corr, P, P, s}, st);
     const int64_t total = B * P * (int64_t)P;

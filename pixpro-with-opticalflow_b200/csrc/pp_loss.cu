@@ -593,7 +593,7 @@ int64_t pp_regression_loss_workspace(int64_t B, int C, int G) {
     int64_t P = (int64_t)G * G;
     int64_t bytes = (5 * B * P + 2 * B + B * loss_ntile((int)P)) * (int64_t)sizeof(float);
     if (P > PMAX) bytes += B * P * (int64_t)sizeof(int) + B * P * P;  // row counts + byte matrix of positives
-    if (loss_tc2(C, (int)P)) bytes += 16 + (B * P * P + 2 * B * (int64_t)C * P) * (int64_t)sizeof(float);  // (16-byte aligned) 0/1 float plane, hi / lo planes of k
+    if (loss_tc2(C, (int)P)) bytes += 16 + B * P * P * (int64_t)sizeof(float);  // (16-byte aligned) 0/1 float plane
     return bytes;
 }
 
@@ -659,18 +659,14 @@ static int regression_loss_impl(const LossCall* calls, int ncall, int64_t B, int
             PP_LAUNCH("loss_centres", st, loss_centres_kernel<<<(unsigned)B, 256, 0, st>>>(pa[c]));
             const bool tma = loss_tc2(C, P);
             float* posf = tma ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(pa[c].ws.posb + B * (int64_t)P * P) + 15) & ~(uintptr_t)15) : nullptr;
-            float *k_hi = posf + B * (int64_t)P * P, *k_lo = k_hi + B * (int64_t)C * P;
             PP_LAUNCH("loss_pos", st, loss_pos_kernel<<<dim3((P + 7) / 8, (unsigned)B), 256, 0, st>>>(pa[c].ws, P, pa[c].pr, posb, posf));
             PP_LAUNCH("loss_cnt", st, loss_cnt_kernel<<<(unsigned)B, 256, 0, st>>>(pa[c].ws, P, pa[c].pos_num, pa[c].pos_mean));
             rc = check_launch("loss prep (large grid)");
             if (rc) return rc;
             rc = -1;
-            if (tma) {
-                rc = tc2::launch_split(calls[c].k, B * (int64_t)C * P, k_hi, k_lo, st);
-                if (rc) return rc;
-                rc = tc2::launch_tc2<false>("loss M=K*pos^T (tcgen05)", B, C, P, P, k_hi, k_lo, posf, posf,
+            if (tma)  // A = k as it is (split by the kernel's converter warps), B = the 0/1 plane (exact: no lo part)
+                rc = tc2::launch_tc2<false>("loss M=K*pos^T (tcgen05)", B, C, P, P, calls[c].k, nullptr, posf, posf,
                                             TcStDq{calls[c].dq, pa[c].ws.den, scale, C, P}, st);
-            }
             if (rc < 0)
                 rc = launch_tc("loss M=K*pos^T (tcgen05)", B, C, P, P, TcLdN{calls[c].k, C, P}, TcLdPos{posb, P},
                                TcStDq{calls[c].dq, pa[c].ws.den, scale, C, P}, st);

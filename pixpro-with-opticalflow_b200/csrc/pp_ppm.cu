@@ -56,6 +56,26 @@ __global__ void __launch_bounds__(256) coldiv_kernel(const float* y, const float
     out[e] = y[e] / nrm[b * P + i];
 }
 
+// out[b,c,i] = y[b,c,i] / n[b,i] (n == nullptr: y itself) and its hi / lo split in the same [B,C,P] layout: the planes the
+// similarity contractions stream MN-major (splitting 24 KB of operands per K chunk inside the contraction kernel costs it a
+// quarter of its tensor-pipe rate — shared-memory bandwidth — so operands that feed a P x P output are split here, once)
+__global__ void __launch_bounds__(256) coldiv_split_kernel(const float* __restrict__ y, const float* __restrict__ nrm, int C, int P, int64_t total,
+                                                            float* __restrict__ out, float* __restrict__ hi, float* __restrict__ lo) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    float v = __ldg(y + e);
+    if (nrm) {
+        int i = (int)(e % P);
+        int64_t b = e / ((int64_t)C * P);
+        v = v / nrm[b * P + i];
+    }
+    if (out) out[e] = v;
+    float h, l;
+    tc2::split1(v, h, l);
+    hi[e] = h;
+    lo[e] = l;
+}
+
 // normalisation backward: out = (g − û (g·û)) / n, û = u / n_u  (û given by u and its norm,
 // or directly when u is already normalised: pass nu = nullptr).
 // grid (ceil(P/32), B), block (32,8).
@@ -267,53 +287,11 @@ struct TcStGradS {  // gS[b][i][j] = v * A'(S[b][i][j])
     }
 };
 
-// ---- TMA-fed tensor-core route (pp_tc2.cuh): operands as pre-split hi / lo planes -----------------------------------------
-// One pass over a [B,C,P] tensor u (optionally divided by a column norm) that writes whatever the contractions need of it:
-//   out        u / n as plain fp32 [B,C,P]                      (kept for the normalisation backward)
-//   hi, lo     the same values split, [B,C,P]   (K = spatial index: the A operand of Y / gv / gx)
-//   thi, tlo   the same values split and TRANSPOSED, [B,P,C]    (K = channel: both operands of S and gS)
-// grid (ceil(P/32), ceil(C/32), B), block (32, 8); the transpose goes through a padded 32 x 32 shared-memory tile.
-__global__ void __launch_bounds__(256) planes_kernel(const float* __restrict__ u, const float* __restrict__ nrm, int C, int P,
-                                                      float* __restrict__ out, float* __restrict__ hi, float* __restrict__ lo,
-                                                      float* __restrict__ thi, float* __restrict__ tlo) {
-    __shared__ float t[32][33];
-    const int64_t b = blockIdx.z;
-    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-    const int p = p0 + threadIdx.x;
-    const float n = (nrm && p < P) ? __ldg(nrm + b * P + p) : 1.0f;
-#pragma unroll
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int c = c0 + r;
-        float v = 0.0f;
-        if (c < C && p < P) {
-            const int64_t o = (b * C + c) * (int64_t)P + p;
-            v = __ldg(u + o);
-            if (nrm) v = v / n;
-            if (out) out[o] = v;
-            if (hi) {
-                float h, l;
-                tc2::split1(v, h, l);
-                hi[o] = h;
-                lo[o] = l;
-            }
-        }
-        t[r][threadIdx.x] = v;
-    }
-    if (!thi) return;
-    __syncthreads();
-    const int c = c0 + threadIdx.x;
-#pragma unroll
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int pp_ = p0 + r;
-        if (c < C && pp_ < P) {
-            float h, l;
-            tc2::split1(t[threadIdx.x][r], h, l);
-            const int64_t o = (b * P + pp_) * (int64_t)C + c;
-            thi[o] = h;
-            tlo[o] = l;
-        }
-    }
-}
+// ---- TMA-fed tensor-core route (pp_tc2.cuh) ---------------------------------------------------------------------------------
+// [B,C,P] operands (x̂, v̂, gy) are split into hi / lo planes once, in their own layout, by the pass that normalises them
+// (coldiv_split_kernel), and streamed by TMA in place — K-major where the contraction runs over pixels, MN-major where it runs
+// over channels: no transposed copies exist.  The P x P operands (relu^gamma(S), gS + gS^T) are written as planes by the
+// epilogue of the contraction that produces them.
 // Epilogue of the similarity contraction: S itself (kept for the backward) and relu^gamma(S) already split into the planes the
 // propagation contractions stream — the activation pass over S is gone.  Requires P % 4 == 0 (the TMA route does).
 struct TcStSAct {
@@ -376,17 +354,14 @@ struct TcStSymPlanes {
     }
 };
 // The TMA route needs 16-byte row strides in every plane: C % 4 == 0 and P % 4 == 0 (PIXPRO_B200_TC2=0 disables it).
+// Pre-split planes of the [B,C,P] operands pay off at large grids (28x28: the similarity contractions are 15-25 % faster than with
+// the split done by the contraction kernel's converter warps, which costs it shared-memory bandwidth); at 14x14 the extra pass
+// over the operands costs more than it saves (measured 1.16 vs 1.11 ms/step), so there the fp32 tensors are streamed as they are.
+static inline bool ppm_presplit(int P) { return P >= 512; }
 static inline bool ppm_tc2(int C, int P) {
     static const int off = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
     return !off && use_tensor_cores(P) && C % 4 == 0 && P % 4 == 0;
 }
-static int launch_planes(const float* u, const float* nrm, int64_t B, int C, int P, float* out, float* hi, float* lo, float* thi,
-                         float* tlo, cudaStream_t st) {
-    dim3 grid((P + 31) / 32, (C + 31) / 32, (unsigned)B), block(32, 8);
-    PP_LAUNCH("ppm planes", st, planes_kernel<<<grid, block, 0, st>>>(u, nrm, C, P, out, hi, lo, thi, tlo));
-    return check_launch("ppm planes");
-}
-
 template <class LA, class LB, class EP>
 static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la, LB lb, EP ep, cudaStream_t st) {
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (unsigned)B);
@@ -396,8 +371,8 @@ static int launch_bgemm(const char* what, int64_t B, int M, int N, int K, LA la,
 
 struct Saved {
     float *nx, *nv, *ny, *S, *xh, *vh;  // xh, vh: normalised operands (generic path only)
-    // TMA route only (ppm_tc2): hi / lo planes.  a: relu^gamma(S) [B,P,P]; x, v: [B,C,P]; xt, vt: transposed [B,P,C]
-    float *a_hi, *a_lo, *x_hi, *x_lo, *xt_hi, *xt_lo, *v_hi, *v_lo, *vt_hi, *vt_lo;
+    // TMA route only (ppm_tc2): hi / lo planes of relu^gamma(S) [B,P,P], and of x̂ and v̂ in their own [B,C,P] layout
+    float *a_hi, *a_lo, *x_hi, *x_lo, *v_hi, *v_lo;
 };
 static Saved carve_saved(void* p, int64_t B, int C, int P) {
     Saved s;
@@ -411,8 +386,10 @@ static Saved carve_saved(void* p, int64_t B, int C, int P) {
     const int64_t pp2 = B * (int64_t)P * P, cp = B * (int64_t)C * P;
     s.a_hi = f; f += pp2;
     s.a_lo = f; f += pp2;
-    float** q[8] = {&s.x_hi, &s.x_lo, &s.xt_hi, &s.xt_lo, &s.v_hi, &s.v_lo, &s.vt_hi, &s.vt_lo};
-    for (int i = 0; i < 8; i++) { *q[i] = f; f += cp; }
+    s.x_hi = f; f += cp;
+    s.x_lo = f; f += cp;
+    s.v_hi = f; f += cp;
+    s.v_lo = f;
     return s;
 }
 
@@ -426,7 +403,7 @@ int64_t pp_ppm_saved_bytes(int64_t B, int C, int P) {
     int64_t f = 3 * B * P + B * (int64_t)P * P;
     if (!ppm_small_supported(C, P)) {
         f += 2 * B * (int64_t)C * P;  // normalised operands kept for the backward contractions
-        if (ppm_tc2(C, P)) f += 2 * B * (int64_t)P * P + 8 * B * (int64_t)C * P;  // hi / lo planes (see Saved)
+        if (ppm_tc2(C, P)) f += 2 * B * (int64_t)P * P + 4 * B * (int64_t)C * P;  // hi / lo planes of relu^gamma(S), x̂, v̂
     }
     return f * (int64_t)sizeof(float);
 }
@@ -434,7 +411,7 @@ int64_t pp_ppm_saved_bytes(int64_t B, int C, int P) {
 int64_t pp_ppm_bwd_workspace(int64_t B, int C, int P) {
     // gy [B,C,P] + gS [B,P,P] + gvh [B,C,P] + gxh [B,C,P]
     int64_t f = 3 * B * (int64_t)C * P + B * (int64_t)P * P;
-    if (!ppm_small_supported(C, P) && ppm_tc2(C, P)) f += 4 * B * (int64_t)C * P + 2 * B * (int64_t)P * P;  // gy, gy^T and (gS+gS^T) planes
+    if (!ppm_small_supported(C, P) && ppm_tc2(C, P)) f += 2 * B * (int64_t)P * P + 2 * B * (int64_t)C * P;  // (gS+gS^T) planes, gy planes
     return f * (int64_t)sizeof(float);
 }
 
@@ -455,14 +432,25 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
     // S[i][j] = Σ_c x̂[c][i] x̂[c][j]
     const int64_t total = B * (int64_t)C * P;
     if (ppm_tc2(C, P)) {
-        // TMA route: one pass per operand writes the normalised tensor and every plane the five contractions stream
-        rc = launch_planes(feat, sv.nx, B, C, P, sv.xh, sv.x_hi, sv.x_lo, sv.xt_hi, sv.xt_lo, st);
+        // TMA route: normalise once (x̂, v̂ kept for the backward), then stream them in place
+        const bool pre = ppm_presplit(P);
+        if (pre) {
+            PP_LAUNCH("ppm coldiv", st, coldiv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, sv.nx, C, P, total, sv.xh, sv.x_hi, sv.x_lo));
+            PP_LAUNCH("ppm coldiv", st, coldiv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(val, sv.nv, C, P, total, sv.vh, sv.v_hi, sv.v_lo));
+        } else {
+            PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, sv.nx, C, P, total, sv.xh));
+            PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(val, sv.nv, C, P, total, sv.vh));
+        }
+        rc = check_launch("ppm coldiv");
         if (rc) return rc;
-        rc = launch_planes(val, sv.nv, B, C, P, sv.vh, sv.v_hi, sv.v_lo, sv.vt_hi, sv.vt_lo, st);
-        if (rc) return rc;
-        rc = tc2::launch_tc2("ppm S (tcgen05)", B, P, P, C, sv.xt_hi, sv.xt_lo, sv.xt_hi, sv.xt_lo, TcStSAct{sv.S, sv.a_hi, sv.a_lo, P, act}, st);
+        const float *x_hi = pre ? sv.x_hi : sv.xh, *x_lo = pre ? sv.x_lo : nullptr, *v_hi = pre ? sv.v_hi : sv.vh, *v_lo = pre ? sv.v_lo : nullptr;
+        {   // S[i][j] = Σ_c x̂[c][i] x̂[c][j]: both operands are x̂ read MN-major ([C][P]: the channel index is the K line)
+            tc2::Operands o{x_hi, x_lo, x_hi, x_lo, C};
+            o.a_mn = o.b_mn = true;
+            rc = tc2::launch_tc2_sets("ppm S (tcgen05)", B, P, P, &o, 1, TcStSAct{sv.S, sv.a_hi, sv.a_lo, P, act}, st, false);
+        }
         if (rc > 0) return rc;
-        if (rc == 0) rc = tc2::launch_tc2("ppm Y (tcgen05)", B, C, P, P, sv.v_hi, sv.v_lo, sv.a_hi, sv.a_lo, TcStN{out, C, P}, st);
+        if (rc == 0) rc = tc2::launch_tc2("ppm Y (tcgen05)", B, C, P, P, v_hi, v_lo, sv.a_hi, sv.a_lo, TcStN{out, C, P}, st);
         if (rc > 0) return rc;
         if (rc < 0) {  // tensor maps could not be encoded: the thread-staged kernels read the same normalised tensors
             rc = launch_tc("ppm S (tcgen05)", B, P, P, C, TcLdT{sv.xh, C, P}, TcLdT{sv.xh, C, P}, TcStSAct{sv.S, sv.a_hi, sv.a_lo, P, act}, st);
@@ -518,23 +506,32 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
         if (rc) return rc;
         gyp = gy;
     }
-    if (ppm_tc2(C, P)) {
+    if (ppm_tc2(C, P) && (reinterpret_cast<uintptr_t>(gyp) & 15) == 0) {  // gy is streamed by TMA as it is: 16-byte aligned
         float* f = gxh + B * (int64_t)C * P;
-        const int64_t cp = B * (int64_t)C * P, pp2 = B * (int64_t)P * P;
-        float *gy_hi = f, *gy_lo = f + cp, *gyt_hi = f + 2 * cp, *gyt_lo = f + 3 * cp, *sym_hi = f + 4 * cp, *sym_lo = sym_hi + pp2;
-        rc = launch_planes(gyp, nullptr, B, C, P, nullptr, gy_hi, gy_lo, gyt_hi, gyt_lo, st);
-        if (rc) return rc;
+        const int64_t pp2 = B * (int64_t)P * P;
+        const bool pre = ppm_presplit(P);
+        float *sym_hi = f, *sym_lo = sym_hi + pp2;
+        const float *gy_hi = gyp, *gy_lo = nullptr, *x_hi = sv.xh, *x_lo = nullptr, *v_hi = sv.vh, *v_lo = nullptr;
+        if (pre) {
+            float *gh = sym_lo + pp2, *gl = gh + B * (int64_t)C * P;
+            gy_hi = gh; gy_lo = gl; x_hi = sv.x_hi; x_lo = sv.x_lo; v_hi = sv.v_hi; v_lo = sv.v_lo;
+            const int64_t total = B * (int64_t)C * P;
+            PP_LAUNCH("ppm coldiv", st, coldiv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gyp, nullptr, C, P, total, nullptr, gh, gl));
+            rc = check_launch("ppm split(gy)");
+            if (rc) return rc;
+        }
         // (gS + gS^T)[i][j] = (G + G^T)[i][j] A'(S[i][j]) with G = gy^T v̂: ONE contraction with two operand sets accumulates
         // gy^T v̂ and v̂^T gy into the same tile (K = 2C), and its epilogue writes the symmetrised gradient directly as the planes
         // the gx contraction streams — gS itself, its store, and the transposing symmetrisation pass never exist.
-        const tc2::Operands sets[2] = {{gyt_hi, gyt_lo, sv.vt_hi, sv.vt_lo, C}, {sv.vt_hi, sv.vt_lo, gyt_hi, gyt_lo, C}};
+        tc2::Operands sets[2] = {{gy_hi, gy_lo, v_hi, v_lo, C}, {v_hi, v_lo, gy_hi, gy_lo, C}};  // [C][P] tensors read MN-major
+        sets[0].a_mn = sets[0].b_mn = sets[1].a_mn = sets[1].b_mn = true;
         rc = tc2::launch_tc2_sets("ppm gS (tcgen05)", B, P, P, sets, 2, TcStSymPlanes{sym_hi, sym_lo, sv.S, P, act}, st, false);
         if (rc > 0) return rc;
         if (rc == 0) {
             // gv̂[c][j] = Σ_i gy[c][i] A[i][j]; A is symmetric, so the B operand row j is row j of the saved relu^γ(S) planes
             rc = tc2::launch_tc2("ppm gvh (tcgen05)", B, C, P, P, gy_hi, gy_lo, sv.a_hi, sv.a_lo, TcStN{gvh, C, P}, st);
             if (rc) return rc < 0 ? PP_ERR_CUDA : rc;
-            rc = tc2::launch_tc2("ppm gxh (tcgen05)", B, C, P, P, sv.x_hi, sv.x_lo, sym_hi, sym_lo, TcStN{gxh, C, P}, st);
+            rc = tc2::launch_tc2("ppm gxh (tcgen05)", B, C, P, P, x_hi, x_lo, sym_hi, sym_lo, TcStN{gxh, C, P}, st);
             if (rc) return rc < 0 ? PP_ERR_CUDA : rc;
         } else {
             rc = launch_tc("ppm gS (tcgen05)", B, P, P, C, TcLdT{gyp, C, P}, TcLdT{sv.vh, C, P}, TcStGradS{gS, sv.S, P, act}, st);

@@ -68,13 +68,34 @@ extern "C" int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_
     float* a_lo = a_hi + batch * (int64_t)M * K;
     float* b_hi = a_lo + batch * (int64_t)M * K;
     float* b_lo = b_hi + batch * (int64_t)N * K;
+    static const int planes = [] { const char* e = getenv("PIXPRO_B200_TC2_PLANES"); return (e && e[0] == '1') ? 1 : 0; }();
     if (tc2::applicable(K, A, B, workspace, C)) {
-        int rc = tc2::launch_split(A, batch * (int64_t)M * K, a_hi, a_lo, st);
-        if (rc) return rc;
-        rc = tc2::launch_split(B, batch * (int64_t)N * K, b_hi, b_lo, st);
-        if (rc) return rc;
-        rc = tc2::launch_tc2("tc2_gemm_nt", batch, M, N, K, a_hi, a_lo, b_hi, b_lo, tc::StoreC{C, M, N}, st);
+        int rc;
+        if (planes) {  // A/B switch: operands pre-split into hi / lo planes by a separate pass
+            rc = tc2::launch_split(A, batch * (int64_t)M * K, a_hi, a_lo, st);
+            if (rc) return rc;
+            rc = tc2::launch_split(B, batch * (int64_t)N * K, b_hi, b_lo, st);
+            if (rc) return rc;
+            rc = tc2::launch_tc2("tc2_gemm_nt", batch, M, N, K, a_hi, a_lo, b_hi, b_lo, tc::StoreC{C, M, N}, st);
+        } else {       // default: fp32 operands streamed as they are, split by the kernel's converter warps
+            rc = tc2::launch_tc2("tc2_gemm_nt", batch, M, N, K, A, nullptr, B, nullptr, tc::StoreC{C, M, N}, st);
+        }
         if (rc >= 0) return rc;
     }
     return launch_tc("tc_gemm_nt", batch, M, N, K, tc::LoadRowK{A, M, K}, tc::LoadRowK{B, N, K}, tc::StoreC{C, M, N}, st);
+}
+
+// General layouts through the TMA-fed kernel: a_mn / b_mn = the operand is stored MN-major, i.e. A as [batch][K][M] (resp. B as
+// [batch][K][N]) — how a [C, P] feature map serves as the P x C operand of the similarity contraction without a transposing pass.
+// fp32 operands are streamed as they are and split into hi / lo by the kernel's converter warps.  No fallback: returns
+// PP_ERR_INVALID when the shape is not streamable (K, and the contiguous extent of an MN-major operand, must be multiples of 4).
+extern "C" int pp_tc_gemm_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, int a_mn, int b_mn, void* stream) {
+    PP_REQUIRE(A && B && C, "pp_tc_gemm_ws: null pointer");
+    PP_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "pp_tc_gemm_ws: bad shape");
+    tc2::Operands o{A, nullptr, B, nullptr, K};
+    o.a_mn = a_mn != 0;
+    o.b_mn = b_mn != 0;
+    const int rc = tc2::launch_tc2_sets("tc2_gemm", batch, M, N, &o, 1, tc::StoreC{C, M, N}, (cudaStream_t)stream, false);
+    PP_REQUIRE(rc >= 0, "pp_tc_gemm_ws: shape / alignment not streamable by TMA (K %% 4, contiguous extents %% 4, 16-byte aligned pointers)");
+    return rc;
 }

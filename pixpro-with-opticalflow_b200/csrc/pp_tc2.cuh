@@ -34,7 +34,8 @@ namespace tc2 {
 
 constexpr int TM = 128;
 constexpr int TN = 256;
-constexpr int THREADS = 384;  // warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocation, warps 4-11: epilogue
+constexpr int THREADS = 512;  // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocation, 2-3 and 12-15: converters, 4-11: epilogue
+constexpr int NCONV = 6 * 32;  // converter threads
 constexpr uint32_t RING_BYTES = 192 * 1024;
 constexpr int EPI_STRIDE = 20;  // floats per row of an epilogue warp's 32 x 16 transpose buffer (80 bytes: conflict-free 16-byte writes)
 constexpr uint32_t EPI_BYTES = 8 * 32 * EPI_STRIDE * 4;  // 8 epilogue warps
@@ -68,6 +69,22 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
     return d;
 }
 
+// MN-major operand (memory [K][rows], rows contiguous — e.g. a [C, P] feature map used as the P x C operand).  For 32-bit
+// elements the only MN-major layout the tensor core reads is SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>:
+// 32-byte chunks of a 128-byte line XORed with the line index mod 4; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  The tile is
+// staged as boxes of 32 rows x TK k-lines (one 128-byte line per k): 4 k-lines form a 512-byte atom (SBO), consecutive 32-row
+// groups are one box = TK * 128 bytes apart (LBO).  One MMA (K = 8) consumes 8 k-lines = 1024 bytes of every group.
+template <int TK>
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((TK * 128) >> 4) << 16;  // LBO: next 32 rows
+    d |= (uint64_t)(512 >> 4) << 32;         // SBO: next 4 k-lines
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                  // SWIZZLE_128B_BASE32B
+    return d;
+}
+
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -78,6 +95,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(tc::smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(tc::smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* tm) {
@@ -105,7 +128,26 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t addr_a, uint32_t addr_b, fl
 // accumulated into the same tile (C = A0 B0^T + A1 B1^T: how the PPM backward forms G + G^T without ever writing G).
 struct Maps {
     CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2];
+    // MN-major operands only: the same plane viewed 4-D as [batch][row group][K][32 rows], so that ONE box brings all the 32-row
+    // groups of a tile (TM / 32 or TN / 32) in the staged order [group][k-line][32 rows]; used for tiles whose groups are all
+    // complete (a ragged last tile takes one 3-D box per group from a_lo / b_lo, whose row dimension clips properly)
+    CUtensorMap a_grp[2], b_grp[2];      // the plane the lo slot receives (the single fp32 plane of a raw operand, else the lo plane)
+    CUtensorMap a_grp_hi[2], b_grp_hi[2];  // pre-split MN-major operands: the hi plane
 };
+// in-place split of a staged fp32 tile: 16-byte chunk i of `lo` -> hi part to chunk i of `hi`, lo part back (NCONV converter threads)
+__device__ __forceinline__ void split_tile(uint8_t* hi, uint8_t* lo, int n16, int tid) {
+#pragma unroll 4
+    for (int i = tid; i < n16; i += 192) {
+        const float4 v = *reinterpret_cast<const float4*>(lo + 16 * i);
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+        *reinterpret_cast<float4*>(hi + 16 * i) = h;
+        *reinterpret_cast<float4*>(lo + 16 * i) = l;
+    }
+}
 __device__ __forceinline__ bool m_in_range(int m, int M) { return m < M; }
 // Base of epilogue functors: store4(b, m, n, float4) for 4 consecutive columns of one row; functors with kAux = true also
 // provide aux4(b, m, n, M, N) (a second operand, loaded ahead), prefetch_line(b, m, n) and store4(b, m, n, v, aux).
@@ -127,12 +169,16 @@ struct EpNoAux {
 // accumulators the ring already holds the next tile's first chunks; barriers: full/empty per stage, acc_full/acc_empty.
 // BLO = false: the B operand is exact in TF32 (e.g. a 0/1 mask) — its lo plane is neither loaded nor multiplied.
 template <int TK, bool BLO, class EP>
-__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int K1, int batch, int a_bcast, EP ep) {
+__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int K1, int batch, int a_bcast, int raw, EP ep) {
     using C = Cfg<TK>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t tc2_smem_raw[];
-    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full, acc_empty;
+    __shared__ uint64_t full[STAGES], empty[STAGES], conv[STAGES], acc_full, acc_empty;
     __shared__ uint32_t tmem_slot;
+    // raw & 1 (A) / raw & 2 (B): the operand comes as ONE fp32 plane (the lo map); TMA lands it in the stage's lo slot and the
+    // converter warps (2, 3) split it there: hi -> the hi slot, lo back in place (same swizzled offsets in both slots).
+    // raw & 4 / raw & 8: that fp32 plane is MN-major ([K][rows]) and is staged / described accordingly (desc_mnmajor).
+    const bool a_raw = raw & 1, b_raw = raw & 2, a_mn = raw & 4, b_mn = raw & 8, any_raw = raw & 3;
     const uint32_t base = (tc::smem_u32(tc2_smem_raw) + 1023u) & ~1023u;
     float* epi = reinterpret_cast<float*>(tc2_smem_raw + (base - tc::smem_u32(tc2_smem_raw)) + RING_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
     const int nchunk0 = (K + TK - 1) / TK;
     const int nchunk = nchunk0 + (K1 + TK - 1) / TK;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); tc::mbar_init(&conv[s], NCONV / 32); }
         tc::mbar_init(&acc_full, 1);
         tc::mbar_init(&acc_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,11 +211,39 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
                     const uint32_t st = base + s * C::kStageBytes;
                     const int set = c >= nchunk0 ? 1 : 0;
                     const int k0 = (set ? c - nchunk0 : c) * TK;
-                    mbar_arrive_expect_tx(&full[s], BLO ? C::kStageBytes : C::kStageBytes - C::kBTile);
-                    tma_load_3d(st, &maps.a_hi[set], k0, mt * TM, a_bcast ? 0 : b, &full[s]);
-                    tma_load_3d(st + C::kATile, &maps.a_lo[set], k0, mt * TM, a_bcast ? 0 : b, &full[s]);
-                    tma_load_3d(st + 2 * C::kATile, &maps.b_hi[set], k0, nt * TN, b, &full[s]);
-                    if (BLO) tma_load_3d(st + 2 * C::kATile + C::kBTile, &maps.b_lo[set], k0, nt * TN, b, &full[s]);
+                    mbar_arrive_expect_tx(&full[s], (a_raw ? 1 : 2) * C::kATile + ((BLO && !b_raw) ? 2 : 1) * C::kBTile);
+                    if (!a_raw && !a_mn) tma_load_3d(st, &maps.a_hi[set], k0, mt * TM, a_bcast ? 0 : b, &full[s]);
+                    if (a_mn) {  // boxes of 32 rows x TK k-lines
+                        if (mt * TM + TM <= M) {
+                            tma_load_4d(st + C::kATile, &maps.a_grp[set], 0, k0, mt * (TM / 32), a_bcast ? 0 : b, &full[s]);
+                            if (!a_raw) tma_load_4d(st, &maps.a_grp_hi[set], 0, k0, mt * (TM / 32), a_bcast ? 0 : b, &full[s]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < TM / 32; u++) {
+                                tma_load_3d(st + C::kATile + u * (TK * 128), &maps.a_lo[set], mt * TM + 32 * u, k0, a_bcast ? 0 : b, &full[s]);
+                                if (!a_raw) tma_load_3d(st + u * (TK * 128), &maps.a_hi[set], mt * TM + 32 * u, k0, a_bcast ? 0 : b, &full[s]);
+                            }
+                        }
+                    } else {
+                        tma_load_3d(st + C::kATile, &maps.a_lo[set], k0, mt * TM, a_bcast ? 0 : b, &full[s]);
+                    }
+                    if (b_mn) {
+                        if (nt * TN + TN <= N) {
+                            tma_load_4d(st + 2 * C::kATile + C::kBTile, &maps.b_grp[set], 0, k0, nt * (TN / 32), b, &full[s]);
+                            if (!b_raw) tma_load_4d(st + 2 * C::kATile, &maps.b_grp_hi[set], 0, k0, nt * (TN / 32), b, &full[s]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < TN / 32; u++) {
+                                tma_load_3d(st + 2 * C::kATile + C::kBTile + u * (TK * 128), &maps.b_lo[set], nt * TN + 32 * u, k0, b, &full[s]);
+                                if (!b_raw) tma_load_3d(st + 2 * C::kATile + u * (TK * 128), &maps.b_hi[set], nt * TN + 32 * u, k0, b, &full[s]);
+                            }
+                        }
+                    } else if (b_raw) {
+                        tma_load_3d(st + 2 * C::kATile + C::kBTile, &maps.b_lo[set], k0, nt * TN, b, &full[s]);
+                    } else {
+                        tma_load_3d(st + 2 * C::kATile, &maps.b_hi[set], k0, nt * TN, b, &full[s]);
+                        if (BLO) tma_load_3d(st + 2 * C::kATile + C::kBTile, &maps.b_lo[set], k0, nt * TN, b, &full[s]);
+                    }
                 }
             }
         }
@@ -181,22 +255,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
                 const int nt = t % NT;
                 const int tn = min(TN, ((N - nt * TN) + 15) & ~15);  // UMMA N of this tile
-                const uint32_t idesc = tc::make_idesc(TM, tn);
+                const uint32_t idesc = tc::make_idesc(TM, tn) | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u);  // operand major-ness bits
                 if (i > 0) tc::mbar_wait(&acc_empty, (i - 1) & 1);  // the epilogue has drained the accumulators
                 tc::fence_after_sync();
 #pragma unroll 1
                 for (int c = 0; c < nchunk; c++, g++) {
                     const int s = g % STAGES, round = g / STAGES;
-                    tc::mbar_wait(&full[s], round & 1);
+                    tc::mbar_wait(any_raw ? &conv[s] : &full[s], round & 1);
                     tc::fence_after_sync();
                     const uint32_t a_hi = base + s * C::kStageBytes, a_lo = a_hi + C::kATile, b_hi = a_hi + 2 * C::kATile, b_lo = b_hi + C::kBTile;
 #pragma unroll
-                    for (int kk = 0; kk < TK / 8; kk++) {  // one MMA consumes K = 8 fp32 = 32 bytes of the swizzle row
-                        const uint32_t ko = kk * 32;
+                    for (int kk = 0; kk < TK / 8; kk++) {  // one MMA consumes K = 8 fp32: 32 bytes of a K-major row, one atom of an MN-major tile
                         const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-                        tc::mma_tf32(tmem_d, desc_kmajor<TK>(a_hi + ko), desc_kmajor<TK>(b_hi + ko), idesc, acc);
-                        if (BLO) tc::mma_tf32(tmem_d + TN, desc_kmajor<TK>(a_hi + ko), desc_kmajor<TK>(b_lo + ko), idesc, acc);
-                        tc::mma_tf32(tmem_d + TN, desc_kmajor<TK>(a_lo + ko), desc_kmajor<TK>(b_hi + ko), idesc, BLO ? 1u : acc);
+                        const uint64_t dah = a_mn ? desc_mnmajor<TK>(a_hi + kk * 1024) : desc_kmajor<TK>(a_hi + kk * 32);
+                        const uint64_t dal = a_mn ? desc_mnmajor<TK>(a_lo + kk * 1024) : desc_kmajor<TK>(a_lo + kk * 32);
+                        const uint64_t dbh = b_mn ? desc_mnmajor<TK>(b_hi + kk * 1024) : desc_kmajor<TK>(b_hi + kk * 32);
+                        tc::mma_tf32(tmem_d, dah, dbh, idesc, acc);
+                        if (BLO) {
+                            const uint64_t dbl = b_mn ? desc_mnmajor<TK>(b_lo + kk * 1024) : desc_kmajor<TK>(b_lo + kk * 32);
+                            tc::mma_tf32(tmem_d + TN, dah, dbl, idesc, acc);
+                        }
+                        tc::mma_tf32(tmem_d + TN, dal, dbh, idesc, BLO ? 1u : acc);
                     }
                     tc::mma_commit(&empty[s]);  // frees the stage when these MMAs have read it
                 }
@@ -204,8 +283,29 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
-        // ===== epilogue (8 warps): thread t of warp w owns accumulator row 32 (w % 4) + t (a warp reads only its own TMEM lane
+    } else if (warp < 4 || warp >= 12) {
+        // ===== converter warps (2, 3, 12-15): hi / lo split of operands that arrive as one fp32 plane.  Two warps could not keep
+        // up with two MN-major operands (24 KB per 768 tensor-pipe cycles: measured 35 % slower main loops); six can. =====
+        if (any_raw) {
+            const int tid = warp < 4 ? threadIdx.x - 64 : threadIdx.x - 12 * 32 + 64;  // 0..NCONV-1
+            int g = 0;
+#pragma unroll 1
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+#pragma unroll 1
+                for (int c = 0; c < nchunk; c++, g++) {
+                    const int s = g % STAGES, round = g / STAGES;
+                    tc::mbar_wait(&full[s], round & 1);
+                    uint8_t* st = tc2_smem_raw + (base - tc::smem_u32(tc2_smem_raw)) + s * C::kStageBytes;
+                    if (a_raw) split_tile(st, st + C::kATile, C::kATile / 16, tid);
+                    if (b_raw) split_tile(st + 2 * C::kATile, st + 2 * C::kATile + C::kBTile, C::kBTile / 16, tid);
+                    tc::fence_smem_to_async();  // generic-proxy writes -> visible to the tensor core's operand reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&conv[s]);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (warps 4-11): thread t of warp w owns accumulator row 32 (w % 4) + t (a warp reads only its own TMEM lane
         // quarter); the two warps of a quarter alternate 16-column groups =====
         const int q = warp & 3, half = (warp - 4) >> 2;
         const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
@@ -307,6 +407,33 @@ static inline EncodeTiledFn encode_fn() {
     }();
     return fn;
 }
+// MN-major plane [batch][K][rows] fp32 viewed as a 3-D tensor (rows fastest); box = 32 rows x tk k-lines x 1, 128-byte swizzle of
+// 32-byte atoms
+static inline bool make_mn_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int tk) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)K, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)rows * 4, (cuuint64_t)rows * K * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)tk, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// the same MN-major plane viewed 4-D: dims {32 rows, K, complete 32-row groups, batch}; box = 32 x tk x groups_per_tile x 1
+static inline bool make_mn_group_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int tk, int groups_per_tile) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    const int groups = rows / 32;  // complete groups only: a box never straddles the end of a k-line
+    if (groups < groups_per_tile) {  // no tile is complete: the map is never used; encode a valid dummy (the 3-D map's geometry)
+        return make_mn_map(tm, base, batch, rows, K, tk);
+    }
+    cuuint64_t dims[4] = {32, (cuuint64_t)K, (cuuint64_t)groups, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)rows * 4, 128, (cuuint64_t)rows * K * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)tk, (cuuint32_t)groups_per_tile, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // plane [batch][rows][K] fp32 viewed as a 3-D tensor (K fastest); box = tk x box_rows x 1, swizzle span = one box row
 static inline bool make_plane_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int box_rows, int tk) {
     EncodeTiledFn enc = encode_fn();
@@ -334,11 +461,11 @@ static inline int num_sms() {  // of the current device
 
 static inline bool applicable(int K, const void* a, const void* b, const void* c, const void* d) {
     static const int off = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
-    return !off && K % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+    return !off && K % 4 == 0 && a && c && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
 }
 
 template <int TK, bool BLO, class EP>
-static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int M, int N, int K, int K1, int a_bcast, EP ep, cudaStream_t st) {
+static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int M, int N, int K, int K1, int a_bcast, int raw, EP ep, cudaStream_t st) {
     auto kern = tc2_gemm_kernel<TK, BLO, EP>;
     static unsigned long long opted = 0;  // per template instantiation, one bit per device
     if (smem_opt_in(kern, (int)SMEM_BYTES, opted) != cudaSuccess) {
@@ -347,7 +474,7 @@ static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, 
     }
     const int64_t ntiles = batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN);
     const unsigned grid = (unsigned)(ntiles < num_sms() ? ntiles : num_sms());
-    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, K1, (int)batch, a_bcast, ep));
+    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, K1, (int)batch, a_bcast, raw, ep));
     return check_launch(what);
 }
 
@@ -355,30 +482,48 @@ static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, 
 // Returns -1 when not applicable (caller uses pp_tc.cuh's kernel).
 // PIXPRO_B200_TC2: 0 = off, 1 (default) = 64-byte chunks x 4 stages, 2 = 128-byte chunks x 2 stages (A/B switch).
 struct Operands {  // hi / lo planes of one product: A [batch][M][K] (or [M][K] with a_bcast), B [batch][N][K]
-    const float *a_hi, *a_lo, *b_hi, *b_lo;
+    const float *a_hi, *a_lo, *b_hi, *b_lo;  // an operand given as ONE fp32 plane (split in the kernel): hi = the plane, lo = nullptr
     int K;
+    bool a_mn = false, b_mn = false;  // the operand's plane(s) are MN-major: memory [batch][K][rows] (rows contiguous) instead of [batch][rows][K]
 };
 template <bool BLO = true, class EP>
 static inline int launch_tc2_sets(const char* what, int64_t batch, int M, int N, const Operands* sets, int nsets, EP ep, cudaStream_t st,
                                   bool a_bcast) {
     if (batch > 65535 || nsets < 1 || nsets > 2) return -1;
-    for (int i = 0; i < nsets; i++)
+    const bool a_raw = sets[0].a_lo == nullptr, b_raw = BLO && sets[0].b_lo == nullptr;
+    const bool a_mn = sets[0].a_mn, b_mn = sets[0].b_mn;
+    if (b_mn && !BLO) return -1;
+    for (int i = 0; i < nsets; i++) {
+        if ((sets[i].a_lo == nullptr) != a_raw || (BLO && (sets[i].b_lo == nullptr) != b_raw)) return -1;  // same form in both sets
+        if (sets[i].a_mn != a_mn || sets[i].b_mn != b_mn) return -1;
         if (!applicable(sets[i].K, sets[i].a_hi, sets[i].a_lo, sets[i].b_hi, sets[i].b_lo)) return -1;
+        if ((a_mn && M % 4 != 0) || (b_mn && N % 4 != 0)) return -1;  // 16-byte row strides of the MN-major planes
+    }
     if (batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN) >= (1ll << 31)) return -1;
     static const int mode = [] { const char* e = getenv("PIXPRO_B200_TC2"); return e ? atoi(e) : 1; }();
-    const int tk = mode == 2 ? 32 : 16;
+    const int tk = (mode == 2 && !a_mn && !b_mn) ? 32 : 16;
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     const int64_t abatch = a_bcast ? 1 : batch;
     for (int i = 0; i < 2; i++) {
         const Operands& o = sets[i < nsets ? i : 0];
-        if (!make_plane_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, TM, tk) || !make_plane_map(&maps.a_lo[i], o.a_lo, abatch, M, o.K, TM, tk) ||
-            !make_plane_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, TN, tk) || !make_plane_map(&maps.b_lo[i], BLO ? o.b_lo : o.b_hi, batch, N, o.K, TN, tk))
-            return -1;
+        // raw operand: the single fp32 plane is what the "lo" map describes (it is loaded into the stage's lo slot)
+        const float* a_lo_src = a_raw ? o.a_hi : o.a_lo;                  // what the stage's lo slot receives
+        const float* b_lo_src = (BLO && !b_raw) ? o.b_lo : o.b_hi;
+        bool ok = a_mn ? (make_mn_map(&maps.a_lo[i], a_lo_src, abatch, M, o.K, tk) && make_mn_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, tk) &&
+                          make_mn_group_map(&maps.a_grp[i], a_lo_src, abatch, M, o.K, tk, TM / 32) &&
+                          make_mn_group_map(&maps.a_grp_hi[i], o.a_hi, abatch, M, o.K, tk, TM / 32))
+                       : (make_plane_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, TM, tk) && make_plane_map(&maps.a_lo[i], a_lo_src, abatch, M, o.K, TM, tk));
+        ok = ok && (b_mn ? (make_mn_map(&maps.b_lo[i], b_lo_src, batch, N, o.K, tk) && make_mn_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, tk) &&
+                            make_mn_group_map(&maps.b_grp[i], b_lo_src, batch, N, o.K, tk, TN / 32) &&
+                            make_mn_group_map(&maps.b_grp_hi[i], o.b_hi, batch, N, o.K, tk, TN / 32))
+                         : (make_plane_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, TN, tk) && make_plane_map(&maps.b_lo[i], b_lo_src, batch, N, o.K, TN, tk)));
+        if (!ok) return -1;
     }
     const int K0 = sets[0].K, K1 = nsets > 1 ? sets[1].K : 0;
-    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, ep, st)
-                    : launch_cfg<16, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, ep, st);
+    const int raw = (a_raw ? 1 : 0) | (b_raw ? 2 : 0) | (a_mn ? 4 : 0) | (b_mn ? 8 : 0);
+    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, raw, ep, st)
+                    : launch_cfg<16, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, raw, ep, st);
 }
 
 // Planes: A_hi/A_lo [batch][M][K] (or [M][K] shared by every batch entry: a_bcast), B_hi/B_lo [batch][N][K].

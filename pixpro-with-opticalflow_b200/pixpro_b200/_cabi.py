@@ -63,6 +63,7 @@ SIGNATURES = {
     "pp_bn_apply": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp]),
     "pp_bn_bwd_stats": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pp_bn_bwd_apply": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pp_tc_gemm_ws": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp]),
     "pp_corr_volume": (_i, [_vp, _vp, _l, _i, _i, _i, _vp, _vp]),
     "pp_corr_pool": (_i, [_vp, _l, _i, _i, _vp, _vp]),
     "pp_corr_lookup": (_i, [_vp, _i, _vp, _l, _i, _i, _i, _i, _vp, _vp]),

@@ -637,6 +637,22 @@ def tc_gemm_nt(A, B, tma=True, workspace=None):
     return C
 
 
+def tc_gemm(A, B, a_mn=False, b_mn=False):
+    """C[b][m][n] = sum_k A(m,k) B(n,k) on the TMA-fed tcgen05 kernel, operands in place in either layout:
+    A [batch,M,K] (or [batch,K,M] with a_mn), B [batch,N,K] (or [batch,K,N] with b_mn) -> [batch,M,N]."""
+    A = _f32(A, "A")
+    B = _f32(B, "B")
+    assert A.ndim == 3 and B.ndim == 3 and A.shape[0] == B.shape[0]
+    batch = A.shape[0]
+    M, K = (A.shape[2], A.shape[1]) if a_mn else (A.shape[1], A.shape[2])
+    N, K2 = (B.shape[2], B.shape[1]) if b_mn else (B.shape[1], B.shape[2])
+    assert K == K2
+    C = torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        _cabi.check(_cabi.lib().pp_tc_gemm_ws(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, int(a_mn), int(b_mn), _stream()), "pp_tc_gemm_ws")
+    return C
+
+
 # ---------------------------------------------------------------------- RAFT correlation --
 
 def corr_volume(fmap1, fmap2):

@@ -25,6 +25,23 @@ def test_tc_gemm_nt_matches_fp64(batch, M, N, K, tma):
     assert err < 5e-6
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("batch,M,N,K", [(2, 128, 256, 64), (3, 196, 196, 256), (2, 784, 784, 256), (2, 256, 784, 784), (1, 132, 520, 72)])
+def test_tc_gemm_operand_layouts(batch, M, N, K, a_mn, b_mn):
+    """The TMA-fed kernel with operands in place in either layout (K-major [rows, K] or MN-major [K, rows]: TMA boxes of
+    32 rows x 16 k-lines and MN-major UMMA descriptors), fp32 operands split by the kernel's converter warps."""
+    from pixpro_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K)
+    A = torch.randn(batch, M, K, generator=g).to(DEV)
+    B = torch.randn(batch, N, K, generator=g).to(DEV)
+    Ain = A.transpose(1, 2).contiguous() if a_mn else A
+    Bin = B.transpose(1, 2).contiguous() if b_mn else B
+    C = ops.tc_gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn)
+    ref = torch.bmm(A.double(), B.double().transpose(1, 2))
+    err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-6, err
+
+
 @pytest.mark.parametrize("tma", [False, True], ids=["staged", "tma"])
 def test_tc_gemm_exact_on_small_integers(tma):
     """Integer-valued operands below 2^10 are exact in TF32 and sums below 2^24 are exact in
