@@ -86,6 +86,13 @@ PP_API int pp_concat_flow(const float* flows, int n, int64_t B, int H, int W, in
 PP_API int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int W, double alpha_1, double alpha_2,
                       int is_norm, int div_mode, uint8_t* mask, float* cycle, float* coords1_norm, void* stream);
 
+/* ---- a5 x2: both FB masks of apply_optical_flow — contrast/util.py:211-213 ----------------
+ * (forward_backward_consistency(fwd, bwd) and (bwd, fwd)) in one launch: fwd,bwd [B,2,H,W] ->
+ * mask_fwd, mask_bwd u8 [B,H,W].  The mask half of pp_flow_stage as its own entry, for callers
+ * that schedule it on another stream than the chain (sample chunks).                          */
+PP_API int pp_fb_masks(const float* fwd, const float* bwd, int64_t B, int H, int W, double alpha_1, double alpha_2,
+                int is_norm, int div_mode, uint8_t* mask_fwd, uint8_t* mask_bwd, void* stream);
+
 /* ---- a6 (a1+a3+a5 fused): flow stage of apply_optical_flow — contrast/util.py:175-248 ---
  * (use_flow_file, not use_flow_frames).  lo_fwd/lo_bwd in the loader layout [B,n,2,h,w]
  * (contrast/data/dataset.py:485-495).  flow_up: links are x8-upsampled on the fly, fused into the
@@ -230,6 +237,13 @@ PP_API int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_t ba
  * [batch][K][N]) and read in place by TMA boxes + MN-major UMMA descriptors; fp32 operands are split into hi / lo by the kernel's
  * converter warps (no workspace).  PP_ERR_INVALID when a shape is not streamable (no fallback).                     */
 PP_API int pp_tc_gemm_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, int a_mn, int b_mn, void* stream);
+/* The same with padded operands and sums over batch entries.  a_pitch / b_pitch: allocated length in floats (a multiple of 4;
+ * 0 = dense) of the operand's contiguous dimension (K when K-major, M resp. N when MN-major) — a [C, 49] map of the 7x7 grid
+ * (contrast/models/PixPro.py:339-363 at the published crop size) copied to a pitch of 52 floats is streamable, the dense one is not
+ * (TMA strides are multiples of 16 bytes).  kb > 1: C[g] = sum over the kb batch entries of group g of A[b] B[b]^T, C is
+ * [ceil(batch / kb)][M][N] — how the value transform's weight gradient sums its per-sample products.              */
+PP_API int pp_tc_gemm_ex(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, int a_mn, int b_mn, int a_pitch,
+                  int b_pitch, int kb, void* stream);
 
 /* ---- synchronised batch normalisation in three launches per direction (csrc/pp_syncbn.cu) ----------------------------
  * The reference converts every BatchNorm of encoder / projector to torch.nn.SyncBatchNorm (contrast/models/PixPro.py:289-292,

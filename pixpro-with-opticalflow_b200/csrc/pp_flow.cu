@@ -954,6 +954,20 @@ int pp_fb_consistency(const float* fwd, const float* bwd, int64_t B, int H, int 
                      (cudaStream_t)stream);
 }
 
+// Both FB masks of apply_optical_flow (contrast/util.py:211-213: the two forward_backward_consistency calls, arguments
+// swapped) in ONE launch — the second half of pp_flow_stage as its own entry, so a caller can run it on another stream
+// than the chain (sample chunks: the masks of chunk i under the up-sampling of chunk i+1; host_step.py).
+int pp_fb_masks(const float* fwd, const float* bwd, int64_t B, int H, int W, double alpha_1, double alpha_2, int is_norm,
+                int div_mode, uint8_t* mask_fwd, uint8_t* mask_bwd, void* stream) {
+    PP_REQUIRE(B >= 0 && H > 1 && W > 1, "pp_fb_masks: bad shape B=%lld H=%d W=%d", (long long)B, H, W);
+    PP_REQUIRE(B * 2 <= 65535, "pp_fb_masks: B=%lld exceeds 32767", (long long)B);
+    PP_REQUIRE((int64_t)H * W * 2 < (1ll << 31), "pp_fb_masks: frame too large");
+    if (B == 0) return PP_OK;
+    PP_REQUIRE(fwd && bwd && mask_fwd && mask_bwd, "pp_fb_masks: null pointer");
+    return launch_fb(fwd, bwd, mask_fwd, mask_bwd, nullptr, nullptr, 2, B, H, W, alpha_1, alpha_2, is_norm, div_mode,
+                     (cudaStream_t)stream);
+}
+
 // The n > 1 flow_up path needs no scratch since round 2 (the x8 up-sampling is fused into the chain kernel,
 // pp_chainup.cuh); the entry stays in the ABI and returns 0.
 int64_t pp_flow_stage_workspace(int64_t B, int n, int h, int w, int flow_up) {

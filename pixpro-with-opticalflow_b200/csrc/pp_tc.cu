@@ -69,7 +69,7 @@ extern "C" int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_
     float* b_hi = a_lo + batch * (int64_t)M * K;
     float* b_lo = b_hi + batch * (int64_t)N * K;
     static const int planes = [] { const char* e = getenv("PIXPRO_B200_TC2_PLANES"); return (e && e[0] == '1') ? 1 : 0; }();
-    if (tc2::applicable(K, A, B, workspace, C)) {
+    if (K % 4 == 0 && tc2::applicable(A, B, workspace, C)) {
         int rc;
         if (planes) {  // A/B switch: operands pre-split into hi / lo planes by a separate pass
             rc = tc2::launch_split(A, batch * (int64_t)M * K, a_hi, a_lo, st);
@@ -90,12 +90,23 @@ extern "C" int pp_tc_gemm_nt_ws(const float* A, const float* B, float* C, int64_
 // fp32 operands are streamed as they are and split into hi / lo by the kernel's converter warps.  No fallback: returns
 // PP_ERR_INVALID when the shape is not streamable (K, and the contiguous extent of an MN-major operand, must be multiples of 4).
 extern "C" int pp_tc_gemm_ws(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, int a_mn, int b_mn, void* stream) {
-    PP_REQUIRE(A && B && C, "pp_tc_gemm_ws: null pointer");
-    PP_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0, "pp_tc_gemm_ws: bad shape");
+    return pp_tc_gemm_ex(A, B, C, batch, M, N, K, a_mn, b_mn, 0, 0, 1, stream);
+}
+
+// The same with padded operands and sums over batch entries: a_pitch / b_pitch = allocated length (floats, % 4 == 0; 0 = dense) of
+// each operand's contiguous dimension (K for a K-major operand, M resp. N for an MN-major one) — how a [C, 49] map copied to a
+// pitch of 52 floats becomes streamable; kb > 1: C[g] = sum over the kb batch entries of group g of A[b] B[b]^T, C is
+// [ceil(batch / kb)][M][N] (the weight gradient of the 1x1 convolution sums per-sample products this way).
+extern "C" int pp_tc_gemm_ex(const float* A, const float* B, float* C, int64_t batch, int M, int N, int K, int a_mn, int b_mn, int a_pitch,
+                             int b_pitch, int kb, void* stream) {
+    PP_REQUIRE(A && B && C, "pp_tc_gemm_ex: null pointer");
+    PP_REQUIRE(batch > 0 && batch <= 65535 && M > 0 && N > 0 && K > 0 && kb >= 1 && a_pitch >= 0 && b_pitch >= 0, "pp_tc_gemm_ex: bad shape");
     tc2::Operands o{A, nullptr, B, nullptr, K};
     o.a_mn = a_mn != 0;
     o.b_mn = b_mn != 0;
-    const int rc = tc2::launch_tc2_sets("tc2_gemm", batch, M, N, &o, 1, tc::StoreC{C, M, N}, (cudaStream_t)stream, false);
-    PP_REQUIRE(rc >= 0, "pp_tc_gemm_ws: shape / alignment not streamable by TMA (K %% 4, contiguous extents %% 4, 16-byte aligned pointers)");
+    o.a_pitch = a_pitch;
+    o.b_pitch = b_pitch;
+    const int rc = tc2::launch_tc2_sets("tc2_gemm", batch, M, N, &o, 1, tc::StoreC{C, M, N}, (cudaStream_t)stream, false, kb);
+    PP_REQUIRE(rc >= 0, "pp_tc_gemm_ex: shape / alignment not streamable by TMA (contiguous extents or pitches %% 4, 16-byte aligned pointers)");
     return rc;
 }

@@ -169,7 +169,7 @@ struct EpNoAux {
 // accumulators the ring already holds the next tile's first chunks; barriers: full/empty per stage, acc_full/acc_empty.
 // BLO = false: the B operand is exact in TF32 (e.g. a 0/1 mask) — its lo plane is neither loaded nor multiplied.
 template <int TK, bool BLO, class EP>
-__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int K1, int batch, int a_bcast, int raw, EP ep) {
+__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int K1, int batch, int kb, int a_bcast, int raw, EP ep) {
     using C = Cfg<TK>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t tc2_smem_raw[];
@@ -183,9 +183,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
     float* epi = reinterpret_cast<float*>(tc2_smem_raw + (base - tc::smem_u32(tc2_smem_raw)) + RING_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MT = (M + TM - 1) / TM, NT = (N + TN - 1) / TN;
-    const int ntiles = batch * MT * NT;
+    // kb > 1 ("batch as K"): one output tile sums the products of kb consecutive batch entries, C[g] = sum_{b in group g} A[b] B[b]^T
+    // (the weight gradient of the 1x1 convolution: K = the pixels of a sample, summed over samples); set 1 is not used then.
+    const int ntiles = ((batch + kb - 1) / kb) * MT * NT;
     const int nchunk0 = (K + TK - 1) / TK;
-    const int nchunk = nchunk0 + (K1 + TK - 1) / TK;
+    const int nchunk = kb * nchunk0 + (K1 + TK - 1) / TK;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); tc::mbar_init(&conv[s], NCONV / 32); }
         tc::mbar_init(&acc_full, 1);
@@ -203,15 +205,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
             int g = 0;  // chunks issued so far by this CTA (ring position)
 #pragma unroll 1
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                const int nt = t % NT, mt = (t / NT) % MT, b = t / (NT * MT);
+                const int nt = t % NT, mt = (t / NT) % MT, bg = t / (NT * MT);
 #pragma unroll 1
                 for (int c = 0; c < nchunk; c++, g++) {
                     const int s = g % STAGES, round = g / STAGES;
                     if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage have completed
                     const uint32_t st = base + s * C::kStageBytes;
-                    const int set = c >= nchunk0 ? 1 : 0;
-                    const int k0 = (set ? c - nchunk0 : c) * TK;
-                    mbar_arrive_expect_tx(&full[s], (a_raw ? 1 : 2) * C::kATile + ((BLO && !b_raw) ? 2 : 1) * C::kBTile);
+                    const int set = c >= kb * nchunk0 ? 1 : 0;
+                    const int cc = set ? c - kb * nchunk0 : c;
+                    const int k0 = (kb > 1 ? cc % nchunk0 : cc) * TK;
+                    const int b = kb > 1 ? bg * kb + cc / nchunk0 : bg;  // a batch entry past the end reads as zeros (TMA fill)
+                    // a ragged last MN-major B tile brings only the 32-row groups the MMA (N = tn) reads
+                    const bool b_ragged = b_mn && nt * TN + TN > N;
+                    const int b_grps = b_ragged ? (min(TN, N - nt * TN) + 31) / 32 : TN / 32;
+                    const uint32_t b_plane = b_ragged ? (uint32_t)b_grps * (TK * 128) : C::kBTile;
+                    mbar_arrive_expect_tx(&full[s], (a_raw ? 1 : 2) * C::kATile + ((BLO && !b_raw) ? 2 : 1) * b_plane);
                     if (!a_raw && !a_mn) tma_load_3d(st, &maps.a_hi[set], k0, mt * TM, a_bcast ? 0 : b, &full[s]);
                     if (a_mn) {  // boxes of 32 rows x TK k-lines
                         if (mt * TM + TM <= M) {
@@ -233,10 +241,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
                             if (!b_raw) tma_load_4d(st + 2 * C::kATile, &maps.b_grp_hi[set], 0, k0, nt * (TN / 32), b, &full[s]);
                         } else {
 #pragma unroll
-                            for (int u = 0; u < TN / 32; u++) {
-                                tma_load_3d(st + 2 * C::kATile + C::kBTile + u * (TK * 128), &maps.b_lo[set], nt * TN + 32 * u, k0, b, &full[s]);
-                                if (!b_raw) tma_load_3d(st + 2 * C::kATile + u * (TK * 128), &maps.b_hi[set], nt * TN + 32 * u, k0, b, &full[s]);
-                            }
+                            for (int u = 0; u < TN / 32; u++)
+                                if (u < b_grps) {
+                                    tma_load_3d(st + 2 * C::kATile + C::kBTile + u * (TK * 128), &maps.b_lo[set], nt * TN + 32 * u, k0, b, &full[s]);
+                                    if (!b_raw) tma_load_3d(st + 2 * C::kATile + u * (TK * 128), &maps.b_hi[set], nt * TN + 32 * u, k0, b, &full[s]);
+                                }
                         }
                     } else if (b_raw) {
                         tma_load_3d(st + 2 * C::kATile + C::kBTile, &maps.b_lo[set], k0, nt * TN, b, &full[s]);
@@ -291,13 +300,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const __grid_const
             int g = 0;
 #pragma unroll 1
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int nt = t % NT;
+                const int b16 = (b_mn && nt * TN + TN > N) ? ((min(TN, N - nt * TN) + 31) / 32) * (TK * 128 / 16) : (int)(C::kBTile / 16);
 #pragma unroll 1
                 for (int c = 0; c < nchunk; c++, g++) {
                     const int s = g % STAGES, round = g / STAGES;
                     tc::mbar_wait(&full[s], round & 1);
                     uint8_t* st = tc2_smem_raw + (base - tc::smem_u32(tc2_smem_raw)) + s * C::kStageBytes;
                     if (a_raw) split_tile(st, st + C::kATile, C::kATile / 16, tid);
-                    if (b_raw) split_tile(st + 2 * C::kATile, st + 2 * C::kATile + C::kBTile, C::kBTile / 16, tid);
+                    if (b_raw) split_tile(st + 2 * C::kATile, st + 2 * C::kATile + C::kBTile, b16, tid);
                     tc::fence_smem_to_async();  // generic-proxy writes -> visible to the tensor core's operand reads
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&conv[s]);
@@ -409,37 +420,37 @@ static inline EncodeTiledFn encode_fn() {
 }
 // MN-major plane [batch][K][rows] fp32 viewed as a 3-D tensor (rows fastest); box = 32 rows x tk k-lines x 1, 128-byte swizzle of
 // 32-byte atoms
-static inline bool make_mn_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int tk) {
+static inline bool make_mn_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int tk, int pitch) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)K, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)rows * 4, (cuuint64_t)rows * K * 4};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * K * 4};
     cuuint32_t box[3] = {32, (cuuint32_t)tk, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // the same MN-major plane viewed 4-D: dims {32 rows, K, complete 32-row groups, batch}; box = 32 x tk x groups_per_tile x 1
-static inline bool make_mn_group_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int tk, int groups_per_tile) {
+static inline bool make_mn_group_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int tk, int groups_per_tile, int pitch) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     const int groups = rows / 32;  // complete groups only: a box never straddles the end of a k-line
     if (groups < groups_per_tile) {  // no tile is complete: the map is never used; encode a valid dummy (the 3-D map's geometry)
-        return make_mn_map(tm, base, batch, rows, K, tk);
+        return make_mn_map(tm, base, batch, rows, K, tk, pitch);
     }
     cuuint64_t dims[4] = {32, (cuuint64_t)K, (cuuint64_t)groups, (cuuint64_t)batch};
-    cuuint64_t strides[3] = {(cuuint64_t)rows * 4, 128, (cuuint64_t)rows * K * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, 128, (cuuint64_t)pitch * K * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)tk, (cuuint32_t)groups_per_tile, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // plane [batch][rows][K] fp32 viewed as a 3-D tensor (K fastest); box = tk x box_rows x 1, swizzle span = one box row
-static inline bool make_plane_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int box_rows, int tk) {
+static inline bool make_plane_map(CUtensorMap* tm, const float* base, int64_t batch, int rows, int K, int box_rows, int tk, int pitch) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)rows * K * 4};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)rows * pitch * 4};
     cuuint32_t box[3] = {(cuuint32_t)tk, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -459,22 +470,22 @@ static inline int num_sms() {  // of the current device
     return v;
 }
 
-static inline bool applicable(int K, const void* a, const void* b, const void* c, const void* d) {
+static inline bool applicable(const void* a, const void* b, const void* c, const void* d) {
     static const int off = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
-    return !off && K % 4 == 0 && a && c && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+    return !off && a && c && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
 }
 
 template <int TK, bool BLO, class EP>
-static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int M, int N, int K, int K1, int a_bcast, int raw, EP ep, cudaStream_t st) {
+static inline int launch_cfg(const char* what, const Maps& maps, int64_t batch, int kb, int M, int N, int K, int K1, int a_bcast, int raw, EP ep, cudaStream_t st) {
     auto kern = tc2_gemm_kernel<TK, BLO, EP>;
     static unsigned long long opted = 0;  // per template instantiation, one bit per device
     if (smem_opt_in(kern, (int)SMEM_BYTES, opted) != cudaSuccess) {
         set_error("%s: cudaFuncSetAttribute(%u B of shared memory) failed: %s", what, SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
         return PP_ERR_CUDA;
     }
-    const int64_t ntiles = batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN);
+    const int64_t ntiles = ((batch + kb - 1) / kb) * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN);
     const unsigned grid = (unsigned)(ntiles < num_sms() ? ntiles : num_sms());
-    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, K1, (int)batch, a_bcast, raw, ep));
+    PP_LAUNCH(what, st, kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, K, K1, (int)batch, kb, a_bcast, raw, ep));
     return check_launch(what);
 }
 
@@ -485,19 +496,24 @@ struct Operands {  // hi / lo planes of one product: A [batch][M][K] (or [M][K] 
     const float *a_hi, *a_lo, *b_hi, *b_lo;  // an operand given as ONE fp32 plane (split in the kernel): hi = the plane, lo = nullptr
     int K;
     bool a_mn = false, b_mn = false;  // the operand's plane(s) are MN-major: memory [batch][K][rows] (rows contiguous) instead of [batch][rows][K]
+    // allocated length (floats, a multiple of 4) of the contiguous dimension when it is padded: K for a K-major plane, rows for an
+    // MN-major one; 0 = dense.  E.g. the [C, 49] maps of the 7x7 grid copied to a pitch of 52 floats: TMA needs 16-byte strides.
+    int a_pitch = 0, b_pitch = 0;
 };
 template <bool BLO = true, class EP>
 static inline int launch_tc2_sets(const char* what, int64_t batch, int M, int N, const Operands* sets, int nsets, EP ep, cudaStream_t st,
-                                  bool a_bcast) {
-    if (batch > 65535 || nsets < 1 || nsets > 2) return -1;
+                                  bool a_bcast, int kb = 1) {
+    if (batch > 65535 || nsets < 1 || nsets > 2 || kb < 1 || (kb > 1 && nsets != 1)) return -1;
     const bool a_raw = sets[0].a_lo == nullptr, b_raw = BLO && sets[0].b_lo == nullptr;
     const bool a_mn = sets[0].a_mn, b_mn = sets[0].b_mn;
     if (b_mn && !BLO) return -1;
     for (int i = 0; i < nsets; i++) {
         if ((sets[i].a_lo == nullptr) != a_raw || (BLO && (sets[i].b_lo == nullptr) != b_raw)) return -1;  // same form in both sets
         if (sets[i].a_mn != a_mn || sets[i].b_mn != b_mn) return -1;
-        if (!applicable(sets[i].K, sets[i].a_hi, sets[i].a_lo, sets[i].b_hi, sets[i].b_lo)) return -1;
-        if ((a_mn && M % 4 != 0) || (b_mn && N % 4 != 0)) return -1;  // 16-byte row strides of the MN-major planes
+        if (!applicable(sets[i].a_hi, sets[i].a_lo, sets[i].b_hi, sets[i].b_lo)) return -1;
+        // 16-byte strides: the (possibly padded) contiguous dimension of every plane is a multiple of 4 floats
+        const int ap = sets[i].a_pitch ? sets[i].a_pitch : (a_mn ? M : sets[i].K), bp = sets[i].b_pitch ? sets[i].b_pitch : (b_mn ? N : sets[i].K);
+        if (ap % 4 != 0 || bp % 4 != 0 || ap < (a_mn ? M : sets[i].K) || bp < (b_mn ? N : sets[i].K)) return -1;
     }
     if (batch * (int64_t)((M + TM - 1) / TM) * ((N + TN - 1) / TN) >= (1ll << 31)) return -1;
     static const int mode = [] { const char* e = getenv("PIXPRO_B200_TC2"); return e ? atoi(e) : 1; }();
@@ -510,20 +526,21 @@ static inline int launch_tc2_sets(const char* what, int64_t batch, int M, int N,
         // raw operand: the single fp32 plane is what the "lo" map describes (it is loaded into the stage's lo slot)
         const float* a_lo_src = a_raw ? o.a_hi : o.a_lo;                  // what the stage's lo slot receives
         const float* b_lo_src = (BLO && !b_raw) ? o.b_lo : o.b_hi;
-        bool ok = a_mn ? (make_mn_map(&maps.a_lo[i], a_lo_src, abatch, M, o.K, tk) && make_mn_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, tk) &&
-                          make_mn_group_map(&maps.a_grp[i], a_lo_src, abatch, M, o.K, tk, TM / 32) &&
-                          make_mn_group_map(&maps.a_grp_hi[i], o.a_hi, abatch, M, o.K, tk, TM / 32))
-                       : (make_plane_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, TM, tk) && make_plane_map(&maps.a_lo[i], a_lo_src, abatch, M, o.K, TM, tk));
-        ok = ok && (b_mn ? (make_mn_map(&maps.b_lo[i], b_lo_src, batch, N, o.K, tk) && make_mn_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, tk) &&
-                            make_mn_group_map(&maps.b_grp[i], b_lo_src, batch, N, o.K, tk, TN / 32) &&
-                            make_mn_group_map(&maps.b_grp_hi[i], o.b_hi, batch, N, o.K, tk, TN / 32))
-                         : (make_plane_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, TN, tk) && make_plane_map(&maps.b_lo[i], b_lo_src, batch, N, o.K, TN, tk)));
+        const int ap = o.a_pitch ? o.a_pitch : (a_mn ? M : o.K), bp = o.b_pitch ? o.b_pitch : (b_mn ? N : o.K);
+        bool ok = a_mn ? (make_mn_map(&maps.a_lo[i], a_lo_src, abatch, M, o.K, tk, ap) && make_mn_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, tk, ap) &&
+                          make_mn_group_map(&maps.a_grp[i], a_lo_src, abatch, M, o.K, tk, TM / 32, ap) &&
+                          make_mn_group_map(&maps.a_grp_hi[i], o.a_hi, abatch, M, o.K, tk, TM / 32, ap))
+                       : (make_plane_map(&maps.a_hi[i], o.a_hi, abatch, M, o.K, TM, tk, ap) && make_plane_map(&maps.a_lo[i], a_lo_src, abatch, M, o.K, TM, tk, ap));
+        ok = ok && (b_mn ? (make_mn_map(&maps.b_lo[i], b_lo_src, batch, N, o.K, tk, bp) && make_mn_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, tk, bp) &&
+                            make_mn_group_map(&maps.b_grp[i], b_lo_src, batch, N, o.K, tk, TN / 32, bp) &&
+                            make_mn_group_map(&maps.b_grp_hi[i], o.b_hi, batch, N, o.K, tk, TN / 32, bp))
+                         : (make_plane_map(&maps.b_hi[i], o.b_hi, batch, N, o.K, TN, tk, bp) && make_plane_map(&maps.b_lo[i], b_lo_src, batch, N, o.K, TN, tk, bp)));
         if (!ok) return -1;
     }
     const int K0 = sets[0].K, K1 = nsets > 1 ? sets[1].K : 0;
     const int raw = (a_raw ? 1 : 0) | (b_raw ? 2 : 0) | (a_mn ? 4 : 0) | (b_mn ? 8 : 0);
-    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, raw, ep, st)
-                    : launch_cfg<16, BLO>(what, maps, batch, M, N, K0, K1, a_bcast ? 1 : 0, raw, ep, st);
+    return tk == 32 ? launch_cfg<32, BLO>(what, maps, batch, kb, M, N, K0, K1, a_bcast ? 1 : 0, raw, ep, st)
+                    : launch_cfg<16, BLO>(what, maps, batch, kb, M, N, K0, K1, a_bcast ? 1 : 0, raw, ep, st);
 }
 
 // Planes: A_hi/A_lo [batch][M][K] (or [M][K] shared by every batch entry: a_bcast), B_hi/B_lo [batch][N][K].

@@ -33,6 +33,7 @@ SIGNATURES = {
     "pp_normalize": (_i, [_vp, _l, _i, _i, _i, _i, _vp, _vp]),
     "pp_concat_flow": (_i, [_vp, _i, _l, _i, _i, _l, _l, _i, _i, _vp, _vp]),
     "pp_fb_consistency": (_i, [_vp, _vp, _l, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp]),
+    "pp_fb_masks": (_i, [_vp, _vp, _l, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp]),
     "pp_flow_stage_workspace": (_l, [_l, _i, _i, _i, _i]),
     "pp_flow_stage": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _l, _vp]),
     "pp_calc_mask_ratio": (_i, [_vp, _l, _i, _i, _vp, _vp]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "pp_bn_bwd_stats": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pp_bn_bwd_apply": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pp_tc_gemm_ws": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp]),
+    "pp_tc_gemm_ex": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pp_corr_volume": (_i, [_vp, _vp, _l, _i, _i, _i, _vp, _vp]),
     "pp_corr_pool": (_i, [_vp, _l, _i, _i, _vp, _vp]),
     "pp_corr_lookup": (_i, [_vp, _i, _vp, _l, _i, _i, _i, _i, _vp, _vp]),

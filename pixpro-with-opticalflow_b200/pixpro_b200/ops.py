@@ -173,6 +173,27 @@ def flow_stage(lo_fwd, lo_bwd, flow_up=True, alpha_1=0.01, alpha_2=0.5, is_norm=
     return ff, fb, (mf.view(torch.bool) if use_mask else None), (mb.view(torch.bool) if use_mask else None)
 
 
+def fb_masks(flow_fwd, flow_bwd, alpha_1=0.01, alpha_2=0.5, is_norm=False, out=None):
+    """Both FB masks of apply_optical_flow (contrast/util.py:211-213) in one launch (pp_fb_masks).
+    flow_fwd/flow_bwd [B,2,H,W] -> (mask_fwd, mask_bwd) u8 [B,H,W] (out=(mf, mb) to write in place)."""
+    f = _f32(flow_fwd, "flow_fwd")
+    b = _f32(flow_bwd, "flow_bwd")
+    assert f.shape == b.shape and f.ndim == 4 and f.shape[1] == 2 and f.is_contiguous() and b.is_contiguous()
+    B, _, H, W = f.shape
+    if out is not None:
+        mf, mb = out
+        for t_ in (mf, mb):
+            if tuple(t_.shape) != (B, H, W) or t_.dtype != torch.uint8 or not t_.is_contiguous() or not t_.is_cuda:
+                raise ValueError(f"fb_masks: out tensor must be contiguous CUDA uint8 of shape {(B, H, W)}")
+    else:
+        mf = torch.empty((B, H, W), device=f.device, dtype=torch.uint8)
+        mb = torch.empty((B, H, W), device=f.device, dtype=torch.uint8)
+    with torch.cuda.device(f.device):
+        _cabi.check(_cabi.lib().pp_fb_masks(_ptr(f), _ptr(b), B, H, W, float(alpha_1), float(alpha_2), int(is_norm),
+                                            _div_mode, _ptr(mf), _ptr(mb), _stream()), "pp_fb_masks")
+    return mf, mb
+
+
 def calc_mask_ratio(mask):
     """contrast/util.py:361-366"""
     m = _mask_u8(mask, "mask")
@@ -650,6 +671,24 @@ def tc_gemm(A, B, a_mn=False, b_mn=False):
     C = torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
     with torch.cuda.device(A.device):
         _cabi.check(_cabi.lib().pp_tc_gemm_ws(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, int(a_mn), int(b_mn), _stream()), "pp_tc_gemm_ws")
+    return C
+
+
+def tc_gemm_padded(A, B, M, N, K, a_mn=False, b_mn=False, kb=1):
+    """pp_tc_gemm_ex: like tc_gemm, but A / B may be padded along their contiguous dimension (the logical extents M, N, K are
+    given; the pitch is the tensor's last dimension) and kb > 1 sums the products of kb consecutive batch entries:
+    returns [ceil(batch / kb), M, N]."""
+    A = _f32(A, "A")
+    B = _f32(B, "B")
+    assert A.ndim == 3 and B.ndim == 3 and A.shape[0] == B.shape[0] and A.is_contiguous() and B.is_contiguous()
+    batch = A.shape[0]
+    assert A.shape[1] == (K if a_mn else M) and B.shape[1] == (K if b_mn else N)
+    a_pitch, b_pitch = A.shape[2], B.shape[2]
+    assert a_pitch >= (M if a_mn else K) and b_pitch >= (N if b_mn else K)
+    C = torch.empty(((batch + kb - 1) // kb, M, N), device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        _cabi.check(_cabi.lib().pp_tc_gemm_ex(_ptr(A), _ptr(B), _ptr(C), batch, M, N, K, int(a_mn), int(b_mn), a_pitch, b_pitch,
+                                              int(kb), _stream()), "pp_tc_gemm_ex")
     return C
 
 

@@ -95,6 +95,15 @@ def test_flow_stage_golden(ops, tag):
         assert rel_err(npy(ops.calc_mask_ratio(mf)), g["mask_ratio_fwd"]) < 1e-6
 
 
+@pytest.mark.parametrize("tag", ["n1_up", "n5_up", "n2_noup"])
+def test_fb_masks_entry_golden(ops, tag):
+    """pp_fb_masks (both FB masks of apply_optical_flow in one launch, util.py:211-213) on the reference's composite flows."""
+    g = load_golden("flow_stage_" + tag)
+    mf, mb = ops.fb_masks(cu(g["flow_fwd"]), cu(g["flow_bwd"]), 0.01, 0.5)
+    assert_bits_equal(npy(mf.view(torch.bool)), unpack_mask(g["mask_fwd"], mf.shape), "mask_fwd")
+    assert_bits_equal(npy(mb.view(torch.bool)), unpack_mask(g["mask_bwd"], mb.shape), "mask_bwd")
+
+
 @pytest.mark.parametrize("tag", ["full_n1", "full_n5"])
 def test_flow_stage_full_size_golden(ops, tag):
     g = load_golden("flow_stage_" + tag)

@@ -42,6 +42,33 @@ def test_tc_gemm_operand_layouts(batch, M, N, K, a_mn, b_mn):
     assert err < 5e-6, err
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("batch,M,N,K,kb", [(5, 256, 49, 256, 1), (9, 256, 256, 49, 4), (128, 256, 256, 49, 4), (3, 100, 25, 60, 2),
+                                            (2, 130, 300, 21, 1)])
+def test_tc_gemm_padded_and_batch_sums(batch, M, N, K, kb, a_mn, b_mn):
+    """pp_tc_gemm_ex: operands padded to a pitch of 4 floats along their contiguous dimension (the pad holds garbage that must
+    never be read: it is NaN here) and products summed over groups of kb batch entries (the last group may be short)."""
+    from pixpro_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K + kb)
+    A = torch.randn(batch, M, K, generator=g).to(DEV)
+    B = torch.randn(batch, N, K, generator=g).to(DEV)
+
+    def padded(t, mn):  # [batch, rows, K] -> its stored form with the last dimension padded to a multiple of 4 (+4: a real pad)
+        t = t.transpose(1, 2).contiguous() if mn else t
+        pitch = ((t.shape[2] + 3) // 4) * 4 + 4
+        out = torch.full((t.shape[0], t.shape[1], pitch), float("nan"), device=DEV)
+        out[:, :, :t.shape[2]] = t
+        return out
+
+    C = ops.tc_gemm_padded(padded(A, a_mn), padded(B, b_mn), M, N, K, a_mn=a_mn, b_mn=b_mn, kb=kb)
+    ref = torch.bmm(A.double(), B.double().transpose(1, 2))
+    groups = (batch + kb - 1) // kb
+    ref = torch.stack([ref[i * kb:(i + 1) * kb].sum(0) for i in range(groups)])
+    assert C.shape == ref.shape
+    err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-6, err
+
+
 @pytest.mark.parametrize("tma", [False, True], ids=["staged", "tma"])
 def test_tc_gemm_exact_on_small_integers(tma):
     """Integer-valued operands below 2^10 are exact in TF32 and sums below 2^24 are exact in
@@ -55,7 +82,7 @@ def test_tc_gemm_exact_on_small_integers(tma):
     assert torch.equal(C, ref)
 
 
-@pytest.mark.parametrize("B,Cin,Cout,G", [(128, 256, 256, 7), (5, 256, 256, 14), (3, 64, 96, 5)])
+@pytest.mark.parametrize("B,Cin,Cout,G", [(128, 256, 256, 7), (5, 256, 256, 14), (3, 64, 96, 5), (7, 32, 64, 7), (2, 8, 12, 3), (6, 256, 256, 13)])
 def test_conv1x1_matches_torch(B, Cin, Cout, G):
     """value transform (1x1 conv) forward/backward on the tensor cores vs cuDNN in true fp32."""
     import torch.nn.functional as F
