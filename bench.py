@@ -121,6 +121,7 @@ def kernel_work(kernel, B, n, G):
         "conv1x1 bias grad reduce": (0, 0),
         "ppm colnorm": (2 * 3 * cp, 0),       # three maps per view are normed per step (feat, val, out)
         "ppm coldiv": (2 * 3 * 2 * cp, 0),
+        "ppm colnorm+div": (2 * 3 * 2 * cp, 0),   # norm + scale in one pass: read each map once, write it once (planes not counted)
         "ppm normbwd": (2 * 3 * 3 * cp, 0),
         "loss_dot": (2 * 2 * cp, 0),
         "loss_pos": (2 * pp // 4, 0),

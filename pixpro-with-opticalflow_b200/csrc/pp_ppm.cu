@@ -115,6 +115,158 @@ __global__ void __launch_bounds__(256) normbwd_kernel(const float* __restrict__ 
     }
 }
 
+// ---- the same passes with the sample's 32-column tile held in registers: every tensor is read ONCE ------------------
+// colnorm_kernel + coldiv(_split)_kernel read their input twice (norm pass, then scale pass: 2 launches), normbwd_kernel
+// reads g and u twice inside one launch, and normbwd + coldiv_split write gy only to read it back.  At the 28x28 grid these
+// passes move 1.9 GB per step against 1.0 GB for one read per tensor and cost 0.40 ms of a 2.1 ms step.  Here a block owns
+// 32 columns x all C <= 8 RMAX channels of one sample: thread (x, y) keeps rows y, y + 8, ... of column x in registers, the
+// column sums take the same order as in the two-pass kernels (bit-identical norms and outputs), and the scaled values leave as
+// the fp32 tensor and / or its hi / lo planes.  grid (ceil(P/32), B), block (32, 8).
+constexpr int kRegRows = 32;  // C <= 256
+struct NormJob {  // one tensor of a colnorm_scale launch
+    const float* u;
+    float *nrm, *out, *hi, *lo;
+};
+struct NormJobs {
+    NormJob j[2];  // blockIdx.z selects: feat and val of a forward share one launch (fuller waves, one launch latency)
+};
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) colnorm_scale_kernel(NormJobs jobs, int C, int P) {
+    __shared__ float red[8][33];
+    __shared__ float nsh[32];
+    const NormJob& jb = jobs.j[blockIdx.z];
+    const float* u = jb.u;
+    float *nrm = jb.nrm, *out = jb.out, *hi = jb.hi, *lo = jb.lo;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const int64_t base = b * C * (int64_t)P + i;
+    float v[kRegRows];
+#pragma unroll
+    for (int r = 0; r < kRegRows; r++) {
+        const int c = threadIdx.y + 8 * r;
+        v[r] = (i < P && c < C) ? u[base + c * (int64_t)P] : 0.0f;  // plain loads: `out` may alias `u` (in-place final norm)
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kRegRows; r++)
+        if (threadIdx.y + 8 * r < C) s = fmaf(v[r], v[r], s);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t += red[r][threadIdx.x];
+        t = fmaxf(sqrtf(t), kNormEps);
+        nsh[threadIdx.x] = t;
+        if (i < P) nrm[b * P + i] = t;
+    }
+    __syncthreads();
+    const float n = nsh[threadIdx.x];
+    if (i < P) {
+#pragma unroll
+        for (int r = 0; r < kRegRows; r++) {
+            const int c = threadIdx.y + 8 * r;
+            if (c < C) {
+                const int64_t o = base + c * (int64_t)P;
+                const float q = v[r] / n;
+                if (out) out[o] = q;
+                if (SPLIT) {
+                    float h, l;
+                    tc2::split1(q, h, l);
+                    hi[o] = h;
+                    lo[o] = l;
+                }
+            }
+        }
+    }
+}
+// normbwd_kernel with g and u in registers; out (fp32, may be null when SPLIT) and / or the hi / lo planes of the result
+struct NormBwdJob {
+    const float *g, *u, *nu, *ndiv;
+    float *out, *hi, *lo;
+};
+struct NormBwdJobs {
+    NormBwdJob j[2];  // blockIdx.z selects: d_feat and d_val of a backward share one launch
+};
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) normbwd_reg_kernel(NormBwdJobs jobs, int C, int P) {
+    __shared__ float red[8][33];
+    __shared__ float dot[32];
+    const NormBwdJob& jb = jobs.j[blockIdx.z];
+    const float* __restrict__ g = jb.g;
+    const float* __restrict__ u = jb.u;
+    const float* __restrict__ nu = jb.nu;
+    const float* __restrict__ ndiv = jb.ndiv;
+    float* __restrict__ out = jb.out;
+    float* __restrict__ hi = jb.hi;
+    float* __restrict__ lo = jb.lo;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const int64_t base = b * C * (int64_t)P + i;
+    float rn = 1.0f, rdiv = 1.0f;
+    if (i < P) {
+        rn = nu ? 1.0f / nu[b * P + i] : 1.0f;
+        rdiv = 1.0f / ndiv[b * P + i];
+    }
+    float gv[kRegRows], uv[kRegRows];
+#pragma unroll
+    for (int r = 0; r < kRegRows; r++) {
+        const int c = threadIdx.y + 8 * r;
+        const bool in = i < P && c < C;
+        gv[r] = in ? __ldg(g + base + c * (int64_t)P) : 0.0f;
+        uv[r] = in ? __ldg(u + base + c * (int64_t)P) : 0.0f;
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kRegRows; r++)
+        if (threadIdx.y + 8 * r < C) s = fmaf(gv[r], uv[r] * rn, s);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t += red[r][threadIdx.x];
+        dot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (i < P) {
+        const float d = dot[threadIdx.x];
+#pragma unroll
+        for (int r = 0; r < kRegRows; r++) {
+            const int c = threadIdx.y + 8 * r;
+            if (c < C) {
+                const int64_t o = base + c * (int64_t)P;
+                const float q = (gv[r] - uv[r] * rn * d) * rdiv;
+                if (out) out[o] = q;
+                if (SPLIT) {
+                    float h, l;
+                    tc2::split1(q, h, l);
+                    hi[o] = h;
+                    lo[o] = l;
+                }
+            }
+        }
+    }
+}
+// PIXPRO_B200_PPMREG=0: the two-pass kernels (A/B switch)
+static inline bool ppm_reg_passes(int C) {
+    static const int off = [] { const char* e = getenv("PIXPRO_B200_PPMREG"); return (e && e[0] == '0') ? 1 : 0; }();
+    return !off && C <= 8 * kRegRows;
+}
+
+static inline NormJobs norm_jobs(NormJob a, NormJob b = NormJob{}) {
+    NormJobs j;
+    j.j[0] = a;
+    j.j[1] = b;
+    return j;
+}
+static inline NormBwdJobs normbwd_jobs(NormBwdJob a, NormBwdJob b = NormBwdJob{}) {
+    NormBwdJobs j;
+    j.j[0] = a;
+    j.j[1] = b;
+    return j;
+}
+
 // ---- batched register-tiled GEMM with functor operands ------------------------------------
 // Cmn = Σ_k A(m,k) B(k,n);  LA/LB: element loaders (b, m|n, k) -> float;  EP: epilogue.
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -425,16 +577,27 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
     if (ppm_small_supported(C, P))  // e.g. the 7x7 grid: one block per sample, one launch
         return ppm_fwd_small(feat, val, B, C, P, act, final_norm, out, sv.nx, sv.nv, sv.ny, sv.S, st);
     dim3 nb((P + 31) / 32, (unsigned)B), nt(32, 8);
-    PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(feat, C, P, sv.nx));
-    PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(val, C, P, sv.nv));
-    int rc = check_launch("colnorm_kernel");
-    if (rc) return rc;
+    const bool reg = ppm_reg_passes(C) && (ppm_tc2(C, P) || use_tensor_cores(P));  // norm + scale (+ split) in one pass per tensor
+    int rc = PP_OK;
+    if (!reg) {
+        PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(feat, C, P, sv.nx));
+        PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(val, C, P, sv.nv));
+        rc = check_launch("colnorm_kernel");
+        if (rc) return rc;
+    }
     // S[i][j] = Σ_c x̂[c][i] x̂[c][j]
     const int64_t total = B * (int64_t)C * P;
     if (ppm_tc2(C, P)) {
         // TMA route: normalise once (x̂, v̂ kept for the backward), then stream them in place
         const bool pre = ppm_presplit(P);
-        if (pre) {
+        const dim3 nb2(nb.x, nb.y, 2);
+        if (reg && pre) {
+            PP_LAUNCH("ppm colnorm+div", st, colnorm_scale_kernel<true><<<nb2, nt, 0, st>>>(
+                norm_jobs(NormJob{feat, sv.nx, sv.xh, sv.x_hi, sv.x_lo}, NormJob{val, sv.nv, sv.vh, sv.v_hi, sv.v_lo}), C, P));
+        } else if (reg) {
+            PP_LAUNCH("ppm colnorm+div", st, colnorm_scale_kernel<false><<<nb2, nt, 0, st>>>(
+                norm_jobs(NormJob{feat, sv.nx, sv.xh, nullptr, nullptr}, NormJob{val, sv.nv, sv.vh, nullptr, nullptr}), C, P));
+        } else if (pre) {
             PP_LAUNCH("ppm coldiv", st, coldiv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, sv.nx, C, P, total, sv.xh, sv.x_hi, sv.x_lo));
             PP_LAUNCH("ppm coldiv", st, coldiv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(val, sv.nv, C, P, total, sv.vh, sv.v_hi, sv.v_lo));
         } else {
@@ -460,8 +623,13 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
         }
     } else if (use_tensor_cores(P)) {
         // normalise once (x̂, v̂ kept for backward), then the two contractions on the tensor cores
-        PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, sv.nx, C, P, total, sv.xh));
-        PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(val, sv.nv, C, P, total, sv.vh));
+        if (reg) {
+            PP_LAUNCH("ppm colnorm+div", st, colnorm_scale_kernel<false><<<dim3(nb.x, nb.y, 2), nt, 0, st>>>(
+                norm_jobs(NormJob{feat, sv.nx, sv.xh, nullptr, nullptr}, NormJob{val, sv.nv, sv.vh, nullptr, nullptr}), C, P));
+        } else {
+            PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, sv.nx, C, P, total, sv.xh));
+            PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(val, sv.nv, C, P, total, sv.vh));
+        }
         rc = check_launch("ppm coldiv");
         if (rc) return rc;
         rc = launch_tc("ppm S (tcgen05)", B, P, P, C, TcLdT{sv.xh, C, P}, TcLdT{sv.xh, C, P}, TcStN{sv.S, P, P}, st);
@@ -476,8 +644,12 @@ int pp_ppm_fwd(const float* feat, const float* val, int64_t B, int C, int P, dou
         if (rc) return rc;
     }
     if (final_norm) {
-        PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(out, C, P, sv.ny));
-        PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, sv.ny, C, P, total, out));
+        if (ppm_reg_passes(C)) {
+            PP_LAUNCH("ppm colnorm+div", st, colnorm_scale_kernel<false><<<nb, nt, 0, st>>>(norm_jobs(NormJob{out, sv.ny, out, nullptr, nullptr}), C, P));
+        } else {
+            PP_LAUNCH("ppm colnorm", st, colnorm_kernel<<<nb, nt, 0, st>>>(out, C, P, sv.ny));
+            PP_LAUNCH("ppm coldiv", st, coldiv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, sv.ny, C, P, total, out));
+        }
         rc = check_launch("ppm final normalize");
     }
     return rc;
@@ -500,12 +672,17 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
     dim3 nb((P + 31) / 32, (unsigned)B), nt(32, 8);
     int rc;
     const float* gyp = g;
-    if (final_norm) {  // gy = (g − ŷ (g·ŷ)) / ny ; `out` is ŷ
-        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(g, out, nullptr, sv.ny, C, P, gy));
+    const bool regp = ppm_reg_passes(C);
+    // pre-split TMA route with the final normalisation: gy leaves its pass directly as hi / lo planes (and as fp32: the
+    // fallback below reads it), one launch instead of normbwd + split
+    const bool fuse_gy = final_norm && regp && ppm_tc2(C, P) && ppm_presplit(P) && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
+    if (final_norm && !fuse_gy) {  // gy = (g − ŷ (g·ŷ)) / ny ; `out` is ŷ
+        if (regp) PP_LAUNCH("ppm normbwd", st, normbwd_reg_kernel<false><<<nb, nt, 0, st>>>(normbwd_jobs(NormBwdJob{g, out, nullptr, sv.ny, gy, nullptr, nullptr}), C, P));
+        else PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(g, out, nullptr, sv.ny, C, P, gy));
         rc = check_launch("ppm normbwd(out)");
         if (rc) return rc;
-        gyp = gy;
     }
+    if (final_norm) gyp = gy;
     if (ppm_tc2(C, P) && (reinterpret_cast<uintptr_t>(gyp) & 15) == 0) {  // gy is streamed by TMA as it is: 16-byte aligned
         float* f = gxh + B * (int64_t)C * P;
         const int64_t pp2 = B * (int64_t)P * P;
@@ -516,7 +693,8 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
             float *gh = sym_lo + pp2, *gl = gh + B * (int64_t)C * P;
             gy_hi = gh; gy_lo = gl; x_hi = sv.x_hi; x_lo = sv.x_lo; v_hi = sv.v_hi; v_lo = sv.v_lo;
             const int64_t total = B * (int64_t)C * P;
-            PP_LAUNCH("ppm coldiv", st, coldiv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gyp, nullptr, C, P, total, nullptr, gh, gl));
+            if (fuse_gy) PP_LAUNCH("ppm normbwd", st, normbwd_reg_kernel<true><<<nb, nt, 0, st>>>(normbwd_jobs(NormBwdJob{g, out, nullptr, sv.ny, gy, gh, gl}), C, P));
+            else PP_LAUNCH("ppm coldiv", st, coldiv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gyp, nullptr, C, P, total, nullptr, gh, gl));
             rc = check_launch("ppm split(gy)");
             if (rc) return rc;
         }
@@ -541,8 +719,14 @@ int pp_ppm_bwd(const float* feat, const float* val, const float* out, const floa
             rc = launch_tc("ppm gxh (tcgen05)", B, C, P, P, TcLdN{sv.xh, C, P}, TcLdSymN{gS, P}, TcStN{gxh, C, P}, st);
             if (rc) return rc;
         }
-        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gxh, sv.xh, nullptr, sv.nx, C, P, d_feat_sim));
-        PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gvh, sv.vh, nullptr, sv.nv, C, P, d_val));
+        if (regp) {
+            PP_LAUNCH("ppm normbwd", st, normbwd_reg_kernel<false><<<dim3(nb.x, nb.y, 2), nt, 0, st>>>(
+                normbwd_jobs(NormBwdJob{gxh, sv.xh, nullptr, sv.nx, d_feat_sim, nullptr, nullptr},
+                             NormBwdJob{gvh, sv.vh, nullptr, sv.nv, d_val, nullptr, nullptr}), C, P));
+        } else {
+            PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gxh, sv.xh, nullptr, sv.nx, C, P, d_feat_sim));
+            PP_LAUNCH("ppm normbwd", st, normbwd_kernel<<<nb, nt, 0, st>>>(gvh, sv.vh, nullptr, sv.nv, C, P, d_val));
+        }
         return check_launch("ppm normbwd(in)");
     }
     // gS[i][j] = (Σ_c gy[c][i] v̂[c][j]) A'(S[i][j])
