@@ -346,8 +346,6 @@ def make_hot_path(ctx, batch, n_frames, grid):
 
     def hot_path(t, sparse=False, overlap=True):
         """One pass of the path on device-resident tensors t; returns (loss, pos stats, grads)."""
-        f1 = t["feat1"].detach().requires_grad_(True)
-        f2 = t["feat2"].detach().requires_grad_(True)
         w = t["w"].detach().requires_grad_(True)
         bias = t["bias"].detach().requires_grad_(True)
         cur = torch.cuda.current_stream(dev)
@@ -357,9 +355,10 @@ def make_hot_path(ctx, batch, n_frames, grid):
         ppm_stream = ctx.side if overlap else cur
         ppm_stream.wait_stream(cur)
         with torch.cuda.stream(ppm_stream):
-            # as PixPro.forward does: both views through the PPM as one batch
-            f12 = torch.cat([f1, f2], dim=0)
-            pred12 = ops.ppm(f12, ops.conv1x1(f12, w, bias), GAMMA, CLAMP, final_norm=True)
+            # as PixPro.forward does: both views through the PPM as one batch (the leaf is the joint tensor, so the
+            # feature gradient arrives in one piece)
+            f12 = torch.cat([t["feat1"], t["feat2"]], dim=0).requires_grad_(True)
+            pred12 = ops.featprop(f12, w, bias, GAMMA, CLAMP, final_norm=True)  # value transform + PPM, one autograd node
         if use_flow and sparse:
             pair = ops.LazyFlowPair(t["lo_f"], t["lo_b"], flow_up=True, alpha_1=ALPHA1, alpha_2=ALPHA2)
             (ff, fb), (mf, mb) = pair.flow, pair.mask
@@ -369,14 +368,14 @@ def make_hot_path(ctx, batch, n_frames, grid):
             ff = fb = mf = mb = None
         cur.wait_stream(ppm_stream)
         pred12.record_stream(cur)
-        pred1, pred2 = pred12.chunk(2, dim=0)
-        # both loss directions in one launch
-        l12, pn, _ = ops.regression_loss_pair(pred1, t["k2"], t["c1"], t["c2"], pred2, t["k1"], t["c2"], t["c1"], POS_RATIO,
-                                              flow1=ff, flow2=fb, size=size, mask1=mf, mask2=mb)
-        loss = l12[0] + l12[1]
+        f12.record_stream(cur)
+        # both loss directions in one launch, on the joint prediction tensor: loss_1 + loss_2 and one gradient tensor
+        loss, _, pn, _ = ops.regression_loss_pair(pred12, t["k2"], t["c1"], t["c2"], None, t["k1"], t["c2"], t["c1"], POS_RATIO,
+                                                  flow1=ff, flow2=fb, size=size, mask1=mf, mask2=mb)
         pn1, pn2 = pn[0], pn[1]
         loss.backward()
-        return loss.detach(), pn1, pn2, f1.grad, f2.grad
+        B = t["feat1"].shape[0]
+        return loss.detach(), pn1, pn2, f12.grad[:B], f12.grad[B:]
 
     return hot_path, d, pinned
 

@@ -91,9 +91,13 @@ def regression_loss_pair(q1, k1, coord_q1, coord_k1, q2, k2, coord_q2, coord_k2,
         raise NotImplementedError("the --debug image dump of the reference (debug_utils) is out of scope")
     cq1, ck1, flow1, size1, mask1 = _unpack_coords(coord_q1, coord_k1)
     cq2, ck2, flow2, size2, mask2 = _unpack_coords(coord_q2, coord_k2)
+    size = size1 if size1 is not None else size2
+    if q2 is None:  # q1 = [pred_1; pred_2] as one tensor: the sum and its gradient in one piece (ops._RegressionLossPairJoint)
+        loss, _, pos_num, pos_mean = _ops.regression_loss_pair(q1, k1, cq1, ck1, None, k2, cq2, ck2, pos_ratio, flow1=flow1,
+                                                               flow2=flow2, size=size, mask1=mask1, mask2=mask2)
+        return loss, [[pos_num[0], pos_mean[0]], [pos_num[1], pos_mean[1]]]
     loss, pos_num, pos_mean = _ops.regression_loss_pair(q1, k1, cq1, ck1, q2, k2, cq2, ck2, pos_ratio, flow1=flow1,
-                                                        flow2=flow2, size=size1 if size1 is not None else size2,
-                                                        mask1=mask1, mask2=mask2)
+                                                        flow2=flow2, size=size, mask1=mask1, mask2=mask2)
     return loss[0] + loss[1], [[pos_num[0], pos_mean[0]], [pos_num[1], pos_mean[1]]]
 
 
@@ -234,7 +238,11 @@ class PixPro(BaseModel):
         return _ops.ppm(feat, self._value(feat), self.pixpro_p, self.pixpro_clamp_value, final_norm=False)
 
     def _featprop_normalized(self, feat):
-        # featprop followed by F.normalize(dim=1) (PixPro.py:379-380) in one fused op
+        # featprop followed by F.normalize(dim=1) (PixPro.py:379-380) in one fused op; with the published single-conv value
+        # transform the conv and the PPM are one autograd node (the two gradients of `feat` meet in the conv's epilogue)
+        vt = self.value_transform
+        if isinstance(vt, nn.Conv2d) and vt.kernel_size == (1, 1) and feat.is_cuda:
+            return _ops.featprop(feat, vt.weight, vt.bias, self.pixpro_p, self.pixpro_clamp_value, final_norm=True)
         return _ops.ppm(feat, self._value(feat), self.pixpro_p, self.pixpro_clamp_value, final_norm=True)
 
     def regression_loss(self, x, y):
@@ -247,7 +255,7 @@ class PixPro(BaseModel):
         proj_1 = self.projector(feat_1)
         feat_2 = self.encoder(im_2)
         proj_2 = self.projector(feat_2)
-        pred_1, pred_2 = self._featprop_normalized(torch.cat([proj_1, proj_2], dim=0)).chunk(2, dim=0)
+        pred_12 = self._featprop_normalized(torch.cat([proj_1, proj_2], dim=0))  # [pred_1; pred_2]
 
         ins = self.pixpro_ins_loss_weight > 0.
         if ins:
@@ -272,7 +280,8 @@ class PixPro(BaseModel):
                     proj_instance_2_ng = _ins(self.projector_instance_k(feat_2_ng))
 
         # pixel-level loss, both directions (PixPro.py:429-432), fused into one launch
-        loss, pos_num_list = regression_loss_pair(pred_1, proj_2_ng, coord1, coord2, pred_2, proj_1_ng, coord2, coord1,
+        # (the predictions stay one tensor: no chunk / cat / 2-vector glue kernels between the loss and the PPM backward)
+        loss, pos_num_list = regression_loss_pair(pred_12, proj_2_ng, coord1, coord2, None, proj_1_ng, coord2, coord1,
                                                   self.pixpro_pos_ratio)
 
         if ins:

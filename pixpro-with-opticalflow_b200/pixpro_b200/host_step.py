@@ -143,16 +143,14 @@ class HostPixelStep:
             f12 = torch.cat([t["feat1"], t["feat2"]], dim=0).requires_grad_(True)
             wg = w.detach().requires_grad_(True)
             bg = bias.detach().requires_grad_(True)
-            pred12 = ops.ppm(f12, ops.conv1x1(f12, wg, bg), self.gamma, self.clamp, final_norm=True)
+            pred12 = ops.featprop(f12, wg, bg, self.gamma, self.clamp, final_norm=True)
         main.wait_event(self.ready)
         main.wait_stream(self.aux)
         if not capturing:
             for v in list(t.values()) + [pred12, f12]:
                 v.record_stream(main)
-        pred1, pred2 = pred12.chunk(2, dim=0)
-        l12, pn, _ = ops.regression_loss_pair(pred1, t["k2"], t["c1"], t["c2"], pred2, t["k1"], t["c2"], t["c1"],
-                                              self.pos_ratio, flow1=ff, flow2=fb, size=self.size, mask1=mf, mask2=mb)
-        loss = l12[0] + l12[1]
+        loss, _, pn, _ = ops.regression_loss_pair(pred12, t["k2"], t["c1"], t["c2"], None, t["k1"], t["c2"], t["c1"],
+                                                  self.pos_ratio, flow1=ff, flow2=fb, size=self.size, mask1=mf, mask2=mb)
         loss.backward()
         B = t["feat1"].shape[0]
         self.out["loss"].copy_(loss.detach(), non_blocking=True)

@@ -408,54 +408,62 @@ def regression_loss(q, k, coord_q, coord_k, pos_ratio=0.5, flow=None, size=None,
     return _RegressionLoss.apply(q, k.detach(), coord_q, coord_k, flow, mask, size, pos_ratio, debug)
 
 
+def _loss_pair_launch(q1, q2, k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2, size, pos_ratio, warped1, warped2, dqs=None):
+    """One pp_regression_loss_pair(_warped) launch; returns (loss [2], pos_num [2,B], pos_mean [2,B], [dq1, dq2])."""
+    import ctypes
+    qs = [_f32(q1, "q1"), _f32(q2, "q2")]
+    ks = [_f32(k1, "k1"), _f32(k2, "k2")]
+    cqs = [_f32(cq1, "coord_q1"), _f32(cq2, "coord_q2")]
+    cks = [_f32(ck1, "coord_k1"), _f32(ck2, "coord_k2")]
+    B, C, G, G2 = qs[0].shape
+    assert G == G2 and all(t.shape == qs[0].shape for t in qs + ks) and all(t.shape == (B, 10) for t in cqs + cks)
+    dev = qs[0].device
+    flows = [None if f is None else _f32(f, "flow") for f in (flow1, flow2)]
+    masks = [None if m is None else _mask_u8(m, "mask") for m in (mask1, mask2)]
+    Hin = Win = 0
+    for f in flows:
+        if f is not None:
+            Hin, Win = f.shape[-2:]
+    H_orig, W_orig = size
+    L = _cabi.lib()
+    wsz = L.pp_regression_loss_workspace(B, C, G)
+    ws = [torch.empty((wsz,), device=dev, dtype=torch.uint8) for _ in range(2)]
+    loss = torch.empty((2,), device=dev, dtype=torch.float32)
+    pos_num = torch.empty((2, B), device=dev, dtype=torch.float32)
+    pos_mean = torch.empty((2, B), device=dev, dtype=torch.float32)
+    if dqs is None:
+        dqs = [torch.empty_like(qs[0]), torch.empty_like(qs[1])]
+
+    def table(ts):
+        return (ctypes.c_void_p * 2)(*[None if t is None else t.data_ptr() for t in ts])
+
+    keep = [table(qs), table(ks), table(cqs), table(cks), table(flows), table(masks), table([loss[0:], loss[1:]]),
+            table([pos_num[0], pos_num[1]]), table([pos_mean[0], pos_mean[1]]), table(dqs), table(ws)]
+    ptrs = [ctypes.cast(t, ctypes.c_void_p) for t in keep]
+    with torch.cuda.device(dev):
+        if warped1 is not None:
+            wps = [_req(warped1, "warped1"), _req(warped2, "warped2")]
+            assert all(f is None for f in flows + masks) and all(t.shape == (3, B, G * G) for t in wps)
+            wt = table(wps)
+            _cabi.check(L.pp_regression_loss_pair_warped(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3],
+                                                         ctypes.cast(wt, ctypes.c_void_p), H_orig, W_orig, float(pos_ratio),
+                                                         _div_mode, ptrs[6], ptrs[7], ptrs[8], ptrs[9], ptrs[10], _stream()),
+                        "pp_regression_loss_pair_warped")
+        else:
+            _cabi.check(L.pp_regression_loss_pair(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3], ptrs[4], Hin, Win, ptrs[5],
+                                                  H_orig, W_orig, float(pos_ratio), _div_mode, ptrs[6], ptrs[7], ptrs[8],
+                                                  ptrs[9], ptrs[10], _stream()), "pp_regression_loss_pair")
+    return loss, pos_num, pos_mean, dqs
+
+
 class _RegressionLossPair(torch.autograd.Function):
     """Both directions of the pixel loss (PixPro.py:429-430) in one launch."""
 
     @staticmethod
     def forward(ctx, q1, q2, k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2, size, pos_ratio, warped1=None,
                 warped2=None):
-        import ctypes
-        qs = [_f32(q1, "q1"), _f32(q2, "q2")]
-        ks = [_f32(k1, "k1"), _f32(k2, "k2")]
-        cqs = [_f32(cq1, "coord_q1"), _f32(cq2, "coord_q2")]
-        cks = [_f32(ck1, "coord_k1"), _f32(ck2, "coord_k2")]
-        B, C, G, G2 = qs[0].shape
-        assert G == G2 and all(t.shape == qs[0].shape for t in qs + ks) and all(t.shape == (B, 10) for t in cqs + cks)
-        dev = qs[0].device
-        flows = [None if f is None else _f32(f, "flow") for f in (flow1, flow2)]
-        masks = [None if m is None else _mask_u8(m, "mask") for m in (mask1, mask2)]
-        Hin = Win = 0
-        for f in flows:
-            if f is not None:
-                Hin, Win = f.shape[-2:]
-        H_orig, W_orig = size
-        L = _cabi.lib()
-        wsz = L.pp_regression_loss_workspace(B, C, G)
-        ws = [torch.empty((wsz,), device=dev, dtype=torch.uint8) for _ in range(2)]
-        loss = torch.empty((2,), device=dev, dtype=torch.float32)
-        pos_num = torch.empty((2, B), device=dev, dtype=torch.float32)
-        pos_mean = torch.empty((2, B), device=dev, dtype=torch.float32)
-        dqs = [torch.empty_like(qs[0]), torch.empty_like(qs[1])]
-
-        def table(ts):
-            return (ctypes.c_void_p * 2)(*[None if t is None else t.data_ptr() for t in ts])
-
-        keep = [table(qs), table(ks), table(cqs), table(cks), table(flows), table(masks), table([loss[0:], loss[1:]]),
-                table([pos_num[0], pos_num[1]]), table([pos_mean[0], pos_mean[1]]), table(dqs), table(ws)]
-        ptrs = [ctypes.cast(t, ctypes.c_void_p) for t in keep]
-        with torch.cuda.device(dev):
-            if warped1 is not None:
-                wps = [_req(warped1, "warped1"), _req(warped2, "warped2")]
-                assert all(f is None for f in flows + masks) and all(t.shape == (3, B, G * G) for t in wps)
-                wt = table(wps)
-                _cabi.check(L.pp_regression_loss_pair_warped(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3],
-                                                             ctypes.cast(wt, ctypes.c_void_p), H_orig, W_orig, float(pos_ratio),
-                                                             _div_mode, ptrs[6], ptrs[7], ptrs[8], ptrs[9], ptrs[10], _stream()),
-                            "pp_regression_loss_pair_warped")
-            else:
-                _cabi.check(L.pp_regression_loss_pair(ptrs[0], ptrs[1], B, C, G, ptrs[2], ptrs[3], ptrs[4], Hin, Win, ptrs[5],
-                                                      H_orig, W_orig, float(pos_ratio), _div_mode, ptrs[6], ptrs[7], ptrs[8],
-                                                      ptrs[9], ptrs[10], _stream()), "pp_regression_loss_pair")
+        loss, pos_num, pos_mean, dqs = _loss_pair_launch(q1, q2, k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2, size,
+                                                         pos_ratio, warped1, warped2)
         ctx.save_for_backward(dqs[0], dqs[1])
         ctx.mark_non_differentiable(pos_num, pos_mean)
         return loss, pos_num, pos_mean
@@ -466,9 +474,37 @@ class _RegressionLossPair(torch.autograd.Function):
         return (dq1 * g_loss[0], dq2 * g_loss[1]) + (None,) * 14
 
 
+class _RegressionLossPairJoint(torch.autograd.Function):
+    """The same launch for predictions that arrive as ONE tensor q12 = [q1; q2] (both views went through the PPM as one
+    batch, PixPro.py:420-430) and a loss that is consumed as the sum of the two directions (`loss = l1 + l2`, :432): the
+    gradient leaves as one tensor too.  Against chunk() + _RegressionLossPair + `l[0] + l[1]` this removes eight small
+    autograd kernels (select / zeros / copy / add of the 2-vector, two multiplies, the cat of the chunk's backward) from the
+    critical path between the loss and the PPM backward."""
+
+    @staticmethod
+    def forward(ctx, q12, k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2, size, pos_ratio, warped1=None, warped2=None):
+        q12 = _f32(q12, "q12")
+        B = q12.shape[0] // 2
+        dq12 = torch.empty_like(q12)
+        loss, pos_num, pos_mean, _ = _loss_pair_launch(q12[:B], q12[B:], k1, k2, cq1, ck1, cq2, ck2, flow1, flow2, mask1, mask2,
+                                                       size, pos_ratio, warped1, warped2, dqs=[dq12[:B], dq12[B:]])
+        ctx.save_for_backward(dq12)
+        ctx.mark_non_differentiable(loss, pos_num, pos_mean)
+        return loss.sum(), loss, pos_num, pos_mean
+
+    @staticmethod
+    def backward(ctx, g_sum, *unused):
+        dq12, = ctx.saved_tensors
+        return (dq12 * g_sum,) + (None,) * 14
+
+
 def regression_loss_pair(q1, k1, coord_q1, coord_k1, q2, k2, coord_q2, coord_k2, pos_ratio=0.5, flow1=None, flow2=None,
                          size=None, mask1=None, mask2=None, warped1=None, warped2=None):
     """Two regression_loss calls (the two directions of PixPro.forward) fused into one launch.
+
+    q2=None: q1 is the joint prediction tensor [q1; q2] of shape [2B,C,G,G] (both views went through the PPM as one batch)
+    and the result is (loss_1 + loss_2, loss [2], pos_num [2,B], pos_mean [2,B]) with only the sum differentiable — the
+    gradient reaches the joint tensor in one piece (_RegressionLossPairJoint).
 
     flow1/flow2: dense composites (+ dense masks), or the two LazyFlows of one LazyFlowPair (sparse
     correspondence: one pp_sparse_corr launch serves both directions); or pass warped1/warped2 directly.
@@ -493,6 +529,9 @@ def regression_loss_pair(q1, k1, coord_q1, coord_k1, q2, k2, coord_q2, coord_k2,
         flow1 = flow2 = mask1 = mask2 = None
     if warped1 is not None or warped2 is not None:
         assert warped1 is not None and warped2 is not None and size is not None and flow1 is None and flow2 is None
+        if q2 is None:
+            return _RegressionLossPairJoint.apply(q1, k1.detach(), k2.detach(), coord_q1, coord_k1, coord_q2, coord_k2, None, None,
+                                                  None, None, _size_hw(size), pos_ratio, warped1, warped2)
         return _RegressionLossPair.apply(q1, q2, k1.detach(), k2.detach(), coord_q1, coord_k1, coord_q2, coord_k2, None, None,
                                          None, None, _size_hw(size), pos_ratio, warped1, warped2)
     if size is None:
@@ -502,6 +541,9 @@ def regression_loss_pair(q1, k1, coord_q1, coord_k1, q2, k2, coord_q2, coord_k2,
         else:
             size = (coord_q1[0][9].item(), coord_q1[0][8].item())
     size = _size_hw(size)
+    if q2 is None:
+        return _RegressionLossPairJoint.apply(q1, k1.detach(), k2.detach(), coord_q1, coord_k1, coord_q2, coord_k2, flow1, flow2,
+                                              mask1, mask2, size, pos_ratio)
     return _RegressionLossPair.apply(q1, q2, k1.detach(), k2.detach(), coord_q1, coord_k1, coord_q2, coord_k2, flow1, flow2,
                                      mask1, mask2, size, pos_ratio)
 
@@ -591,47 +633,113 @@ class _Conv1x1(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         x, w2 = ctx.saved_tensors
-        dy = _f32(dy, "grad_out")
-        B, Cin = x.shape[:2]
-        P = x[0, 0].numel()
-        Cout = w2.shape[0]
-        L = _cabi.lib()
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        dx = torch.empty_like(x) if need_x else None
-        dw = torch.empty_like(w2) if need_w else None
-        db = torch.empty((Cout,), device=x.device, dtype=torch.float32) if need_b else None
-        ws = torch.empty((L.pp_conv1x1_bwd_workspace(B, Cin, Cout, P),), device=x.device, dtype=torch.uint8)
-        with torch.cuda.device(x.device):
-            if need_x and (need_w or need_b) and not _serial:
-                # dgrad and wgrad (+ bias grad) are independent, latency-bound launches: issue the parameter
-                # gradients on a side stream (all buffers were allocated on the current one, which joins below)
-                cur = torch.cuda.current_stream(x.device)
-                side = _side_stream(x.device)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, _ptr(dw), None, _ptr(ws),
-                                                 _stream()), "pp_conv1x1_bwd")
-                if need_b:  # the bias gradient is a third independent launch
-                    side2 = _side_stream(x.device, 1)
-                    side2.wait_stream(cur)
-                    with torch.cuda.stream(side2):
-                        _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, None, _ptr(db), _ptr(ws),
-                                                     _stream()), "pp_conv1x1_bwd")
-                _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), None, None, _ptr(ws),
-                                             _stream()), "pp_conv1x1_bwd")
-                cur.wait_stream(side)
-                if need_b:
-                    cur.wait_stream(side2)
-            else:
-                _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
-                                             _stream()), "pp_conv1x1_bwd")
+        dx, dw, db = _conv1x1_backward(x, w2, dy, need_x, need_w, need_b)
         return dx, (dw.view(ctx.w_shape) if dw is not None else None), db
+
+
+def _conv1x1_backward(x, w2, dy, need_x, need_w, need_b, dx_acc=None):
+    """dx, dw, db of the 1x1 convolution; dx_acc: a tensor the data gradient is ADDED to (pp_conv1x1_bwd_acc) and returned."""
+    dy = _f32(dy, "grad_out")
+    B, Cin = x.shape[:2]
+    P = x[0, 0].numel()
+    Cout = w2.shape[0]
+    L = _cabi.lib()
+    bwd = L.pp_conv1x1_bwd_acc if dx_acc is not None else L.pp_conv1x1_bwd
+    dx = dx_acc if dx_acc is not None else (torch.empty_like(x) if need_x else None)
+    need_x = need_x or dx_acc is not None
+    dw = torch.empty_like(w2) if need_w else None
+    db = torch.empty((Cout,), device=x.device, dtype=torch.float32) if need_b else None
+    ws = torch.empty((L.pp_conv1x1_bwd_workspace(B, Cin, Cout, P),), device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        if need_x and (need_w or need_b) and not _serial:
+            # dgrad and wgrad (+ bias grad) are independent, latency-bound launches: issue the parameter
+            # gradients on a side stream (all buffers were allocated on the current one, which joins below)
+            cur = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, _ptr(dw), None, _ptr(ws),
+                                             _stream()), "pp_conv1x1_bwd")
+            if need_b:  # the bias gradient is a third independent launch
+                side2 = _side_stream(x.device, 1)
+                side2.wait_stream(cur)
+                with torch.cuda.stream(side2):
+                    _cabi.check(L.pp_conv1x1_bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, None, None, _ptr(db), _ptr(ws),
+                                                 _stream()), "pp_conv1x1_bwd")
+            _cabi.check(bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), None, None, _ptr(ws), _stream()),
+                        "pp_conv1x1_bwd")
+            cur.wait_stream(side)
+            if need_b:
+                cur.wait_stream(side2)
+        else:
+            _cabi.check(bwd(_ptr(x), _ptr(w2), _ptr(dy), B, Cin, Cout, P, _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), _stream()),
+                        "pp_conv1x1_bwd")
+    return dx, dw, db
 
 
 def conv1x1(x, weight, bias=None):
     """1x1 convolution (the PPM value transform, contrast/models/PixPro.py:21-23) on the tcgen05
     tensor cores with 3xTF32 (fp32-accurate).  x [B,Cin,H,W], weight [Cout,Cin,1,1] or [Cout,Cin]."""
     return _Conv1x1.apply(x, weight, bias)
+
+
+class _FeatProp(torch.autograd.Function):
+    """PixPro.featprop with its value transform (contrast/models/PixPro.py:339-363 [+ F.normalize, :380]) as ONE autograd
+    node: forward = pp_conv1x1_fwd -> pp_ppm_fwd; backward = pp_ppm_bwd -> pp_conv1x1_bwd_acc, whose data gradient is added
+    to the similarity-branch gradient in the contraction's epilogue.  Same kernels and bits as ppm(feat, conv1x1(feat, w, b)),
+    minus the element-wise add autograd inserts where the two gradients of `feat` meet, and one node of graph bookkeeping."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, feat, w, bias, gamma, clamp_value, final_norm):
+        feat = _f32(feat, "feat")
+        w2 = _f32(w, "weight").reshape(w.shape[0], w.shape[1])
+        b = _f32(bias, "bias") if bias is not None else None
+        B, C, H, W = feat.shape
+        P = H * W
+        Cout = w2.shape[0]
+        assert w2.shape[1] == C and Cout == C, "the value transform keeps the channel count (PixPro.py:300)"
+        L = _cabi.lib()
+        val = torch.empty_like(feat)
+        out = torch.empty_like(feat)
+        nws = L.pp_conv1x1_fwd_workspace(B, C, Cout, P)
+        ws = torch.empty((nws,), device=feat.device, dtype=torch.uint8) if nws else None
+        saved = torch.empty((L.pp_ppm_saved_bytes(B, C, P),), device=feat.device, dtype=torch.uint8)
+        with torch.cuda.device(feat.device):
+            _cabi.check(L.pp_conv1x1_fwd(_ptr(feat), _ptr(w2), _ptr(b), B, C, Cout, P, _ptr(val), _ptr(ws), _stream()), "pp_conv1x1_fwd")
+            _cabi.check(L.pp_ppm_fwd(_ptr(feat), _ptr(val), B, C, P, float(gamma), float(clamp_value), int(final_norm),
+                                     _ptr(out), _ptr(saved), _stream()), "pp_ppm_fwd")
+        ctx.save_for_backward(feat, w2, val, out, saved)
+        ctx.cfg = (float(gamma), float(clamp_value), int(final_norm))
+        ctx.has_bias = bias is not None
+        ctx.w_shape = tuple(w.shape)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        feat, w2, val, out, saved = ctx.saved_tensors
+        gamma, cv, final_norm = ctx.cfg
+        g = _f32(g, "grad_out")
+        B, C, H, W = feat.shape
+        P = H * W
+        L = _cabi.lib()
+        d_feat = torch.empty_like(feat)
+        d_val = torch.empty_like(val)
+        ws = torch.empty((L.pp_ppm_bwd_workspace(B, C, P),), device=feat.device, dtype=torch.uint8)
+        with torch.cuda.device(feat.device):
+            _cabi.check(L.pp_ppm_bwd(_ptr(feat), _ptr(val), _ptr(out), _ptr(g), _ptr(saved), B, C, P, gamma, cv, final_norm,
+                                     _ptr(d_feat), _ptr(d_val), _ptr(ws), _stream()), "pp_ppm_bwd")
+        need_w, need_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        _, dw, db = _conv1x1_backward(feat, w2, d_val, True, need_w, need_b, dx_acc=d_feat)
+        return d_feat, (dw.view(ctx.w_shape) if dw is not None else None), db, None, None, None
+
+
+def featprop(feat, weight, bias=None, gamma=2.0, clamp_value=0.0, final_norm=True):
+    """ppm(feat, conv1x1(feat, weight, bias), ...) as one autograd node (PixPro.featprop with the single-conv value
+    transform, `pixpro_transform_layer=1`); see _FeatProp."""
+    return _FeatProp.apply(feat, weight, bias, gamma, clamp_value, final_norm)
 
 
 # ---------------------------------------------------------------------------- tensor cores --

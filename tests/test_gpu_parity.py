@@ -155,13 +155,15 @@ def test_regression_loss_golden(ops, tag):
 
 
 @pytest.mark.parametrize("tag", ["l1_p2_g7", "l0_p1_g7", "l1_p2_g14", "l0_p05_cv01", "l0_p3_g7"])
-@pytest.mark.parametrize("conv_impl", ["product", "cudnn"])
+@pytest.mark.parametrize("conv_impl", ["product", "fused", "cudnn"])
 def test_featprop_golden(ops, tag, conv_impl):
     """PixPro.featprop + F.normalize against the reference module's own output and gradients.  `product`: the value
-    transform runs on this repo's conv (ops.conv1x1 — the tcgen05 3xTF32 kernel, or the PPM-fused path), i.e. the
-    reference-generated d_weight / d_bias goldens meet the product's conv; `cudnn`: torch.nn.Conv2d feeds the PPM."""
+    transform runs on this repo's conv (ops.conv1x1 — the tcgen05 3xTF32 kernel), i.e. the reference-generated
+    d_weight / d_bias goldens meet the product's conv; `fused`: ops.featprop, conv + PPM as one autograd node with the
+    two gradients of `feat` joined in the conv's epilogue (what the drop-in PixPro runs); `cudnn`: torch.nn.Conv2d feeds
+    the PPM."""
     g = load_golden("featprop_" + tag)
-    if conv_impl == "cudnn" and "weight" not in g:
+    if conv_impl != "product" and "weight" not in g:
         pytest.skip("identity value transform: nothing to switch")
     feat = cu(g["feat"]).requires_grad_(True)
     w = b = None
@@ -170,13 +172,16 @@ def test_featprop_golden(ops, tag, conv_impl):
     prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False  # true fp32 for the 1e-5 comparison
     try:
-        if w is None:
-            val = feat
-        elif conv_impl == "product":
-            val = ops.conv1x1(feat, w, b)
+        if conv_impl == "fused":
+            out = ops.featprop(feat, w, b, float(g["gamma"]), float(g["clamp"]), final_norm=True)
         else:
-            val = torch.nn.functional.conv2d(feat, w, b)
-        out = ops.ppm(feat, val, float(g["gamma"]), float(g["clamp"]), final_norm=True)
+            if w is None:
+                val = feat
+            elif conv_impl == "product":
+                val = ops.conv1x1(feat, w, b)
+            else:
+                val = torch.nn.functional.conv2d(feat, w, b)
+            out = ops.ppm(feat, val, float(g["gamma"]), float(g["clamp"]), final_norm=True)
         out.backward(cu(g["gout"]))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
@@ -185,6 +190,50 @@ def test_featprop_golden(ops, tag, conv_impl):
     if w is not None:
         assert rel_err(npy(w.grad), g["d_weight"]) < 2e-5
         assert rel_err(npy(b.grad), g["d_bias"]) < 2e-5
+
+
+@pytest.mark.parametrize("B,G", [(6, 7), (3, 14), (2, 28)])
+def test_featprop_fused_node_equals_two_nodes(ops, synth, B, G):
+    """ops.featprop (one autograd node, pp_conv1x1_bwd_acc) against ops.ppm(feat, ops.conv1x1(feat, w, b)): same kernels,
+    the only difference is where the two gradients of `feat` are added — outputs and gradients must be the same bits."""
+    g = torch.Generator(device="cpu").manual_seed(G)
+    C = 256
+    feat = torch.randn(B, C, G, G, generator=g).to(DEV)
+    w = (torch.randn(C, C, 1, 1, generator=g) / 16).to(DEV)
+    b = (torch.randn(C, generator=g) / 8).to(DEV)
+    gout = torch.randn(B, C, G, G, generator=g).to(DEV)
+    outs = []
+    for fused in (False, True):
+        f_, w_, b_ = (t.clone().requires_grad_(True) for t in (feat, w, b))
+        out = ops.featprop(f_, w_, b_, 2.0, 0.0, True) if fused else ops.ppm(f_, ops.conv1x1(f_, w_, b_), 2.0, 0.0, final_norm=True)
+        out.backward(gout)
+        outs.append((out.detach(), f_.grad, w_.grad, b_.grad))
+    for name, a, c in zip(("out", "d_feat", "d_weight", "d_bias"), outs[0], outs[1]):
+        assert torch.equal(a, c), name
+
+
+def test_regression_loss_pair_joint_equals_pair(ops, synth):
+    """regression_loss_pair(q12, ..., q2=None) (one prediction tensor in, loss_1 + loss_2 out, one gradient tensor) against
+    the two-tensor form + `l[0] + l[1]`: same launch, so the sum, the counts and the gradients are the same bits."""
+    B, C, G = 5, 256, 7
+    g = torch.Generator(device="cpu").manual_seed(11)
+    q12 = torch.nn.functional.normalize(torch.randn(2 * B, C, G, G, generator=g), dim=1).to(DEV)
+    k1 = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=g), dim=1).to(DEV)
+    k2 = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=g), dim=1).to(DEV)
+    c1, c2 = synth.crop_coords(B, seed=3).to(DEV), synth.crop_coords(B, seed=4).to(DEV)
+    f, bw = synth.flow_fields(B, 1, seed=5)
+    ff, fb, mf, mb = ops.flow_stage(f.to(DEV), bw.to(DEV))
+    qa = q12.clone().requires_grad_(True)
+    l12, pn, pm = ops.regression_loss_pair(qa[:B], k2, c1, c2, qa[B:], k1, c2, c1, 0.7, flow1=ff, flow2=fb, size=(720, 1280),
+                                           mask1=mf, mask2=mb)
+    (l12[0] + l12[1]).backward()
+    qb = q12.clone().requires_grad_(True)
+    ls, l2, pn2, pm2 = ops.regression_loss_pair(qb, k2, c1, c2, None, k1, c2, c1, 0.7, flow1=ff, flow2=fb, size=(720, 1280),
+                                                mask1=mf, mask2=mb)
+    ls.backward()
+    assert torch.equal(l2, l12.detach()) and torch.equal(pn2, pn) and torch.equal(pm2, pm)
+    assert torch.equal(ls.detach(), (l12[0] + l12[1]).detach())
+    assert torch.equal(qb.grad, qa.grad)
 
 
 # --------------------------------------------------------------------------- vs the oracle, seeded
