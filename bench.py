@@ -99,6 +99,11 @@ def kernel_work(kernel, B, n, G):
     conv = 2 * C * C * P
     per_sample = {                            # name -> (bytes, flops), both views / directions of ONE sample
         "chain_up": (lo + comp, 0),           # F1: read low-res links, write composites
+        "chain_up1": ((lo + comp) // 2, 0),   # F1 of ONE direction (n = 1 fused route: the other composite is written by fb_up)
+        # n = 1 fused route, one launch per direction, each reads its low-res link and the opposite composite and writes
+        # its mask; the backward one (fb_up_w) also writes its own composite
+        "fb_up_w": (lo // 2 + comp + masks // 2, 0),
+        "fb_up": (lo // 2 + comp // 2 + masks // 2, 0),
         "chain_dense": ((n + 1) * comp, 0),   # F1': read n dense links, write the composites
         "fb": (comp + masks, 0),              # F2: read composites, write masks
         "sparse_corr": (lo + 2 * 3 * P * 4, 0),     # at most the links once; writes [3,P] per direction

@@ -268,6 +268,221 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// fbbox_up_kernel — the FB mask of ONE direction with that direction's own composite COMPUTED in the kernel instead of
+// loaded (n == 1 with flow_up, the published n_frames = 2 setting: the composite is the x8-up-sampled low-res link,
+// contrast/flow/utils/utils.py:87-89).  pp_flow_stage then runs
+//     upchain1 (forward composite only)  ->  fbbox_up<WRITE> (backward: computes + writes its composite, gathers the forward
+//     one, writes mask_bwd)  ->  the forward mask (fbbox_up without WRITE, or fbbox_kernel on one direction)
+// instead of upchain1 (both composites) -> fbbox (both masks): the HBM-write-bound up-sampling of one direction (77 us at
+// B = 64) moves into a kernel that is bound by instruction issue and has DRAM bandwidth to spare.
+// Own flow, bit-identical to upchain1_kernel / ATen's upsample_bilinear2d (see pp_chainup.cuh, steps C and D): the tile's
+// 64 columns x <= 8 low-res rows are interpolated HORIZONTALLY once per CTA into shared memory, pre-scaled by 8 (exact),
+//     T8(r, X) = fma(l0x, 8 L[r][i0x], l1x * 8 L[r][i1x])     (both channels as one packed pair),
+// and every pixel takes U(Y, X) = fma(l0y, T8(i0y, X), l1y * T8(i1y, X)) with its row's taps from a 48-entry table.
+// The table fill overlaps the flight of the TMA box.  Everything after the own flow is fbbox_kernel's code.
+// Shared memory: box 96 x 64 x 2 fp32 (8 rows fewer than fbbox_kernel's: measured free, profiles/r02_ab_fb_boxrows.txt:
+// 358.8 vs 361.3 us, 0.66 % of the pixels on the in-line global path) | T8 [8][TW] pairs | row taps [TH].
+// (Keeping a thread's table rows in registers across its rows — they are 8 apart, so the south row of one is the north row
+// of the next: 7 instead of 12 table loads per column — was built and measured: no change, 207 vs 203 us; removed.)
+struct UpArgs {
+    const float* lo;     // own direction's low-res link of sample b at lo + b * lo_stride, [2,h,w]
+    int64_t lo_stride;
+    float* own_out;      // WRITE: [B,2,H,W], receives the own composite
+    const float* other;  // the opposite composite [B,2,H,W], complete in memory: the gather source
+    uint8_t* mask;       // [B,H,W]
+    int H, W, h, w, B, pf_samples;
+    float rh, rw, half_w, half_h, a1, a2;
+    Div<DM_FAST> dw2, dh2;  // / ((W-1)/2), / ((H-1)/2)
+};
+struct RowTap {  // 16 bytes
+    int i0, i1;  // T8 rows
+    float l0, l1;
+};
+constexpr int UP_TROWS = 8;  // low-res rows under a 48-row tile: at most 48 * (h-1)/(8h-1) + 2 < 8
+
+template <int TW, int TH, int BW, int BH, int MINB, int WC, int HC, bool WRITE>
+__global__ void __launch_bounds__(256, MINB) fbbox_up_kernel(const __grid_constant__ CUtensorMap tm_other,
+                                                             const __grid_constant__ CUtensorMap tp_other, UpArgs a) {
+    constexpr int DM = DM_FAST;
+    constexpr int NX = TW / 32, NR = TH / 8;
+    static_assert(TW % 32 == 0 && TH % 16 == 0 && 256 % TW == 0 && (256 / TW) * 2 == UP_TROWS && TH <= 256 && TH / 8 + 2 <= UP_TROWS, "tile shape");
+    constexpr uint32_t BOX_BYTES = 2 * BW * BH * 4;
+    extern __shared__ __align__(1024) uint8_t fbt_smem[];
+    F2* T8 = reinterpret_cast<F2*>(fbt_smem + BOX_BYTES);                           // [UP_TROWS][TW]
+    RowTap* rowtap = reinterpret_cast<RowTap*>(fbt_smem + BOX_BYTES + UP_TROWS * TW * 8);  // [TH]
+    __shared__ uint64_t full;
+    __shared__ int2 origin;
+    __shared__ int nglobal_cta;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = WC ? WC : a.W, H = HC ? HC : a.H, HW = H * W;
+    if (WC) {  // fold every derived constant
+        a.half_w = (float)(WC - 1) / 2.0f; a.half_h = (float)(HC - 1) / 2.0f;
+        a.dw2 = const_div<DM>((float)(WC - 1) / 2.0f);
+        a.dh2 = const_div<DM>((float)(HC - 1) / 2.0f);
+    }
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int b = blockIdx.z;
+    const float* lo = a.lo + b * a.lo_stride;
+    if (threadIdx.x == 0) {
+        nglobal_cta = 0;
+        tc::mbar_init(&full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 32 && b + a.pf_samples < a.B)  // the same tile of the gather source of a LATER sample -> L2
+        tma_prefetch_3d(&tp_other, tx0, ty0, (b + a.pf_samples) * 2);
+    if (warp == 0) {  // place the box (own flow at the lattice points straight from the low-res link) and start the copy
+        const int X = tx0 + ((lane & 7) * (TW - 1)) / 7, Y = ty0 + ((lane >> 3) * (TH - 1)) / 3;
+        const UpLink L{lo, a.h, a.w, a.rh, a.rw};
+        const float2 v = L.value(Y, X);
+        const float fnx = norm_flow_h(v.x, a.dw2), fny = norm_flow_h(v.y, a.dh2);
+        const float c1x = add(norm_coord_h((float)X, a.dw2), fnx), c1y = add(norm_coord_h((float)Y, a.dh2), fny);
+        const bool inb = (fabsf(c1x) < 1.0f) && (fabsf(c1y) < 1.0f);
+        const int x0 = __float2int_rd(mul(add(c1x, 1.0f), a.half_w)), y0 = __float2int_rd(mul(add(c1y, 1.0f), a.half_h));
+        const int mnx = __reduce_min_sync(0xffffffffu, inb ? x0 : INT_MAX);
+        const int mxx = __reduce_max_sync(0xffffffffu, inb ? x0 : INT_MIN);
+        const int mny = __reduce_min_sync(0xffffffffu, inb ? y0 : INT_MAX);
+        const int mxy = __reduce_max_sync(0xffffffffu, inb ? y0 : INT_MIN);
+        if (lane == 0) {
+            int ox, oy;
+            if (mnx == INT_MAX) {
+                ox = tx0 - (BW - TW) / 2;
+                oy = ty0 - (BH - TH) / 2;
+            } else {
+                ox = mnx - (BW - (mxx + 2 - mnx)) / 2;
+                oy = mny - (BH - (mxy + 2 - mny)) / 2;
+            }
+            ox &= ~3;  // TMA: 16-byte aligned box start
+            origin = make_int2(ox, oy);
+            mbar_arrive_expect_tx(&full, BOX_BYTES);
+            tma_load_3d(fbt_smem, &tm_other, ox, oy, b * 2, &full);
+        }
+        __syncwarp();
+    }
+    // ---- own-flow tables (while the box is in flight) ---------------------------------------------------------------
+    {
+        const int r_lo = axis_tap(ty0, a.rh, a.h).i0;
+        const int c = threadIdx.x & (TW - 1), rg = threadIdx.x / TW;
+        const AxisTap tx = axis_tap(min(tx0 + c, W - 1), a.rw, a.w);
+        const int hw = a.h * a.w;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int r = 2 * rg + u;
+            const float* p = lo + min(r_lo + r, a.h - 1) * a.w;
+            const float ax = mul(8.0f, __ldg(p + tx.i0)), bx = mul(8.0f, __ldg(p + tx.i1));
+            const float ay = mul(8.0f, __ldg(p + hw + tx.i0)), by = mul(8.0f, __ldg(p + hw + tx.i1));
+            T8[r * TW + c] = pk(fma_(tx.l0, ax, mul(tx.l1, bx)), fma_(tx.l0, ay, mul(tx.l1, by)));
+        }
+        if (threadIdx.x < TH) {
+            const AxisTap ty = axis_tap(min(ty0 + (int)threadIdx.x, H - 1), a.rh, a.h);
+            RowTap t;
+            t.i0 = ty.i0 - r_lo; t.i1 = ty.i1 - r_lo; t.l0 = ty.l0; t.l1 = ty.l1;
+            rowtap[threadIdx.x] = t;
+        }
+    }
+    __syncthreads();
+    const Div2 dW = make_div2(a.dw2), dH = make_div2(a.dh2);
+    const F2 one2 = pk1(1.0f), hw2 = pk1(a.half_w), hh2 = pk1(a.half_h), a1_2 = pk1(a.a1), a2_2 = pk1(a.a2);
+    const int X0 = tx0 + lane, Y0 = ty0 + warp;
+    uint8_t* mp = a.mask + (int64_t)b * HW + Y0 * W + X0;
+    float* op = WRITE ? a.own_out + (int64_t)b * 2 * HW + Y0 * W + X0 : nullptr;
+    const int rstep = 8 * W;
+    F2 xn2[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) xn2[c] = pk1(norm_coord_h((float)(X0 + 32 * c), a.dw2));
+    const uint32_t t8_s = tc::smem_u32(T8) + lane * 8, rowtap_s = tc::smem_u32(rowtap) + warp * 16;
+    mbar_wait_bounded(&full, 0);
+    const int2 o = origin;
+    const float* sp = reinterpret_cast<const float*>(fbt_smem);
+    int nglobal = 0;
+    const float* g = a.other + (int64_t)b * 2 * HW;
+#pragma unroll(NR / 2)
+    for (int kp = 0; kp < NR; kp += 2) {
+        RowTap rt[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(rt[p].i0), "=r"(rt[p].i1), "=f"(rt[p].l0), "=f"(rt[p].l1)
+                         : "r"(rowtap_s + (kp + p) * 8 * 16));
+        const F2 yn = sub2(dH(pk((float)(Y0 + 8 * kp), (float)(Y0 + 8 * kp + 8))), one2);
+#pragma unroll
+        for (int c = 0; c < NX; c++) {
+            float fxs[2], fys[2];
+#pragma unroll
+            for (int p = 0; p < 2; p++) {  // U(Y, X) = fma(l0y, T8(i0y, X), l1y * T8(i1y, X)), both channels
+                F2 t0, t1;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t0.v) : "r"(t8_s + (rt[p].i0 * TW + 32 * c) * 8));
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(t1.v) : "r"(t8_s + (rt[p].i1 * TW + 32 * c) * 8));
+                unpk(fma2(pk1(rt[p].l0), t0, mul2(pk1(rt[p].l1), t1)), fxs[p], fys[p]);
+                if (WRITE) {
+                    float* q = ptr_at(op, (kp + p) * rstep + 32 * c);
+                    q[0] = fxs[p];
+                    *ptr_at(q, HW) = fys[p];
+                }
+            }
+            const F2 fnx = dW(pk(fxs[0], fxs[1])), fny = dH(pk(fys[0], fys[1]));
+            const F2 c1x = add2(xn2[c], fnx), c1y = add2(yn, fny);
+            const F2 ix = mul2_nc(add2(c1x, one2), hw2), iy = mul2_nc(add2(c1y, one2), hh2);
+            float c1xs[2], c1ys[2], ixs[2], iys[2];
+            unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
+            unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
+            bool inb[2], outside[2];
+            int gofs[2];
+            float t[2][8], xws[2], yws[2];
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);
+                const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
+                xws[p] = __int2float_rn(x0);
+                yws[p] = __int2float_rn(y0);
+                const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
+                outside[p] = inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
+                gofs[p] = (y0 << 16) | (x0 & 0xffff);
+                const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
+                t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
+                t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
+            }
+            if (outside[0] || outside[1]) {
+#pragma unroll
+                for (int p = 0; p < 2; p++)
+                    if (outside[p]) {
+                        const int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
+                        const float* q = ptr_at(g, y0 * W + x0);
+                        const bool xin = x0 < W - 1, yin = y0 < H - 1;
+                        t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
+                        t[p][1] = xin ? __ldg(q + 1) : 0.0f; t[p][5] = xin ? __ldg(ptr_at(q, HW) + 1) : 0.0f;
+                        t[p][2] = yin ? __ldg(ptr_at(q, W)) : 0.0f; t[p][6] = yin ? __ldg(ptr_at(q, HW + W)) : 0.0f;
+                        t[p][3] = (xin && yin) ? __ldg(ptr_at(q, W) + 1) : 0.0f; t[p][7] = (xin && yin) ? __ldg(ptr_at(q, HW + W) + 1) : 0.0f;
+                        nglobal++;
+                    }
+            }
+            const F2 wx = sub2(ix, pk(xws[0], xws[1])), wy = sub2(iy, pk(yws[0], yws[1]));
+            const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
+            const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
+            const F2 bx = combine4_2(dW(pk(t[0][0], t[1][0])), dW(pk(t[0][1], t[1][1])), dW(pk(t[0][2], t[1][2])),
+                                     dW(pk(t[0][3], t[1][3])), nw, ne, sw, se);
+            const F2 by = combine4_2(dH(pk(t[0][4], t[1][4])), dH(pk(t[0][5], t[1][5])), dH(pk(t[0][6], t[1][6])),
+                                     dH(pk(t[0][7], t[1][7])), nw, ne, sw, se);
+            const F2 cyx = add2(fnx, bx), cyy = add2(fny, by);
+            const F2 cyc2 = add2(mul2_nc(cyx, cyx), mul2_nc(cyy, cyy));
+            const F2 f2 = add2(mul2_nc(fnx, fnx), mul2_nc(fny, fny)), b2 = add2(mul2_nc(bx, bx), mul2_nc(by, by));
+            const F2 eps = add2(mul2_nc(a1_2, add2(f2, b2)), a2_2);
+            float ds[2];
+            unpk(sub2(cyc2, eps), ds[0], ds[1]);
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const uint8_t bit = (inb[p] && (ds[p] <= 0.0f)) ? 1 : 0;
+                *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = bit;
+            }
+        }
+    }
+    const int wsum = __reduce_add_sync(0xffffffffu, nglobal);
+    if (lane == 0 && wsum) atomicAdd(&nglobal_cta, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0 && nglobal_cta) atomicAdd(&g_redo_pixels, (unsigned long long)nglobal_cta);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Dense-link chain (contrast/util.py:301-330, num > 1) with each link's gather footprint staged by
 // TMA.  Same idea as fbbox_kernel, but the gather position of step i depends on steps < i, so per
 // step: every thread evaluates the tap origin of its 12 pixels, the CTA reduces the exact bounding
@@ -502,6 +717,11 @@ static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
     return check_launch("fbbox_kernel");
 }
 
+static bool variant_enabled() {  // PIXPRO_B200_FBTILE=0: gather kernels only
+    static const int v = [] { const char* e = getenv("PIXPRO_B200_FBTILE"); return e ? atoi(e) : 1; }();
+    return v != 0;
+}
+
 // returns -1 when the TMA path is not applicable (caller falls back to the gather kernels)
 static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, int ndir, int64_t B, int H, int W, float a1, float a2,
                   cudaStream_t st) {
@@ -523,10 +743,58 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
     // banks measured best (360 us); pitches 88 / 92 / 100 / 104 / 108 (with the box height adjusted to the same shared memory)
     // trade same-row conflicts for cross-row ones and cost 376-412 us (profiles/r02_t_fb_pitch.txt).
     if (W == 1280 && H == 720 && variant == 2) return launch_cfg<64, 48, 96, 72, 3, 1280, 720>(a, B, st);  // experiment: 3 CTAs / SM
+    if (W == 1280 && H == 720 && variant == 3) return launch_cfg<64, 48, 96, 64, 4, 1280, 720>(a, B, st);  // experiment: 64-row box
+    if (W == 1280 && H == 720 && variant == 4) return launch_cfg<64, 48, 96, 60, 4, 1280, 720>(a, B, st);  // experiment: 60-row box
     if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
     if (H % 48 == 0) return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
     if (H % 32 == 0) return launch_cfg<64, 32, 96, 56, 4>(a, B, st);
     return -1;
+}
+
+template <int TW, int TH, int BW, int BH, int MINB, int WC, int HC, bool WRITE>
+static int launch_up_cfg(const UpArgs& a, cudaStream_t st) {
+    auto kern = fbbox_up_kernel<TW, TH, BW, BH, MINB, WC, HC, WRITE>;
+    constexpr int smem = 2 * BW * BH * 4 + UP_TROWS * TW * 8 + TH * 16;
+    static unsigned long long opted = 0;  // one bit per device
+    if (smem_opt_in(kern, smem, opted) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    CUtensorMap tm, tp;
+    if (!make_map(&tm, a.other, (int64_t)a.B * 2, a.H, a.W, BW, BH) || !make_map(&tp, a.other, (int64_t)a.B * 2, a.H, a.W, TW, TH)) return -1;
+    dim3 grid(a.W / TW, a.H / TH, (unsigned)a.B);
+    PP_LAUNCH(WRITE ? "fb_up_w" : "fb_up", st, (kern<<<grid, 256, smem, st>>>(tm, tp, a)));
+    return check_launch("fbbox_up_kernel");
+}
+
+// PIXPRO_B200_FBUP: n == 1 flow stages with masks — 0 = upchain1 (both composites) + fbbox (both masks); 1 = upchain1
+// (forward) + fbbox_up<WRITE> (backward) + fbbox_up (forward); 2 = the same with the forward mask on fbbox_kernel
+static int up_mode() {
+    static const int m = [] { const char* e = getenv("PIXPRO_B200_FBUP"); return e ? atoi(e) : 1; }();
+    return m;
+}
+static bool up_enabled() { return up_mode() != 0; }
+// shapes the fused kernel handles: whole 64 x 48 tiles, x8 up-sampling (the table sizes assume it), TMA-addressable planes
+static bool up_applicable(const float* c0, const float* c1, int64_t B, int H, int W, int h, int w, float a1) {
+    return up_enabled() && variant_enabled() && H == 8 * h && W == 8 * w && h >= 2 && w >= 2 && W % 64 == 0 && H % 48 == 0 && H < 32768 &&
+           W < 32768 && B <= 65535 && a1 >= 0.0f && ((((uintptr_t)c0 | (uintptr_t)c1) & 15) == 0) && encode_tiled_fn() != nullptr;
+}
+// FB mask of one direction, own composite computed from the low-res link (and written to own_out when it is not null).
+// -1 = not applicable (only possible when up_applicable() was not checked, or a tensor map could not be encoded).
+static int launch_up(const float* lo, int64_t lo_stride, float* own_out, const float* other, uint8_t* mask, int64_t B, int H, int W,
+                     int h, int w, float a1, float a2, cudaStream_t st) {
+    UpArgs a;
+    a.lo = lo; a.lo_stride = lo_stride; a.own_out = own_out; a.other = other; a.mask = mask;
+    a.H = H; a.W = W; a.h = h; a.w = w; a.B = (int)B;
+    static const int pf = [] { const char* e = getenv("PIXPRO_B200_FBPF"); return e ? atoi(e) : 1; }();
+    a.pf_samples = pf > 0 ? pf : (int)B;
+    a.rh = up_scale(h, H); a.rw = up_scale(w, W);
+    a.half_w = (float)(W - 1) / 2.0f; a.half_h = (float)(H - 1) / 2.0f;
+    a.a1 = a1; a.a2 = a2;
+    a.dw2 = make_div<DM_FAST>((float)(W - 1) / 2.0f); a.dh2 = make_div<DM_FAST>((float)(H - 1) / 2.0f);
+    if (W == 1280 && H == 720)
+        return own_out ? launch_up_cfg<64, 48, 96, 64, 4, 1280, 720, true>(a, st) : launch_up_cfg<64, 48, 96, 64, 4, 1280, 720, false>(a, st);
+    return own_out ? launch_up_cfg<64, 48, 96, 64, 4, 0, 0, true>(a, st) : launch_up_cfg<64, 48, 96, 64, 4, 0, 0, false>(a, st);
 }
 
 template <int TW, int TH, int BW, int BH, int MINB>

@@ -657,7 +657,7 @@ static int launch_chain_dm(const float* l0, const float* l1, float* o0, float* o
     dim3 block(32, 8);
     if (up && n == 1 && !is_norm) {  // W = 8w is a multiple of 4; H = 8h a multiple of 8
         dim3 grid((W / 4 + 31) / 32, (H / 8 + 7) / 8, (unsigned)(B * ndir));
-        PP_LAUNCH("chain_up", st, upchain1_kernel<DM><<<grid, block, 0, st>>>(a));
+        PP_LAUNCH(ndir == 1 ? "chain_up1" : "chain_up", st, upchain1_kernel<DM><<<grid, block, 0, st>>>(a));  // chain_up1: one direction
         return check_launch("upchain1_kernel");
     }
     if constexpr (DM == DM_FAST) {
@@ -989,6 +989,25 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
     int64_t link = 2 * (int64_t)h * w;  // loader layout [B,n,2,h,w]
     int rc;
     (void)workspace; (void)workspace_bytes;
+    // n == 1 with up-sampling and masks (the published n_frames = 2 setting): the backward composite is produced inside its
+    // mask kernel and the forward mask kernel recomputes its own composite (fbt::fbbox_up_kernel, pp_fbtile.cuh) — same bits,
+    // one HBM-write-bound half of the up-sampling launch gone.  Conditions = those of the TMA-staged FB kernel (launch_fb).
+    if (n == 1 && flow_up && use_mask && !is_norm && div_mode != PP_DIV_RCP && div_certified((float)(W - 1)) &&
+        div_certified((float)(H - 1)) && div_certified((float)(W - 1) / 2.0f) && div_certified((float)(H - 1) / 2.0f) &&
+        fb_alpha2_eff(alpha_2, H, W) >= 1e-12f && fbt::up_applicable(flow_fwd, flow_bwd, B, H, W, h, w, (float)alpha_1)) {
+        rc = launch_chain(lo_fwd, nullptr, flow_fwd, nullptr, 1, 1, B, H, W, h, w, true, link, link, 0, div_mode, st);
+        if (rc) return rc;
+        const float a2e = fb_alpha2_eff(alpha_2, H, W);
+        rc = fbt::launch_up(lo_bwd, link, flow_bwd, flow_fwd, mask_bwd, B, H, W, h, w, (float)alpha_1, a2e, st);
+        if (rc == 0 && fbt::up_mode() == 2)  // experiment: the forward mask on the plain kernel (its own composite loaded)
+            return launch_fb(flow_fwd, flow_bwd, mask_fwd, nullptr, nullptr, nullptr, 1, B, H, W, alpha_1, alpha_2, 0, div_mode, st);
+        if (rc == 0) rc = fbt::launch_up(lo_fwd, link, nullptr, flow_bwd, mask_fwd, B, H, W, h, w, (float)alpha_1, a2e, st);
+        if (rc >= 0) return rc;
+        // a tensor map could not be encoded: the forward composite exists, finish on the two-kernel route below
+        rc = launch_chain(lo_bwd, nullptr, flow_bwd, nullptr, 1, 1, B, H, W, h, w, true, link, link, 0, div_mode, st);
+        if (rc) return rc;
+        return launch_fb(flow_fwd, flow_bwd, mask_fwd, mask_bwd, nullptr, nullptr, 2, B, H, W, alpha_1, alpha_2, 0, div_mode, st);
+    }
     rc = launch_chain(lo_fwd, lo_bwd, flow_fwd, flow_bwd, 2, n, B, H, W, h, w, flow_up != 0, link, (int64_t)n * link, is_norm,
                       div_mode, st);
     if (rc) return rc;
