@@ -106,6 +106,7 @@ def kernel_work(kernel, B, n, G):
         "fb_up": (lo // 2 + comp // 2 + masks // 2, 0),
         "chain_dense": ((n + 1) * comp, 0),   # F1': read n dense links, write the composites
         "fb": (comp + masks, 0),              # F2: read composites, write masks
+        "fb1": (comp + masks // 2, 0),        # F2 of one direction: its own composite + the gather source, one mask
         "sparse_corr": (lo + 2 * 3 * P * 4, 0),     # at most the links once; writes [3,P] per direction
         "add_flow": (2 * 5 * P * 4, 0),
         "loss_small": (6 * cp, 2 * gemm),     # F3: read q, k, write dq, both directions; one masked contraction each

@@ -713,7 +713,7 @@ static int launch_cfg(const Args& a, int64_t B, cudaStream_t st) {
         return -1;
     }
     dim3 grid(a.W / TW, a.H / TH, (unsigned)(B * a.ndir));
-    PP_LAUNCH("fb", st, (kern<<<grid, 256, smem, st>>>(tm0, tm1, tp0, tp1, a)));
+    PP_LAUNCH(a.ndir == 1 ? "fb1" : "fb", st, (kern<<<grid, 256, smem, st>>>(tm0, tm1, tp0, tp1, a)));  // fb1: one direction
     return check_launch("fbbox_kernel");
 }
 
@@ -768,15 +768,17 @@ static int launch_up_cfg(const UpArgs& a, cudaStream_t st) {
 }
 
 // PIXPRO_B200_FBUP: n == 1 flow stages with masks — 0 = upchain1 (both composites) + fbbox (both masks); 1 = upchain1
-// (forward) + fbbox_up<WRITE> (backward) + fbbox_up (forward); 2 = the same with the forward mask on fbbox_kernel
-static int up_mode() {
-    static const int m = [] { const char* e = getenv("PIXPRO_B200_FBUP"); return e ? atoi(e) : 1; }();
-    return m;
+// (forward) + fbbox_up<WRITE> (backward) + fbbox_up (forward); 2 = the same with the forward mask on fbbox_kernel.
+// Unset: by batch size.  Measured (profiles/r02_ag_flow_routes.txt, one call, graph replay, B200): B = 64: 505.9 / 491.6 /
+// 485.4 us for modes 0 / 1 / 2; B = 32: 264.2 / 258.1 / 260.1 us; B = 16: 141.3 / 143.4 / 147.5 us — three dependent launches
+// need more waves than two to amortise their tails, so small batches (the 16-sample chunks of HostPixelStep) stay on mode 0.
+static int up_mode(int64_t B) {
+    static const int m = [] { const char* e = getenv("PIXPRO_B200_FBUP"); return e ? atoi(e) : -1; }();
+    return m >= 0 ? m : (B >= 32 ? 2 : 0);
 }
-static bool up_enabled() { return up_mode() != 0; }
 // shapes the fused kernel handles: whole 64 x 48 tiles, x8 up-sampling (the table sizes assume it), TMA-addressable planes
 static bool up_applicable(const float* c0, const float* c1, int64_t B, int H, int W, int h, int w, float a1) {
-    return up_enabled() && variant_enabled() && H == 8 * h && W == 8 * w && h >= 2 && w >= 2 && W % 64 == 0 && H % 48 == 0 && H < 32768 &&
+    return up_mode(B) != 0 && variant_enabled() && H == 8 * h && W == 8 * w && h >= 2 && w >= 2 && W % 64 == 0 && H % 48 == 0 && H < 32768 &&
            W < 32768 && B <= 65535 && a1 >= 0.0f && ((((uintptr_t)c0 | (uintptr_t)c1) & 15) == 0) && encode_tiled_fn() != nullptr;
 }
 // FB mask of one direction, own composite computed from the low-res link (and written to own_out when it is not null).

@@ -999,7 +999,7 @@ int pp_flow_stage(const float* lo_fwd, const float* lo_bwd, int64_t B, int n, in
         if (rc) return rc;
         const float a2e = fb_alpha2_eff(alpha_2, H, W);
         rc = fbt::launch_up(lo_bwd, link, flow_bwd, flow_fwd, mask_bwd, B, H, W, h, w, (float)alpha_1, a2e, st);
-        if (rc == 0 && fbt::up_mode() == 2)  // experiment: the forward mask on the plain kernel (its own composite loaded)
+        if (rc == 0 && fbt::up_mode(B) == 2)  // the forward mask on the plain kernel (its own composite loaded)
             return launch_fb(flow_fwd, flow_bwd, mask_fwd, nullptr, nullptr, nullptr, 1, B, H, W, alpha_1, alpha_2, 0, div_mode, st);
         if (rc == 0) rc = fbt::launch_up(lo_fwd, link, nullptr, flow_bwd, mask_fwd, B, H, W, h, w, (float)alpha_1, a2e, st);
         if (rc >= 0) return rc;

@@ -36,6 +36,7 @@ class HostPixelStep:
         self.side = torch.cuda.Stream(device=self.dev)
         self.aux = torch.cuda.Stream(device=self.dev, priority=-1)  # few latency-bound blocks: first free SM slots
         self.ready = torch.cuda.Event()
+        self.ready_feat = torch.cuda.Event()
         self.use_graph = use_graph
         self.graph = None
         self.calls = 0
@@ -86,27 +87,43 @@ class HostPixelStep:
         capturing = torch.cuda.is_current_stream_capturing()  # graph-private memory needs no record_stream
         self.side.wait_stream(main)
         chunks = []
-        feat_keys = ("feat1", "feat2", "k1", "k2", "c1", "c2")
+        feat_keys, rest_keys = ("feat1", "feat2"), ("k1", "k2", "c1", "c2")
+        # Copy queue (one PCIe direction, ~0.5 ms for the 27.6 MB of the bench batch — as long as the flow kernels): link
+        # chunks first (the flow kernels are the critical path and wait for nothing else), then the two feature maps (all the
+        # PPM forward needs: it starts before the keys have arrived), keys and crop descriptors last (the loss needs them).
+        # Measured alternative: features right after the FIRST link chunk — the flow kernels then stall for the later chunks
+        # and the step gets 1.5 % slower (profiles/r02_af_e2e_order.txt).
         with torch.cuda.stream(self.side):
+            t = {}
             if use_flow and self.sparse:
-                # sparse correspondence: the flow work is ~10 us, so the copy queue is ordered for the PPM instead —
-                # features first (the PPM forward runs underneath the link copies), links last
-                t = {k: host[k].to(dev, non_blocking=True) for k in feat_keys}
+                # sparse correspondence: the flow work is ~10 us, so the copy queue is ordered for the PPM alone —
+                # features first, then keys / descriptors, links last
+                t.update({k: host[k].to(dev, non_blocking=True) for k in feat_keys})
+                self.ready_feat.record(self.side)
+                t.update({k: host[k].to(dev, non_blocking=True) for k in rest_keys})
                 self.ready.record(self.side)
                 lf = host["lo_f"].to(dev, non_blocking=True)
                 lb = host["lo_b"].to(dev, non_blocking=True)
                 self.chunk_ready[0].record(self.side)
                 chunks.append((0, lf, lb, self.chunk_ready[0]))
             else:
-                if use_flow:  # first in the copy queue, chunk by chunk: the flow kernels depend on nothing else
+                bounds = []
+                if use_flow:
                     B = host["lo_f"].shape[0]
                     step = (B + self.flow_chunks - 1) // self.flow_chunks
-                    for i, b0 in enumerate(range(0, B, step)):
-                        lf = host["lo_f"][b0:b0 + step].to(dev, non_blocking=True)
-                        lb = host["lo_b"][b0:b0 + step].to(dev, non_blocking=True)
-                        self.chunk_ready[i].record(self.side)
-                        chunks.append((b0, lf, lb, self.chunk_ready[i]))
-                t = {k: host[k].to(dev, non_blocking=True) for k in feat_keys}
+                    bounds = list(enumerate(range(0, B, step)))
+
+                def copy_chunk(i, b0):
+                    lf = host["lo_f"][b0:b0 + step].to(dev, non_blocking=True)
+                    lb = host["lo_b"][b0:b0 + step].to(dev, non_blocking=True)
+                    self.chunk_ready[i].record(self.side)
+                    chunks.append((b0, lf, lb, self.chunk_ready[i]))
+
+                for i, b0 in bounds:
+                    copy_chunk(i, b0)
+                t.update({k: host[k].to(dev, non_blocking=True) for k in feat_keys})
+                self.ready_feat.record(self.side)
+                t.update({k: host[k].to(dev, non_blocking=True) for k in rest_keys})
                 self.ready.record(self.side)
         ff = fb = mf = mb = None
         if use_flow and self.sparse:
@@ -136,10 +153,10 @@ class HostPixelStep:
         # PPM forward on a third stream: it needs only the features, so it runs underneath the tail of
         # the flow kernels instead of after them; the loss (which needs both) joins the two.
         with torch.cuda.stream(self.aux):
-            self.aux.wait_event(self.ready)  # also forks aux from the (possibly capturing) main stream
+            self.aux.wait_event(self.ready_feat)  # also forks aux from the (possibly capturing) main stream
             if not capturing:
-                for v in t.values():
-                    v.record_stream(self.aux)
+                for k in feat_keys:
+                    t[k].record_stream(self.aux)
             f12 = torch.cat([t["feat1"], t["feat2"]], dim=0).requires_grad_(True)
             wg = w.detach().requires_grad_(True)
             bg = bias.detach().requires_grad_(True)

@@ -686,9 +686,9 @@ def conv1x1(x, weight, bias=None):
 
 class _FeatProp(torch.autograd.Function):
     """PixPro.featprop with its value transform (contrast/models/PixPro.py:339-363 [+ F.normalize, :380]) as ONE autograd
-    node: forward = pp_conv1x1_fwd -> pp_ppm_fwd; backward = pp_ppm_bwd -> pp_conv1x1_bwd_acc, whose data gradient is added
-    to the similarity-branch gradient in the contraction's epilogue.  Same kernels and bits as ppm(feat, conv1x1(feat, w, b)),
-    minus the element-wise add autograd inserts where the two gradients of `feat` meet, and one node of graph bookkeeping."""
+    node: forward = pp_conv1x1_fwd -> pp_ppm_fwd; backward = pp_ppm_bwd -> pp_conv1x1_bwd(_acc): at P >= 128 the data gradient
+    is added to the similarity-branch gradient in the contraction's epilogue, at small grids by one in-place add.  Same kernels
+    and bits as ppm(feat, conv1x1(feat, w, b)), one node of graph bookkeeping less."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -732,7 +732,14 @@ class _FeatProp(torch.autograd.Function):
             _cabi.check(L.pp_ppm_bwd(_ptr(feat), _ptr(val), _ptr(out), _ptr(g), _ptr(saved), B, C, P, gamma, cv, final_norm,
                                      _ptr(d_feat), _ptr(d_val), _ptr(ws), _stream()), "pp_ppm_bwd")
         need_w, need_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        _, dw, db = _conv1x1_backward(feat, w2, d_val, True, need_w, need_b, dx_acc=d_feat)
+        if P >= 128 and P % 4 == 0 and C % 4 == 0:
+            # TMA-fed route: the epilogue adds into d_feat with 16-byte read-modify-writes (free next to the contraction)
+            _, dw, db = _conv1x1_backward(feat, w2, d_val, True, need_w, need_b, dx_acc=d_feat)
+        else:
+            # thread-staged route (7x7): its epilogue owns 16 joint indices of one channel per thread, a strided scalar
+            # read-modify-write that costs the launch 16 us (31 -> 47 us measured) — one element-wise add is cheaper
+            dx, dw, db = _conv1x1_backward(feat, w2, d_val, True, need_w, need_b)
+            d_feat.add_(dx)
         return d_feat, (dw.view(ctx.w_shape) if dw is not None else None), db, None, None, None
 
 

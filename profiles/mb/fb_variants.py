@@ -8,6 +8,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "pixpro-with-opticalflow_b200"))
+os.environ.setdefault("PIXPRO_B200_FBUP", "0")  # this script studies fbbox_kernel itself: the two-kernel route
 from pixpro_b200 import _cabi, ops, synth  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -28,6 +29,7 @@ rep = _cabi.profile_report()
 _cabi.profile_enable(False)
 redo = _cabi.fb_redo_count()
 h = hashlib.sha256(out[2].cpu().numpy().tobytes() + out[3].cpu().numpy().tobytes()).hexdigest()[:16]
-l, ms = rep["fb"]
+l, ms = rep["fb"] if "fb" in rep else (sum(rep[k][0] for k in ("fb_up_w", "fb1", "fb_up") if k in rep) // 2,
+                                        sum(rep[k][1] for k in ("fb_up_w", "fb1", "fb_up") if k in rep))  # fused route: both mask launches
 print(f"variant={os.environ.get('PIXPRO_B200_FBTILE', 'default')} fb {ms / l * 1000:.1f} us/launch  mask sha {h}  "
       f"valid {out[2].float().mean().item():.4f}  redo pixels/launch {redo / 10:.0f}")

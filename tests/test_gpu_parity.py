@@ -95,6 +95,19 @@ def test_flow_stage_golden(ops, tag):
         assert rel_err(npy(ops.calc_mask_ratio(mf)), g["mask_ratio_fwd"]) < 1e-6
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_flow_stage_fused_routes(mode):
+    """The three routes of the n = 1 flow stage (PIXPRO_B200_FBUP: 0 = upchain1 + fbbox; 1 / 2 = one direction's composite
+    computed inside its mask kernel, fbbox_up_kernel) against the reference's 720x1280 golden and the oracle on small frames —
+    each in its own process, since the library reads the switch once (unset, the route follows the batch size)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PIXPRO_B200_FBUP=mode)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_fused_route_check.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FUSED ROUTE OK " + mode in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 @pytest.mark.parametrize("tag", ["n1_up", "n5_up", "n2_noup"])
 def test_fb_masks_entry_golden(ops, tag):
     """pp_fb_masks (both FB masks of apply_optical_flow in one launch, util.py:211-213) on the reference's composite flows."""

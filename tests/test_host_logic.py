@@ -317,6 +317,12 @@ def test_algorithmic_bytes_of_the_other_kernels():
     ab = lambda k, B, n, G=7: bench.kernel_work(k, B, n, G)[0]
     assert ab("chain_dense", 64, 5) == 64 * 6 * comp           # F1': n links in, composites out
     assert ab("fb", 64, 1) == 64 * (comp + 2 * 720 * 1280)      # F2
+    # the n = 1 fused route: one direction's up-sampling inside its mask kernel; the three launches move the same bytes plus
+    # one extra read of a composite
+    lo1 = 2 * 2 * 90 * 160 * 4
+    assert ab("chain_up1", 64, 1) == 64 * (lo1 + comp) // 2
+    assert ab("fb_up_w", 64, 1) == 64 * (lo1 // 2 + comp + 720 * 1280)
+    assert ab("fb1", 64, 1) == 64 * (comp + 720 * 1280)
     assert ab("loss_small", 64, 1, 7) == 64 * 6 * cp4           # F3: q, k in; dq out; both directions
     assert ab("ppm_fwd_small", 64, 1, 7) == 64 * 6 * cp4
     assert ab("ppm_bwd_small", 64, 1, 7) == 64 * 12 * cp4
