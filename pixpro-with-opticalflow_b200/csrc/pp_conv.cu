@@ -174,42 +174,11 @@ static inline bool conv_tc2(int Cin, int Cout, int P) {
     return !off && use_tensor_cores(P) && Cin % 4 == 0 && Cout % 4 == 0 && P % 4 == 0;
 }
 // Grids the in-place route cannot stream (P % 4 != 0: a [C, 49] map of the 7x7 grid has 196-byte rows, TMA strides are multiples
-// of 16 bytes; or too small for use_tensor_cores): x and dy are first copied to a pitch of PP = P rounded up to 4 floats (one pass,
-// ~2 x 6.5 MB at B = 128, C = 256, 7x7), then the same three contractions run on the TMA-fed kernel — per sample for y and dx
-// (N = P, one ragged tile that brings only the 32-row groups it needs), and for dW as a sum over samples inside the kernel
-// (kb = kWgradKb samples per output tile, "batch as K", then the deterministic reduce over B / kb partials).
-static inline int pad4(int P) { return (P + 3) & ~3; }
-// MEASURED (profiles/r02_v_conv7.txt, r02_w_convpad_step.txt; B = 128, 256 -> 256, 7x7): dgrad 36.9 -> 29.2 us, wgrad 33.5 -> 25.0 us,
-// fwd unchanged (30 us), plus the pad launches — the whole step gets SLOWER (0.689 -> 0.710 ms dense, 0.218 -> 0.237 ms sparse):
-// these contractions are bound by the latency chain of one tile (16 K chunks through a 4-deep ring, ~0.9 us per chunk), not by how
-// the operands are staged.  The route is therefore opt-in (PIXPRO_B200_CONVPAD=1); the thread-staged kernel stays the default here.
-static inline bool conv_tc2_padded(int Cin, int Cout, int P) {
-    static const int off = [] { const char* e = getenv("PIXPRO_B200_CONVPAD"); return (e && e[0] == '1') ? 0 : 1; }();
-    static const int off2 = [] { const char* e = getenv("PIXPRO_B200_TC2"); return (e && e[0] == '0') ? 1 : 0; }();
-    return !off && !off2 && !conv_tc2(Cin, Cout, P) && Cin % 4 == 0 && Cout % 4 == 0;
-}
-constexpr int kWgradKb = 4;  // samples summed per wgrad tile: B / 4 x 2 tiles of 16 chunks at B = 128, 7x7
-// rows of P floats -> rows of PP floats (zero tail), two tensors in one launch (blockIdx.y); src1 may be null
-__global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ src0, float* __restrict__ dst0, int64_t n0,
-                                                       const float* __restrict__ src1, float* __restrict__ dst1, int64_t n1, int P, int PP) {
-    const float* src = blockIdx.y ? src1 : src0;
-    float* dst = blockIdx.y ? dst1 : dst0;
-    const int64_t n = blockIdx.y ? n1 : n0;  // rows * PP
-    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (e >= n) return;
-    const int64_t row = e / PP;
-    const int col = (int)(e - row * PP);
-    dst[e] = col < P ? __ldg(src + row * P + col) : 0.0f;
-}
-static int launch_pad(const float* s0, float* d0, int64_t rows0, const float* s1, float* d1, int64_t rows1, int P, cudaStream_t st) {
-    const int PP = pad4(P);
-    const int64_t n0 = rows0 * PP, n1 = s1 ? rows1 * PP : 0;
-    const int64_t nmax = n0 > n1 ? n0 : n1;
-    dim3 grid((unsigned)((nmax + 255) / 256), s1 ? 2 : 1);
-    PP_LAUNCH("conv1x1 pad", st, pad_rows_kernel<<<grid, 256, 0, st>>>(s0, d0, n0, s1, d1, n1, P, PP));
-    return check_launch("pad_rows_kernel");
-}
-
+// of 16 bytes) stay on the thread-staged kernel.  A route through the TMA-fed kernel on copies padded to a pitch of 52 floats
+// (per-sample y and dx, dW summed over 4 samples per tile: pp_tc_gemm_ex's pitch / kb features) was built and measured at
+// B = 128, 256 -> 256, 7x7: dgrad 36.9 -> 29.2 us, wgrad 33.5 -> 25.0 us, forward unchanged, but with the pad launches the step got
+// SLOWER (0.689 -> 0.710 ms dense, 0.218 -> 0.237 ms sparse; profiles/r02_v_conv7.txt, r02_w_convpad_step.txt) — these contractions
+// are bound by the latency chain of one tile, not by operand staging — and was removed.
 struct TcStBias {  // out[b][m][n..n+3] = v + bias[m]   (acc != 0: out += v + bias[m])
     static constexpr bool kAux = false;
     float* out;
@@ -249,8 +218,8 @@ using namespace pp;
 extern "C" {
 
 int64_t pp_conv1x1_fwd_workspace(int64_t B, int Cin, int Cout, int P) {
-    if (conv_tc2_padded(Cin, Cout, P)) return B * (int64_t)Cin * pad4(P) * (int64_t)sizeof(float);  // x at a pitch of pad4(P)
-    return 0;  // the in-place TMA route streams x and W as they are
+    (void)B; (void)Cin; (void)Cout; (void)P;
+    return 0;  // the TMA route streams x and W in place (kept in the ABI: earlier builds staged planes here)
 }
 
 int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B, int Cin, int Cout, int P, float* y,
@@ -258,16 +227,7 @@ int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B,
     PP_REQUIRE(x && w && y, "pp_conv1x1_fwd: null pointer");
     PP_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && P > 0 && B * P < (1 << 24), "pp_conv1x1_fwd: bad shape");
     const int NP = (int)(B * P);
-    if (conv_tc2_padded(Cin, Cout, P) && workspace && B <= 65535) {
-        float* xp = (float*)workspace;
-        int rc = launch_pad(x, xp, B * Cin, nullptr, nullptr, 0, P, (cudaStream_t)stream);
-        if (rc) return rc;
-        tc2::Operands o{w, nullptr, xp, nullptr, Cin};
-        o.b_mn = true;
-        o.b_pitch = pad4(P);
-        rc = tc2::launch_tc2_sets("conv1x1 fwd (tcgen05)", B, Cout, P, &o, 1, TcStBias{y, bias, Cout, P, 0}, (cudaStream_t)stream, true);
-        if (rc >= 0) return rc;
-    }
+    (void)workspace;
     if (conv_tc2(Cin, Cout, P)) {
         tc2::Operands o{w, nullptr, x, nullptr, Cin};
         o.b_mn = true;
@@ -282,8 +242,6 @@ int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P) {
     const int64_t splits = (B * P + kWgradSplitK - 1) / kWgradSplitK;
     int64_t f = splits * Cin * Cout + B * Cout;  // split-K partials of dW, then the row sums of db
     if (conv_tc2(Cin, Cout, P)) f += B * (int64_t)Cout * Cin;  // wgrad: per-sample partials of dW
-    if (conv_tc2_padded(Cin, Cout, P))  // dy (dgrad) | x, dy (wgrad) at a pitch of pad4(P) | B / kb partials of dW
-        f += B * (int64_t)(2 * Cout + Cin) * pad4(P) + ((B + kWgradKb - 1) / kWgradKb) * (int64_t)Cout * Cin;
     return f * (int64_t)sizeof(float);
 }
 
@@ -297,39 +255,6 @@ static int conv1x1_bwd_impl(const float* x, const float* w, const float* dy, int
     const int64_t base_f = (int64_t)((NP + kWgradSplitK - 1) / kWgradSplitK) * Cin * Cout + B * Cout;
     const bool tma = conv_tc2(Cin, Cout, P);
     float* part_b = (float*)workspace + base_f;  // per-sample partials of dW (TMA route)
-    if (conv_tc2_padded(Cin, Cout, P) && B <= 65535 && (dx || dw)) {
-        // Regions: dy_a (the call that computes dx) | x_p, dy_b (a call that computes only dw) | partials.  The three gradients may
-        // be requested by three concurrent calls on different streams (ops.py), so a dx call and a dw-only call never share a copy.
-        const int PP = pad4(P);
-        float* dy_a = (float*)workspace + base_f;
-        float* x_p = dy_a + B * (int64_t)Cout * PP;
-        float* dy_b = x_p + B * (int64_t)Cin * PP;
-        float* part = dy_b + B * (int64_t)Cout * PP;
-        float* dy_p = dx ? dy_a : dy_b;
-        rc = launch_pad(dy, dy_p, B * Cout, dw ? x : nullptr, x_p, B * Cin, P, st);
-        if (rc) return rc;
-        if (dx) {
-            tc2::Operands o{w, nullptr, dy_p, nullptr, Cout};
-            o.a_mn = o.b_mn = true;
-            o.b_pitch = PP;
-            rc = tc2::launch_tc2_sets("conv1x1 dgrad (tcgen05)", B, Cin, P, &o, 1, TcStBias{dx, nullptr, Cin, P, dx_acc}, st, true);
-            if (rc > 0) return rc;
-            if (rc == 0) dx = nullptr;  // done
-        }
-        if (dw) {
-            tc2::Operands o{dy_p, nullptr, x_p, nullptr, P};
-            o.a_pitch = o.b_pitch = PP;
-            rc = tc2::launch_tc2_sets("conv1x1 wgrad (tcgen05)", B, Cout, Cin, &o, 1, TcStN{part, Cout, Cin}, st, false, kWgradKb);
-            if (rc > 0) return rc;
-            if (rc == 0) {
-                const int total = Cout * Cin, groups = (int)((B + kWgradKb - 1) / kWgradKb);
-                PP_LAUNCH("conv1x1 wgrad reduce", st, conv_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, groups, total, dw));
-                rc = check_launch("conv_wgrad_reduce_kernel");
-                if (rc) return rc;
-                dw = nullptr;  // done
-            }
-        }
-    }
     if (dx && tma) {
         tc2::Operands o{w, nullptr, dy, nullptr, Cout};
         o.a_mn = o.b_mn = true;

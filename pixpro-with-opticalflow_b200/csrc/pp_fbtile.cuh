@@ -742,9 +742,8 @@ static int launch(const float* f0, const float* f1, uint8_t* m0, uint8_t* m1, in
     // the published frame size: every derived constant folds into instruction immediates.  Box row pitch: 96 floats = 0 mod 32
     // banks measured best (360 us); pitches 88 / 92 / 100 / 104 / 108 (with the box height adjusted to the same shared memory)
     // trade same-row conflicts for cross-row ones and cost 376-412 us (profiles/r02_t_fb_pitch.txt).
-    if (W == 1280 && H == 720 && variant == 2) return launch_cfg<64, 48, 96, 72, 3, 1280, 720>(a, B, st);  // experiment: 3 CTAs / SM
-    if (W == 1280 && H == 720 && variant == 3) return launch_cfg<64, 48, 96, 64, 4, 1280, 720>(a, B, st);  // experiment: 64-row box
-    if (W == 1280 && H == 720 && variant == 4) return launch_cfg<64, 48, 96, 60, 4, 1280, 720>(a, B, st);  // experiment: 60-row box
+    // measured and removed again (profiles/r02_u_flow_overlap.txt, r02_ab_fb_boxrows.txt): 3 CTAs / SM at 72 registers (10 % slower);
+    // 64- and 60-row boxes (359 / 358 us vs 361 us, 0.7 % / 1.4 % of the pixels on the global path: free — fbbox_up_kernel uses 64 rows)
     if (W == 1280 && H == 720) return launch_cfg<64, 48, 96, 72, 4, 1280, 720>(a, B, st);
     if (H % 48 == 0) return launch_cfg<64, 48, 96, 72, 4>(a, B, st);
     if (H % 32 == 0) return launch_cfg<64, 32, 96, 56, 4>(a, B, st);

@@ -1,5 +1,6 @@
 """Value transform at the 7x7 grid (1x1 conv 256 -> 256 on [128, 256, 7, 7]) through this package's kernels: device time of every
-launch (the library's event brackets), padded TMA route (default) vs the thread-staged kernel (PIXPRO_B200_CONVPAD=0)."""
+launch (the library's event brackets).  History: written for the A/B of the padded TMA route (PIXPRO_B200_CONVPAD, removed after
+profiles/r02_v_conv7.txt / r02_w_convpad_step.txt); it now times the thread-staged kernels the 7x7 grid runs on."""
 import os
 import sys
 
