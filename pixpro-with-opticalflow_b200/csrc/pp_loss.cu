@@ -339,6 +339,25 @@ __global__ void __launch_bounds__(256) loss_centres_kernel(PrepArgs a) {
     }
 }
 
+// The positive test of one pair, d(s) = RN(RN(sqrt(s)) / md) < pr with s = RN(RN(dx^2) + RN(dy^2)) (PixPro.py:217-219), is a
+// monotone function of s: both correctly rounded operations are non-decreasing.  So for a sample (md) there is ONE float s* with
+// d(s) < pr  <=>  s < s*, and the P^2 pair tests of the large grids (614 656 per sample and direction at 28x28, each a square
+// root and a division = ~20 of their ~30 instructions) become one comparison each — same bits, NaN and infinity included (both
+// forms are false for them).  s* = the smallest float whose d is not below pr, found by stepping ulps from (pr md)^2, with the
+// exact test itself as the judge; < 0 = not found within the step budget (the caller then tests every pair exactly).
+__device__ __forceinline__ bool dist_below(float s, float md, float pr) { return __fdiv_rn(__fsqrt_rn(s), md) < pr; }
+__device__ float pos_threshold(float md, float pr) {
+    if (!(md > 0.0f) || !(pr > 0.0f) || !isfinite(md) || !isfinite(pr)) return -1.0f;
+    float s = mul(mul(pr, md), mul(pr, md));
+    if (!isfinite(s) || !(s > 1e-30f)) return -1.0f;
+    int n = 0;
+    for (; n < 64 && dist_below(s, md, pr); n++) s = __uint_as_float(__float_as_uint(s) + 1u);            // up to the first false
+    if (n == 64) return -1.0f;
+    for (n = 0; n < 64 && !dist_below(__uint_as_float(__float_as_uint(s) - 1u), md, pr); n++)              // down to the smallest false
+        s = __uint_as_float(__float_as_uint(s) - 1u);
+    return (n == 64 || !isfinite(s)) ? -1.0f : s;
+}
+
 // grid (ceil(P/8), B); warp w of the block owns query cell i = 8*blockIdx.x + w
 // posf (optional): the same matrix as 0/1 floats — the B operand plane the TMA-fed contraction streams (exact in TF32)
 __global__ void __launch_bounds__(256) loss_pos_kernel(LossWs ws, int P, float pr, uint8_t* posb, float* posf) {
@@ -351,6 +370,38 @@ __global__ void __launch_bounds__(256) loss_pos_kernel(LossWs ws, int P, float p
     const float* ky = ws.cky + b * P;
     uint8_t* row = posb + (b * P + i) * (int64_t)P;
     int cnt = 0;
+    const float sstar = mg ? pos_threshold(md, pr) : 0.0f;  // warp-uniform (a masked-out query cell has no positives: s < 0 never)
+    if (sstar >= 0.0f && (P & 3) == 0) {  // 4 key cells per lane: one 16-byte and one 4-byte store per 4 pairs
+        float* rowf = posf ? posf + (b * P + i) * (int64_t)P : nullptr;
+        for (int j = 4 * lane; j < P; j += 128) {
+            const float4 x4 = *reinterpret_cast<const float4*>(kx + j), y4 = *reinterpret_cast<const float4*>(ky + j);
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w};
+            bool ps[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float dx = sub(qx, xs[u]), dy = sub(qy, ys[u]);
+                ps[u] = add(mul(dx, dx), mul(dy, dy)) < sstar;
+                cnt += ps[u];
+            }
+            *reinterpret_cast<uchar4*>(row + j) = make_uchar4(ps[0], ps[1], ps[2], ps[3]);
+            if (rowf) *reinterpret_cast<float4*>(rowf + j) = make_float4(ps[0] ? 1.0f : 0.0f, ps[1] ? 1.0f : 0.0f, ps[2] ? 1.0f : 0.0f, ps[3] ? 1.0f : 0.0f);
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) ws.rowcnt[b * P + i] = cnt;
+        return;
+    }
+    if (sstar >= 0.0f) {
+        for (int j = lane; j < P; j += 32) {
+            const float dx = sub(qx, kx[j]), dy = sub(qy, ky[j]);
+            const bool pos = add(mul(dx, dx), mul(dy, dy)) < sstar;
+            row[j] = pos ? 1 : 0;
+            if (posf) posf[(b * P + i) * (int64_t)P + j] = pos ? 1.0f : 0.0f;
+            cnt += pos;
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) ws.rowcnt[b * P + i] = cnt;
+        return;
+    }
     for (int j = lane; j < P; j += 32) {
         bool pos = mg && pair_pos(qx, qy, kx[j], ky[j], md, pr);
         row[j] = pos ? 1 : 0;
