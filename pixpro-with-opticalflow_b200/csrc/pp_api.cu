@@ -85,6 +85,10 @@ static std::vector<int64_t> g_prof_count;
 static std::vector<double> g_prof_ms;
 
 ProfScope::ProfScope(const char* name, cudaStream_t st) : name_(name), st_(st), e1_(nullptr) {
+    // Runs right before every launch of this library (PP_LAUNCH): drop a stale NON-sticky error an earlier call of another
+    // library left in this thread's error slot, so that check_launch() after the launch reports this launch and nothing else
+    // (a sticky error survives cudaGetLastError and is still reported).
+    (void)cudaGetLastError();
     if (!g_prof_on) return;
     cudaEvent_t e0;
     cudaEventCreate(&e0);
