@@ -511,7 +511,7 @@ struct SmallLossArgs2 {
 };
 
 __host__ __device__ inline size_t small_loss_smem_bytes(int C, int P) {
-    return ((size_t)2 * ((size_t)C * P + SLACK) + (size_t)PMAX * PS + 5 * PMAX + 4 * PMAX + 16) * sizeof(float);
+    return ((size_t)2 * ((size_t)C * P + SLACK) + (size_t)PMAX * PS + 5 * PMAX + SM_THREADS + 16) * sizeof(float);
 }
 
 __global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs2 sa2) {
@@ -527,8 +527,8 @@ __global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs2 s
     float* kx = qy + PMAX;
     float* ky = kx + PMAX;
     float* mgs = ky + PMAX;
-    float* red = mgs + PMAX;       // 4*PMAX scratch
-    float* sc = red + 4 * PMAX;    // [0] md, [1] den
+    float* red = mgs + PMAX;       // SM_THREADS scratch
+    float* sc = red + SM_THREADS;  // [0] md, [1] den
     const int64_t b = ((int)blockIdx.x < sa2.B) ? blockIdx.x : blockIdx.x - sa2.B;
     const int64_t off = b * (int64_t)C * P;
     stage_dense(ks, sa.k + off, CP);
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(SM_THREADS) loss_small_kernel(SmallLossArgs2 s
         cnt += pos ? 1.0f : 0.0f;
         if (a.pos_mask) a.pos_mask[(b * P + i) * (int64_t)P + j] = pos ? 1 : 0;
     }
-    red[threadIdx.x] = cnt;  // 4*PMAX = 256 slots
+    red[threadIdx.x] = cnt;
     __syncthreads();
     if (threadIdx.x < 32) {
         float t = 0.0f;

@@ -28,7 +28,9 @@ struct SmallArgs {
 // 512 threads per block: one block per sample keeps one SM busy, so its 16 warps (instead of 8) are
 // what hides the shared-memory and FMA latencies of the short serial phases (measured: issue slots
 // 30 % busy with 8 warps).  The two contractions split their work over the two 256-thread halves
-// (gram_tile_split: channel halves; row_times_mat_split: column halves).
+// (gram_tile_split: channel halves; row_times_mat_split: column halves).  1024 threads (with PMAX = 52 to make room for the
+// two extra gram partials) were measured in round 2: no change (backward 61-64 us, forward 37 us) — the phases are bound by
+// their shared-memory instruction count and the barriers between them, not by the number of warps.
 constexpr int PT = 512;
 constexpr int PRED = PT / 64;  // partial rows of col_reduce
 

@@ -55,7 +55,7 @@ __device__ __forceinline__ void col_reduce(int C, int P, float* red, float* res 
         }
         for (; c < C; c += NPART) s0 += f(c, i);
     }
-    red[part * PMAX + i] = (s0 + s1) + (s2 + s3);
+    if (i < PMAX) red[part * PMAX + i] = (s0 + s1) + (s2 + s3);  // a part is 64 threads wide, a row of `red` PMAX floats
     __syncthreads();
     if (threadIdx.x < PMAX) {
         float t = 0.0f;
