@@ -61,14 +61,14 @@ struct LdCN {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (row < C && k < KS) {
             const int n0 = (int)s * KS + k;
+            int b, p;
+            dp(n0, b, p);  // one (sample, pixel) split per item; the next three joint indices follow by increment
+            const float* q = t + ((int64_t)b * C + row) * dp.P + p;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int n = n0 + u;
-                if (k + u < KS && n < NP) {
-                    int b, p;
-                    dp(n, b, p);
-                    v[u] = __ldg(t + ((int64_t)b * C + row) * dp.P + p);
-                }
+                if (k + u < KS && n0 + u < NP) v[u] = __ldg(q);
+                ++q;
+                if (++p == dp.P) { p = 0; q += (int64_t)(C - 1) * dp.P; }  // row `row` of the next sample
             }
         }
         return make_float4(v[0], v[1], v[2], v[3]);
