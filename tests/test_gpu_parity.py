@@ -395,6 +395,27 @@ def test_regression_loss_vs_oracle(ops, orc, synth, G, C, B, use_flow, use_mask)
     assert rel_err(npy(qg.grad), 3.0 * o["dq"]) < TOL
 
 
+@pytest.mark.parametrize("pos_ratio", [0.0, 1e-3, 0.3, 0.7, 2.5, 1e6])
+def test_large_grid_positive_threshold_vs_oracle(ops, orc, synth, pos_ratio):
+    """The large-grid positive matrix decides each pair by comparing its squared centre distance with a per-sample threshold
+    (pp_loss.cu, pos_threshold) instead of a square root and a division per pair: every bit must equal the oracle's pair-by-pair
+    test, from `no pair is positive` to `every pair is`, including crops of very different sizes (the bin diagonal varies 30x)."""
+    G, C, B = 14, 32, 6
+    cq = synth.crop_coords(B, seed=11, scale=(0.002, 1.0))
+    ck = synth.crop_coords(B, seed=12, scale=(0.002, 1.0))
+    gen = torch.Generator().manual_seed(5)
+    q = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(B, C, G, G, generator=gen), dim=1)
+    o = orc.regression_loss(q.numpy(), k.numpy(), cq.numpy(), ck.numpy(), pos_ratio, size=(720, 1280))
+    _, pos_num, _, pos_mask, _ = ops.regression_loss(q.to(DEV), k.to(DEV), cq.to(DEV), ck.to(DEV), pos_ratio, size=(720, 1280), debug=True)
+    assert_bits_equal(npy(pos_mask), o["pos_mask"], "pos_mask")
+    assert_bits_equal(npy(pos_num), o["pos_num"], "pos_num")
+    if pos_ratio == 0.0:
+        assert npy(pos_num).sum() == 0
+    if pos_ratio == 1e6:
+        assert npy(pos_num).min() == G ** 4
+
+
 @pytest.mark.parametrize("G", [7, 14])
 def test_regression_loss_adversarial_crops_vs_oracle(ops, orc, G):
     """Edge cases of the positive mask: disjoint crops (no positive pair: loss_b = 0 by the 1e-6 in the
