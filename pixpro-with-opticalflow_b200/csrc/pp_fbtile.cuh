@@ -86,6 +86,72 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, i
                  : "memory");
 }
 
+// The FB test of one packed pixel pair (two rows 8 apart of one column), shared by fbbox_kernel and fbbox_up_kernel: own flow
+// (fxs, fys) -> normalised position (util.py:264-276) -> the 2x2 taps of the gather source from the staged box (in line from
+// global memory `g` when the footprint is outside the box) -> cycle test (util.py:279-296) -> the two mask bytes.
+template <int BW, int BH>
+__device__ __forceinline__ void fb_pair(const float (&fxs)[2], const float (&fys)[2], const F2 xn, const F2 yn, const Div2& dW,
+                                        const Div2& dH, const F2 one2, const F2 hw2, const F2 hh2, const F2 a1_2, const F2 a2_2,
+                                        const float* sp, const int2 o, const float* g, const int W, const int H, const int HW,
+                                        uint8_t* m0, uint8_t* m1, int& nglobal) {
+    const F2 fnx = dW(pk(fxs[0], fxs[1])), fny = dH(pk(fys[0], fys[1]));                           // :264
+    const F2 c1x = add2(xn, fnx), c1y = add2(yn, fny);                                             // :275
+    // (c1 + 1) * half: >= 0 for every in-frame pixel, so the non-contractable product form is exact
+    const F2 ix = mul2_nc(add2(c1x, one2), hw2), iy = mul2_nc(add2(c1y, one2), hh2);
+    float c1xs[2], c1ys[2], ixs[2], iys[2];
+    unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
+    unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
+    bool inb[2], outside[2];
+    int gofs[2];
+    float t[2][8], xws[2], yws[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);                               // :276
+        const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
+        xws[p] = __int2float_rn(x0);
+        yws[p] = __int2float_rn(y0);
+        const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
+        outside[p] = inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
+        gofs[p] = (y0 << 16) | (x0 & 0xffff);  // only read for in-frame pixels (launcher: W, H < 32768)
+        // clamp: a pixel outside the box or the frame still addresses the staged box
+        const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
+        t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
+        t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
+    }
+    if (outside[0] || outside[1]) {
+        // footprint outside the staged box (rare): the same taps straight from global memory,
+        // zero where grid_sample pads (an in-frame pixel can only miss column W or row H)
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+            if (outside[p]) {
+                const int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
+                const float* q = ptr_at(g, y0 * W + x0);
+                const bool xin = x0 < W - 1, yin = y0 < H - 1;
+                t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
+                t[p][1] = xin ? __ldg(q + 1) : 0.0f; t[p][5] = xin ? __ldg(ptr_at(q, HW) + 1) : 0.0f;
+                t[p][2] = yin ? __ldg(ptr_at(q, W)) : 0.0f; t[p][6] = yin ? __ldg(ptr_at(q, HW + W)) : 0.0f;
+                t[p][3] = (xin && yin) ? __ldg(ptr_at(q, W) + 1) : 0.0f; t[p][7] = (xin && yin) ? __ldg(ptr_at(q, HW + W) + 1) : 0.0f;
+                nglobal++;
+            }
+    }
+    const F2 wx = sub2(ix, pk(xws[0], xws[1])), wy = sub2(iy, pk(yws[0], yws[1]));
+    const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
+    const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
+    const F2 bx = combine4_2(dW(pk(t[0][0], t[1][0])), dW(pk(t[0][1], t[1][1])), dW(pk(t[0][2], t[1][2])),
+                             dW(pk(t[0][3], t[1][3])), nw, ne, sw, se);
+    const F2 by = combine4_2(dH(pk(t[0][4], t[1][4])), dH(pk(t[0][5], t[1][5])), dH(pk(t[0][6], t[1][6])),
+                             dH(pk(t[0][7], t[1][7])), nw, ne, sw, se);
+    const F2 cyx = add2(fnx, bx), cyy = add2(fny, by);                                             // :279
+    // squares and alpha_1 * sum are never -0 (alpha_1 >= 0 is checked by the launcher)
+    const F2 cyc2 = add2(mul2_nc(cyx, cyx), mul2_nc(cyy, cyy));                                    // :293
+    const F2 f2 = add2(mul2_nc(fnx, fnx), mul2_nc(fny, fny)), b2 = add2(mul2_nc(bx, bx), mul2_nc(by, by));
+    const F2 eps = add2(mul2_nc(a1_2, add2(f2, b2)), a2_2);                                        // :294
+    float ds[2];
+    unpk(sub2(cyc2, eps), ds[0], ds[1]);
+    *m0 = (inb[0] && (ds[0] <= 0.0f)) ? 1 : 0;                                                     // :296
+    *m1 = (inb[1] && (ds[1] <= 0.0f)) ? 1 : 0;
+}
+
 // grid = (W / TW, H / TH, planes); block = 256.  Requires W % TW == 0 and H % TH == 0.
 // WC/HC > 0: the frame size is a compile-time constant (the 1280x720 frames of the published BDD100K runs): every
 // derived constant and row offset folds into instruction immediates (no per-pixel constant-bank loads).
@@ -198,65 +264,8 @@ __global__ void __launch_bounds__(256, MINB) fbbox_kernel(const __grid_constant_
         const F2 yn = sub2(dH(pk((float)(Y0 + 8 * kp), (float)(Y0 + 8 * kp + 8))), one2);          // :271
 #pragma unroll
         for (int c = 0; c < NX; c++) {
-            const F2 fnx = dW(pk(fxs[c][0], fxs[c][1])), fny = dH(pk(fys[c][0], fys[c][1]));       // :264
-            const F2 c1x = add2(xn2[c], fnx), c1y = add2(yn, fny);                                 // :275
-            // (c1 + 1) * half: >= 0 for every in-frame pixel, so the non-contractable product form is exact
-            const F2 ix = mul2_nc(add2(c1x, one2), hw2), iy = mul2_nc(add2(c1y, one2), hh2);
-            float c1xs[2], c1ys[2], ixs[2], iys[2];
-            unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
-            unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
-            bool inb[2], outside[2];
-            int gofs[2];
-            float t[2][8], xws[2], yws[2];
-#pragma unroll
-            for (int p = 0; p < 2; p++) {
-                inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);                       // :276
-                const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
-                xws[p] = __int2float_rn(x0);
-                yws[p] = __int2float_rn(y0);
-                const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
-                outside[p] = inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
-                gofs[p] = (y0 << 16) | (x0 & 0xffff);  // only read for in-frame pixels (launcher: W, H < 32768)
-                // clamp: a pixel outside the box or the frame still addresses the staged box
-                const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
-                t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
-                t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
-            }
-            if (outside[0] || outside[1]) {
-                // footprint outside the staged box (rare): the same taps straight from global memory,
-                // zero where grid_sample pads (an in-frame pixel can only miss column W or row H)
-#pragma unroll
-                for (int p = 0; p < 2; p++)
-                    if (outside[p]) {
-                        const int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
-                        const float* q = ptr_at(g, y0 * W + x0);
-                        const bool xin = x0 < W - 1, yin = y0 < H - 1;
-                        t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
-                        t[p][1] = xin ? __ldg(q + 1) : 0.0f; t[p][5] = xin ? __ldg(ptr_at(q, HW) + 1) : 0.0f;
-                        t[p][2] = yin ? __ldg(ptr_at(q, W)) : 0.0f; t[p][6] = yin ? __ldg(ptr_at(q, HW + W)) : 0.0f;
-                        t[p][3] = (xin && yin) ? __ldg(ptr_at(q, W) + 1) : 0.0f; t[p][7] = (xin && yin) ? __ldg(ptr_at(q, HW + W) + 1) : 0.0f;
-                        nglobal++;
-                    }
-            }
-            const F2 wx = sub2(ix, pk(xws[0], xws[1])), wy = sub2(iy, pk(yws[0], yws[1]));
-            const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
-            const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
-            const F2 bx = combine4_2(dW(pk(t[0][0], t[1][0])), dW(pk(t[0][1], t[1][1])), dW(pk(t[0][2], t[1][2])),
-                                     dW(pk(t[0][3], t[1][3])), nw, ne, sw, se);
-            const F2 by = combine4_2(dH(pk(t[0][4], t[1][4])), dH(pk(t[0][5], t[1][5])), dH(pk(t[0][6], t[1][6])),
-                                     dH(pk(t[0][7], t[1][7])), nw, ne, sw, se);
-            const F2 cyx = add2(fnx, bx), cyy = add2(fny, by);                                     // :279
-            // squares and alpha_1 * sum are never -0 (alpha_1 >= 0 is checked by the launcher)
-            const F2 cyc2 = add2(mul2_nc(cyx, cyx), mul2_nc(cyy, cyy));                            // :293
-            const F2 f2 = add2(mul2_nc(fnx, fnx), mul2_nc(fny, fny)), b2 = add2(mul2_nc(bx, bx), mul2_nc(by, by));
-            const F2 eps = add2(mul2_nc(a1_2, add2(f2, b2)), a2_2);                                // :294
-            float ds[2];
-            unpk(sub2(cyc2, eps), ds[0], ds[1]);
-#pragma unroll
-            for (int p = 0; p < 2; p++) {
-                const uint8_t bit = (inb[p] && (ds[p] <= 0.0f)) ? 1 : 0;                             // :296
-                *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = bit;
-            }
+            fb_pair<BW, BH>(fxs[c], fys[c], xn2[c], yn, dW, dH, one2, hw2, hh2, a1_2, a2_2, sp, o, g, W, H, HW,
+                            byte_ptr_at(mp, kp * rstep + 32 * c), byte_ptr_at(mp, (kp + 1) * rstep + 32 * c), nglobal);
         }
     }
     // diagnostics counter: one global atomic per CTA at most (per-thread atomics on one address
@@ -420,60 +429,8 @@ __global__ void __launch_bounds__(256, MINB) fbbox_up_kernel(const __grid_consta
                     *ptr_at(q, HW) = fys[p];
                 }
             }
-            const F2 fnx = dW(pk(fxs[0], fxs[1])), fny = dH(pk(fys[0], fys[1]));
-            const F2 c1x = add2(xn2[c], fnx), c1y = add2(yn, fny);
-            const F2 ix = mul2_nc(add2(c1x, one2), hw2), iy = mul2_nc(add2(c1y, one2), hh2);
-            float c1xs[2], c1ys[2], ixs[2], iys[2];
-            unpk(c1x, c1xs[0], c1xs[1]); unpk(c1y, c1ys[0], c1ys[1]);
-            unpk(ix, ixs[0], ixs[1]); unpk(iy, iys[0], iys[1]);
-            bool inb[2], outside[2];
-            int gofs[2];
-            float t[2][8], xws[2], yws[2];
-#pragma unroll
-            for (int p = 0; p < 2; p++) {
-                inb[p] = (fabsf(c1xs[p]) < 1.0f) && (fabsf(c1ys[p]) < 1.0f);
-                const int x0 = __float2int_rd(ixs[p]), y0 = __float2int_rd(iys[p]);
-                xws[p] = __int2float_rn(x0);
-                yws[p] = __int2float_rn(y0);
-                const unsigned dx = (unsigned)(x0 - o.x), dy = (unsigned)(y0 - o.y);
-                outside[p] = inb[p] && (dx > (unsigned)(BW - 2) || dy > (unsigned)(BH - 2));
-                gofs[p] = (y0 << 16) | (x0 & 0xffff);
-                const float* q = sp + min(dy, (unsigned)(BH - 2)) * BW + min(dx, (unsigned)(BW - 2));
-                t[p][0] = q[0]; t[p][1] = q[1]; t[p][2] = q[BW]; t[p][3] = q[BW + 1];
-                t[p][4] = q[BW * BH]; t[p][5] = q[BW * BH + 1]; t[p][6] = q[BW * BH + BW]; t[p][7] = q[BW * BH + BW + 1];
-            }
-            if (outside[0] || outside[1]) {
-#pragma unroll
-                for (int p = 0; p < 2; p++)
-                    if (outside[p]) {
-                        const int x0 = gofs[p] & 0xffff, y0 = gofs[p] >> 16;
-                        const float* q = ptr_at(g, y0 * W + x0);
-                        const bool xin = x0 < W - 1, yin = y0 < H - 1;
-                        t[p][0] = __ldg(q); t[p][4] = __ldg(ptr_at(q, HW));
-                        t[p][1] = xin ? __ldg(q + 1) : 0.0f; t[p][5] = xin ? __ldg(ptr_at(q, HW) + 1) : 0.0f;
-                        t[p][2] = yin ? __ldg(ptr_at(q, W)) : 0.0f; t[p][6] = yin ? __ldg(ptr_at(q, HW + W)) : 0.0f;
-                        t[p][3] = (xin && yin) ? __ldg(ptr_at(q, W) + 1) : 0.0f; t[p][7] = (xin && yin) ? __ldg(ptr_at(q, HW + W) + 1) : 0.0f;
-                        nglobal++;
-                    }
-            }
-            const F2 wx = sub2(ix, pk(xws[0], xws[1])), wy = sub2(iy, pk(yws[0], yws[1]));
-            const F2 e = sub2(one2, wx), s_ = sub2(one2, wy);
-            const F2 nw = mul2(s_, e), ne = mul2(s_, wx), sw = mul2(wy, e), se = mul2(wy, wx);
-            const F2 bx = combine4_2(dW(pk(t[0][0], t[1][0])), dW(pk(t[0][1], t[1][1])), dW(pk(t[0][2], t[1][2])),
-                                     dW(pk(t[0][3], t[1][3])), nw, ne, sw, se);
-            const F2 by = combine4_2(dH(pk(t[0][4], t[1][4])), dH(pk(t[0][5], t[1][5])), dH(pk(t[0][6], t[1][6])),
-                                     dH(pk(t[0][7], t[1][7])), nw, ne, sw, se);
-            const F2 cyx = add2(fnx, bx), cyy = add2(fny, by);
-            const F2 cyc2 = add2(mul2_nc(cyx, cyx), mul2_nc(cyy, cyy));
-            const F2 f2 = add2(mul2_nc(fnx, fnx), mul2_nc(fny, fny)), b2 = add2(mul2_nc(bx, bx), mul2_nc(by, by));
-            const F2 eps = add2(mul2_nc(a1_2, add2(f2, b2)), a2_2);
-            float ds[2];
-            unpk(sub2(cyc2, eps), ds[0], ds[1]);
-#pragma unroll
-            for (int p = 0; p < 2; p++) {
-                const uint8_t bit = (inb[p] && (ds[p] <= 0.0f)) ? 1 : 0;
-                *byte_ptr_at(mp, (kp + p) * rstep + 32 * c) = bit;
-            }
+            fb_pair<BW, BH>(fxs, fys, xn2[c], yn, dW, dH, one2, hw2, hh2, a1_2, a2_2, sp, o, g, W, H, HW,
+                            byte_ptr_at(mp, kp * rstep + 32 * c), byte_ptr_at(mp, (kp + 1) * rstep + 32 * c), nglobal);
         }
     }
     const int wsum = __reduce_add_sync(0xffffffffu, nglobal);
