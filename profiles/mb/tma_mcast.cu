@@ -13,7 +13,11 @@
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-constexpr int STAGES = 4, KF = 16;                 // K chunk = 16 floats = 64 bytes per row
+#ifndef KFLOATS
+#define KFLOATS 16
+#endif
+constexpr int KF = KFLOATS;                      // K chunk: 16 floats = 64-byte rows (SWIZZLE_64B), 32 = 128-byte rows
+constexpr int MAXST = KF == 16 ? 4 : 2;
 constexpr int AROWS = 128, BROWS = 256;
 constexpr uint32_t A_BYTES = AROWS * KF * 4, B_BYTES = BROWS * KF * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -30,9 +34,9 @@ __device__ __forceinline__ void cluster_sync() {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64, 1)
 k(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const __grid_constant__ CUtensorMap tmbh, int mode,
-  int iters, int rows_total, int kchunks, int* fail) {
+  int iters, int rows_total, int kchunks, int* fail, int STAGES) {
     extern __shared__ __align__(1024) uint8_t ring[];
-    __shared__ uint64_t full[STAGES], empty[STAGES];
+    __shared__ uint64_t full[MAXST], empty[MAXST];
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,7 +84,9 @@ k(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap t
     cluster_sync();  // no CTA leaves while its peer may still arrive on its barriers / write its shared memory
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const int STAGES = argc > 1 ? (atoi(argv[1]) < MAXST ? atoi(argv[1]) : MAXST) : MAXST;   // ring depth
+    const int grid_arg = argc > 2 ? atoi(argv[2]) : 0;  // CTAs (0 = one per SM)
     const int ROWS = 32768, K = 256;  // 32 MB fp32 matrix: L2-resident after the first pass
     float* d; cudaMalloc(&d, (size_t)ROWS * K * 4); cudaMemset(d, 0, (size_t)ROWS * K * 4);
     void* p = nullptr; cudaDriverEntryPointQueryResult q;
@@ -90,29 +96,29 @@ int main() {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)ROWS}; cuuint64_t strides[1] = {(cuuint64_t)K * 4};
         cuuint32_t box[2] = {KF, (cuuint32_t)box_rows}; cuuint32_t es[2] = {1, 1};
         return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   KF == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     CUtensorMap tma, tmb, tmbh;
     if (mk(&tma, AROWS) || mk(&tmb, BROWS) || mk(&tmbh, BROWS / 2)) { printf("encode failed\n"); return 1; }
     int* fail; cudaMalloc(&fail, 4); cudaMemset(fail, 0, 4);
-    const int smem = STAGES * STAGE_BYTES + 1024;
+    const int smem = MAXST * STAGE_BYTES + 1024;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const int grid = sms & ~1, iters = 4096;
+    const int grid = (grid_arg ? grid_arg : sms) & ~1, iters = 4096;
     for (int mode = 0; mode < 2; mode++) {
         for (int rep = 0; rep < 2; rep++) {
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             cudaEventRecord(e0);
-            k<<<grid, 64, smem>>>(tma, tmb, tmbh, mode, iters, ROWS, K / KF, fail);
+            k<<<grid, 64, smem>>>(tma, tmb, tmbh, mode, iters, ROWS, K / KF, fail, STAGES);
             cudaEventRecord(e1);
             cudaError_t er = cudaDeviceSynchronize();
             float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
             int hf = 0; cudaMemcpy(&hf, fail, 4, cudaMemcpyDeviceToHost);
             const double delivered = (double)iters * STAGE_BYTES, clk = ms * 1e-3 * 1.965e9;
             const double from_l2 = (double)iters * (mode ? A_BYTES + B_BYTES / 2 : STAGE_BYTES);
-            if (rep) printf("mode %d (%s): %s fail=%d  %.3f ms  delivered %.1f B/clk/SM  read from L2 %.1f B/clk/SM  (%d CTAs)\n", mode,
+            if (rep) printf("mode %d (%s): %s fail=%d  %.3f ms  delivered %.1f B/clk/SM  read from L2 %.1f B/clk/SM  (%d CTAs, %d stages)\n", mode,
                             mode ? "B tile multicast inside 2-CTA clusters" : "every CTA loads everything", cudaGetErrorString(er), hf, ms,
-                            delivered / clk, from_l2 / clk, grid);
+                            delivered / clk, from_l2 / clk, grid, STAGES);
         }
     }
     return 0;
