@@ -195,11 +195,6 @@ PP_API int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int
 PP_API int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P);
 PP_API int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
                           float* dw, float* db, void* workspace, void* stream);
-/* The same with dx += instead of dx =: in PixPro.featprop (contrast/models/PixPro.py:343-354) the input feeds both the value
- * transform and the similarity, so its gradient is the sum of this data gradient and pp_ppm_bwd's d_feat_sim; with dx = the
- * buffer pp_ppm_bwd wrote, the sum is formed in the contraction's epilogue (no separate element-wise pass).  dx is required. */
-PP_API int pp_conv1x1_bwd_acc(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
-                              float* dw, float* db, void* workspace, void* stream);
 
 /* ---- multi-tensor optimizer-side kernels ------------------------------
  * A parameter set = a DEVICE table of PpMtTensor entries + a DEVICE chunk map of int pairs

@@ -106,17 +106,13 @@ struct StCN {
     const float* bias;  // may be null
     int C, NP;
     DivP dp;
-    int acc;            // != 0: out += (the data gradient joins the gradient already there, pp_conv1x1_bwd_acc)
     __device__ __forceinline__ void store16(int64_t, int m, int n, const float v[16]) const {
         const float bv = bias ? __ldg(bias + m) : 0.0f;
         int b, p;
         dp(n, b, p);
 #pragma unroll
         for (int u = 0; u < 16; u++) {
-            if (n + u < NP) {
-                float* q = out + ((int64_t)b * C + m) * dp.P + p;
-                *q = acc ? *q + (v[u] + bv) : v[u] + bv;
-            }
+            if (n + u < NP) out[((int64_t)b * C + m) * dp.P + p] = v[u] + bv;
             if (++p == dp.P) { p = 0; b++; }
         }
     }
@@ -179,35 +175,21 @@ static inline bool conv_tc2(int Cin, int Cout, int P) {
 // B = 128, 256 -> 256, 7x7: dgrad 36.9 -> 29.2 us, wgrad 33.5 -> 25.0 us, forward unchanged, but with the pad launches the step got
 // SLOWER (0.689 -> 0.710 ms dense, 0.218 -> 0.237 ms sparse; profiles/r02_v_conv7.txt, r02_w_convpad_step.txt) — these contractions
 // are bound by the latency chain of one tile, not by operand staging — and was removed.
-struct TcStBias {  // out[b][m][n..n+3] = v + bias[m]   (acc != 0: out += v + bias[m])
+struct TcStBias {  // out[b][m][n..n+3] = v + bias[m]
     static constexpr bool kAux = false;
     float* out;
     const float* bias;  // may be null
     int M, N;
-    int acc;
     __device__ __forceinline__ void store4(int64_t b, int m, int n, float4 v) const {
         const float bv = bias ? __ldg(bias + m) : 0.0f;
-        float* q = out + (b * M + m) * (int64_t)N + n;
-        float4 r = make_float4(v.x + bv, v.y + bv, v.z + bv, v.w + bv);
-        if (acc) {
-            if (n + 3 < N && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
-                const float4 o = *reinterpret_cast<const float4*>(q);
-                r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
-            } else {
-                r.x += q[0];
-                if (n + 1 < N) r.y += q[1];
-                if (n + 2 < N) r.z += q[2];
-                if (n + 3 < N) r.w += q[3];
-            }
-        }
-        st4_guard(q, n, N, r);
+        st4_guard(out + (b * M + m) * (int64_t)N + n, n, N, make_float4(v.x + bv, v.y + bv, v.z + bv, v.w + bv));
     }
     __device__ __forceinline__ void store16(int64_t b, int m, int n, const float v[16]) const {
         const float bv = bias ? __ldg(bias + m) : 0.0f;
         float* q = out + (b * M + m) * (int64_t)N + n;
 #pragma unroll
         for (int u = 0; u < 16; u++)
-            if (n + u < N) q[u] = acc ? q[u] + (v[u] + bv) : v[u] + bv;
+            if (n + u < N) q[u] = v[u] + bv;
     }
 };
 
@@ -231,11 +213,11 @@ int pp_conv1x1_fwd(const float* x, const float* w, const float* bias, int64_t B,
     if (conv_tc2(Cin, Cout, P)) {
         tc2::Operands o{w, nullptr, x, nullptr, Cin};
         o.b_mn = true;
-        const int rc = tc2::launch_tc2_sets("conv1x1 fwd (tcgen05)", B, Cout, P, &o, 1, TcStBias{y, bias, Cout, P, 0}, (cudaStream_t)stream, true);
+        const int rc = tc2::launch_tc2_sets("conv1x1 fwd (tcgen05)", B, Cout, P, &o, 1, TcStBias{y, bias, Cout, P}, (cudaStream_t)stream, true);
         if (rc >= 0) return rc;
     }
     return launch_tc("conv1x1 fwd (tcgen05)", 1, Cout, NP, Cin, LdW{w, Cout, Cin}, LdNC{x, Cin, NP, make_divp(P)},
-                     StCN{y, bias, Cout, NP, make_divp(P), 0}, (cudaStream_t)stream);
+                     StCN{y, bias, Cout, NP, make_divp(P)}, (cudaStream_t)stream);
 }
 
 int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P) {
@@ -245,8 +227,8 @@ int64_t pp_conv1x1_bwd_workspace(int64_t B, int Cin, int Cout, int P) {
     return f * (int64_t)sizeof(float);
 }
 
-static int conv1x1_bwd_impl(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
-                            int dx_acc, float* dw, float* db, void* workspace, void* stream) {
+int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
+                   float* dw, float* db, void* workspace, void* stream) {
     PP_REQUIRE(x && w && dy && workspace, "pp_conv1x1_bwd: null pointer");
     PP_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && P > 0 && B * P < (1 << 24), "pp_conv1x1_bwd: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
@@ -258,7 +240,7 @@ static int conv1x1_bwd_impl(const float* x, const float* w, const float* dy, int
     if (dx && tma) {
         tc2::Operands o{w, nullptr, dy, nullptr, Cout};
         o.a_mn = o.b_mn = true;
-        rc = tc2::launch_tc2_sets("conv1x1 dgrad (tcgen05)", B, Cin, P, &o, 1, TcStBias{dx, nullptr, Cin, P, dx_acc}, st, true);
+        rc = tc2::launch_tc2_sets("conv1x1 dgrad (tcgen05)", B, Cin, P, &o, 1, TcStBias{dx, nullptr, Cin, P}, st, true);
         if (rc > 0) return rc;
         if (rc == 0) dx = nullptr;  // done
     }
@@ -276,7 +258,7 @@ static int conv1x1_bwd_impl(const float* x, const float* w, const float* dy, int
     }
     if (dx) {
         rc = launch_tc("conv1x1 dgrad (tcgen05)", 1, Cin, NP, Cout, LdWT{w, Cout, Cin}, LdNC{dy, Cout, NP, make_divp(P)},
-                       StCN{dx, nullptr, Cin, NP, make_divp(P), dx_acc}, st);
+                       StCN{dx, nullptr, Cin, NP, make_divp(P)}, st);
         if (rc) return rc;
     }
     if (dw) {
@@ -301,20 +283,6 @@ static int conv1x1_bwd_impl(const float* x, const float* w, const float* dy, int
         if (rc) return rc;
     }
     return PP_OK;
-}
-
-int pp_conv1x1_bwd(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
-                   float* dw, float* db, void* workspace, void* stream) {
-    return conv1x1_bwd_impl(x, w, dy, B, Cin, Cout, P, dx, 0, dw, db, workspace, stream);
-}
-
-// The same with the data gradient ADDED to what dx holds: in PixPro.featprop the input feeds both the value transform and the
-// similarity (PixPro.py:343-354), so its gradient is the sum of this contraction and the PPM's similarity-branch gradient —
-// written by pp_ppm_bwd first, joined here in the contraction's epilogue instead of by a separate element-wise pass.
-int pp_conv1x1_bwd_acc(const float* x, const float* w, const float* dy, int64_t B, int Cin, int Cout, int P, float* dx,
-                       float* dw, float* db, void* workspace, void* stream) {
-    PP_REQUIRE(dx, "pp_conv1x1_bwd_acc: dx is required (it holds the gradient to add to)");
-    return conv1x1_bwd_impl(x, w, dy, B, Cin, Cout, P, dx, 1, dw, db, workspace, stream);
 }
 
 }  // extern "C"

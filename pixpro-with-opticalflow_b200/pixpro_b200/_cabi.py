@@ -56,7 +56,6 @@ SIGNATURES = {
     "pp_conv1x1_fwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp]),
     "pp_conv1x1_bwd_workspace": (_l, [_l, _i, _i, _i]),
     "pp_conv1x1_bwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "pp_conv1x1_bwd_acc": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pp_tc_gemm_nt": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp]),
     "pp_tc_gemm_nt_workspace": (_l, [_l, _i, _i, _i]),
     "pp_tc_gemm_nt_ws": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp]),

@@ -638,16 +638,15 @@ class _Conv1x1(torch.autograd.Function):
         return dx, (dw.view(ctx.w_shape) if dw is not None else None), db
 
 
-def _conv1x1_backward(x, w2, dy, need_x, need_w, need_b, dx_acc=None):
-    """dx, dw, db of the 1x1 convolution; dx_acc: a tensor the data gradient is ADDED to (pp_conv1x1_bwd_acc) and returned."""
+def _conv1x1_backward(x, w2, dy, need_x, need_w, need_b):
+    """dx, dw, db of the 1x1 convolution (pp_conv1x1_bwd; the three gradients are independent launches)."""
     dy = _f32(dy, "grad_out")
     B, Cin = x.shape[:2]
     P = x[0, 0].numel()
     Cout = w2.shape[0]
     L = _cabi.lib()
-    bwd = L.pp_conv1x1_bwd_acc if dx_acc is not None else L.pp_conv1x1_bwd
-    dx = dx_acc if dx_acc is not None else (torch.empty_like(x) if need_x else None)
-    need_x = need_x or dx_acc is not None
+    bwd = L.pp_conv1x1_bwd
+    dx = torch.empty_like(x) if need_x else None
     dw = torch.empty_like(w2) if need_w else None
     db = torch.empty((Cout,), device=x.device, dtype=torch.float32) if need_b else None
     ws = torch.empty((L.pp_conv1x1_bwd_workspace(B, Cin, Cout, P),), device=x.device, dtype=torch.uint8)
@@ -686,9 +685,8 @@ def conv1x1(x, weight, bias=None):
 
 class _FeatProp(torch.autograd.Function):
     """PixPro.featprop with its value transform (contrast/models/PixPro.py:339-363 [+ F.normalize, :380]) as ONE autograd
-    node: forward = pp_conv1x1_fwd -> pp_ppm_fwd; backward = pp_ppm_bwd -> pp_conv1x1_bwd(_acc): at P >= 128 the data gradient
-    is added to the similarity-branch gradient in the contraction's epilogue, at small grids by one in-place add.  Same kernels
-    and bits as ppm(feat, conv1x1(feat, w, b)), one node of graph bookkeeping less."""
+    node: forward = pp_conv1x1_fwd -> pp_ppm_fwd; backward = pp_ppm_bwd -> pp_conv1x1_bwd, the two gradients of `feat` joined by
+    one in-place add.  Same kernels and bits as ppm(feat, conv1x1(feat, w, b)), one node of graph bookkeeping less."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -732,14 +730,12 @@ class _FeatProp(torch.autograd.Function):
             _cabi.check(L.pp_ppm_bwd(_ptr(feat), _ptr(val), _ptr(out), _ptr(g), _ptr(saved), B, C, P, gamma, cv, final_norm,
                                      _ptr(d_feat), _ptr(d_val), _ptr(ws), _stream()), "pp_ppm_bwd")
         need_w, need_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        if P >= 128 and P % 4 == 0 and C % 4 == 0:
-            # TMA-fed route: the epilogue adds into d_feat with 16-byte read-modify-writes (free next to the contraction)
-            _, dw, db = _conv1x1_backward(feat, w2, d_val, True, need_w, need_b, dx_acc=d_feat)
-        else:
-            # thread-staged route (7x7): its epilogue owns 16 joint indices of one channel per thread, a strided scalar
-            # read-modify-write that costs the launch 16 us (31 -> 47 us measured) — one element-wise add is cheaper
-            dx, dw, db = _conv1x1_backward(feat, w2, d_val, True, need_w, need_b)
-            d_feat.add_(dx)
+        # the two gradients of `feat` (similarity branch, value transform) meet in one in-place add.  Adding inside the conv's
+        # epilogue instead (read-modify-write) was built and measured: 31 -> 47 us at 7x7 (strided scalar accesses of the
+        # thread-staged kernel) and 72 -> 153 us at 28x28 (a dependent global load per epilogue group of the TMA-fed kernel);
+        # the separate element-wise pass costs 4 / 20 us.
+        dx, dw, db = _conv1x1_backward(feat, w2, d_val, True, need_w, need_b)
+        d_feat.add_(dx)
         return d_feat, (dw.view(ctx.w_shape) if dw is not None else None), db, None, None, None
 
 

@@ -207,7 +207,7 @@ def test_featprop_golden(ops, tag, conv_impl):
 
 @pytest.mark.parametrize("B,G", [(6, 7), (3, 14), (2, 28)])
 def test_featprop_fused_node_equals_two_nodes(ops, synth, B, G):
-    """ops.featprop (one autograd node, pp_conv1x1_bwd_acc) against ops.ppm(feat, ops.conv1x1(feat, w, b)): same kernels,
+    """ops.featprop (one autograd node) against ops.ppm(feat, ops.conv1x1(feat, w, b)): same kernels,
     the only difference is where the two gradients of `feat` are added — outputs and gradients must be the same bits."""
     g = torch.Generator(device="cpu").manual_seed(G)
     C = 256
