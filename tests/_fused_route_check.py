@@ -33,7 +33,10 @@ assert names == want, (mode, names)
 assert sha(ff.cpu().numpy()) == str(g["flow_fwd_sha"]) and sha(fb.cpu().numpy()) == str(g["flow_bwd_sha"])
 assert np.array_equal(mf.cpu().numpy(), unpack_mask(g["mask_fwd"], mf.shape))
 assert np.array_equal(mb.cpu().numpy(), unpack_mask(g["mask_bwd"], mb.shape))
-for B, h, w, mag, seed in ((3, 12, 16, 6.0, 5), (2, 18, 24, 1.0, 6), (2, 24, 16, 30.0, 7), (5, 90, 160, 1.5, 8)):
+import random
+rng = random.Random(2026)
+fuzz = [(rng.randint(1, 3), 6 * rng.randint(1, 5), 8 * rng.randint(1, 4), rng.choice([0.5, 3.0, 10.0, 40.0]), 100 + i) for i in range(8)]
+for B, h, w, mag, seed in [(3, 12, 16, 6.0, 5), (2, 18, 24, 1.0, 6), (2, 24, 16, 30.0, 7), (5, 90, 160, 1.5, 8)] + fuzz:
     f, b = synth.flow_fields(B, 1, h=h, w=w, seed=seed, magnitude=mag)
     ref = orc.flow_stage(f.numpy(), b.numpy(), flow_up=True)
     got = ops.flow_stage(f.cuda(), b.cuda())
