@@ -1,4 +1,5 @@
 #!/bin/bash
+# historical: PIXPRO_B200_CONVPAD selected the padded TMA route of the 7x7 value transform, removed after these measurements (profiles/r02_w_convpad_step.txt)
 mkdir -p gpurun_out
 for pad in 1 0; do
   PIXPRO_B200_CONVPAD=$pad timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r02_w_pad$pad.json 2> gpurun_out/r02_w_pad$pad.err

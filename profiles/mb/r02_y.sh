@@ -1,4 +1,5 @@
 #!/bin/bash
+# historical: PIXPRO_B200_PPMREG=0 still selects the two-pass kernels
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_model.py tests/test_gpu_reference_goldens.py -x -q -k "ppm or featprop or model or pixpro" 2>&1 | tail -6 > gpurun_out/r02_y_tests.log; cat gpurun_out/r02_y_tests.log
 for reg in 1 0; do
